@@ -1,0 +1,191 @@
+/*
+ * pegasus_b200.h — C ABI of libpegasus_b200.so: the B200-native (sm_100a) replacement for the
+ * compose -> forward-rasterize hot path of meyerls/PEGASUS.
+ *
+ * Every entry point takes plain pointers and sizes (device pointers unless stated), never a torch
+ * type, and enqueues work on the caller's CUDA stream.  The library allocates no device memory and
+ * keeps no state except a thread-local error string: inputs, outputs and the workspace belong to
+ * the caller (the reference's binding hands the extension three grow-only torch buffers the same way).
+ *
+ * Which reference interface each entry replaces (paths relative to /root/reference,
+ * GSP = submodules/gaussian-splatting-pegasus):
+ *
+ *   pg_rasterize_forward   <- diff_gaussian_rasterization._C.rasterize_gaussians, i.e. what
+ *                             GaussianRasterizer.forward() calls (GSP/gaussian_renderer/__init__.py:14,
+ *                             :38-53 settings, :87-95 call, 3-tuple return color/radii/depth).  The
+ *                             extension source is the un-vendored submodule
+ *                             meyerls/depth-diff-gaussian-rasterization @ 0062df97 (absent from the tree).
+ *   pg_mark_visible        <- GaussianRasterizer.markVisible (upstream API; unused by PEGASUS).
+ *   pg_pose_apply          <- GaussianModel.apply_transformation (src/gs/gaussian_model.py:579-582:
+ *                             apply_transformation_on_xyz :494-497, apply_rotation_on_splats :499-505,
+ *                             apply_rotation_on_sh :507-546) + merge_gaussians (:584-591) as called from
+ *                             PegasusSetup.apply_transformation_on_gs (src/gs/pegasus_setup.py:195-207)
+ *                             and the per-frame merge in pegasus.py:255-264.
+ *   pg_render_composed     <- the K+3 passes of src/gs/render.py:14-129 (render_rgb_and_depth,
+ *                             render_silhouette_mask, render_visib_mask,
+ *                             render_semanticsegmentation_mask) driven by pegasus.py:295-332.
+ *   pg_export_binning      <- test/debug only: the reference keeps these in its binningBuffer /
+ *                             imgBuffer (point_list_keys, point_list, ranges).
+ *   pg_pack_frame          <- the host-side conversions in pegasus.py:340-358 (rgb*255 -> u8,
+ *                             depth*1000 -> u16) done on the device before the D2H copy.
+ */
+#ifndef PEGASUS_B200_H
+#define PEGASUS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PG_OK 0
+#define PG_ERR_INVALID (-1)   /* bad argument */
+#define PG_ERR_CUDA (-2)      /* a CUDA call failed; see pg_last_error() */
+#define PG_ERR_WORKSPACE (-3) /* workspace smaller than pg_workspace_bytes() */
+#define PG_ERR_CAPACITY (-4)  /* pair capacity exceeded (reported by pg_read_status) */
+
+#define PG_MAX_OBJECTS 32
+#define PG_MAX_COLORS 64
+
+typedef void* pg_stream_t; /* cudaStream_t */
+
+/* Mirrors GaussianRasterizationSettings (GSP/gaussian_renderer/__init__.py:38-51).
+ * bg/viewmatrix/projmatrix/campos are DEVICE pointers, exactly as the reference passes CUDA tensors;
+ * viewmatrix/projmatrix are the contiguous transposed 4x4 (flat index [4*col+row]). */
+typedef struct pg_raster_settings {
+    int32_t image_height;
+    int32_t image_width;
+    float tanfovx;
+    float tanfovy;
+    const float* bg;         /* [3] */
+    float scale_modifier;
+    const float* viewmatrix; /* [16] */
+    const float* projmatrix; /* [16] */
+    int32_t sh_degree;
+    const float* campos;     /* [3] */
+    int32_t prefiltered;
+    int32_t debug;           /* !=0: synchronise and check after every stage */
+} pg_raster_settings;
+
+/* Arguments of GaussianRasterizer.forward (GSP/gaussian_renderer/__init__.py:87-95). */
+typedef struct pg_gaussians {
+    int32_t P;
+    const float* means3D;        /* [P,3] */
+    const float* shs;            /* [P,M,3] or NULL */
+    int32_t sh_coeffs;           /* M (16 for max degree 3) */
+    const float* colors_precomp; /* [P,3] or NULL */
+    const float* opacities;      /* [P] (the reference's [P,1]) */
+    const float* scales;         /* [P,3] or NULL */
+    const float* rotations;      /* [P,4] (w,x,y,z), unit, or NULL */
+    const float* cov3D_precomp;  /* [P,6] or NULL */
+} pg_gaussians;
+
+/* The reference's 3-tuple plus optional side channels (NULL = not wanted). */
+typedef struct pg_raster_outputs {
+    float* color;        /* [3,H,W] */
+    int32_t* radii;      /* [P] */
+    float* depth;        /* [1,H,W] */
+    float* final_T;      /* [H,W] optional: transmittance; alpha = 1 - final_T */
+    uint32_t* n_contrib; /* [H,W] optional */
+} pg_raster_outputs;
+
+/* Objects of a composed scene: Gaussians [first[k], first[k+1]) belong to object k, everything
+ * below first[0] is environment (merge order of src/gs/gaussian_model.py:584-591). HOST data. */
+typedef struct pg_object_table {
+    int32_t num_objects;                    /* K <= PG_MAX_OBJECTS */
+    int32_t first[PG_MAX_OBJECTS + 1];
+    int32_t color_index[PG_MAX_OBJECTS];    /* bullet_id - 1: row of `colors` (src/gs/render.py:46) */
+    int32_t num_colors;                     /* rows of the colour set (<= PG_MAX_COLORS) */
+    float colors[PG_MAX_COLORS][3];         /* generate_colors() (src/utility/graphic_utils.py:40-60) */
+} pg_object_table;
+
+/* Outputs of one composed frame = what the reference's K+3 passes produce. NULL = skip. */
+typedef struct pg_frame_outputs {
+    float* color;        /* [3,H,W] RGB pass */
+    int32_t* radii;      /* [P] */
+    float* depth;        /* [1,H,W] */
+    float* final_T;      /* [H,W] optional */
+    float* seg_color;    /* [3,H,W] objects-only flat-colour render (visib / sem-seg pass), optional */
+    uint8_t* sem_seg;    /* [H,W,3] uint8(255*seg) (src/gs/render.py:129) */
+    uint8_t* visible;    /* [num_colors,H,W] 0/1 (src/gs/render.py:89-93) */
+    uint8_t* silhouette; /* [num_colors,H,W] 0/1 (src/gs/render.py:60-63) */
+} pg_frame_outputs;
+
+/* One rigid pose per object (412 bytes, all 4-byte fields): x' = R (x - pivot) + pivot + t; q' = q_R (x) normalize(q);
+ * SH bands l=1..3 multiplied by D1/D2/D3 (row-major). */
+typedef struct pg_pose {
+    float R[9];
+    float t[3];
+    float pivot[3];
+    float q[4];  /* (w,x,y,z) of R */
+    float D1[9];
+    float D2[25];
+    float D3[49];
+    int32_t rotate_sh; /* 0: copy canonical SH (what pegasus.py:262-263 ends up rendering) */
+} pg_pose;
+
+/* Canonical (un-posed) object clouds, concatenated in merge order. DEVICE pointers. */
+typedef struct pg_canonical {
+    int32_t n_total;
+    const float* xyz;           /* [n,3] */
+    const float* rotation;      /* [n,4] raw (w,x,y,z) */
+    const float* features_rest; /* [n,15,3] */
+} pg_canonical;
+
+/* Destination: the composed scene's rasterizer-input arrays. DEVICE pointers. */
+typedef struct pg_scene {
+    int32_t P;
+    float* means3D;   /* [P,3] */
+    float* rotations; /* [P,4] */
+    float* shs;       /* [P,16,3] */
+} pg_scene;
+
+typedef struct pg_status {
+    uint32_t num_rendered; /* R = number of (tile, Gaussian) pairs of the last forward */
+    uint32_t overflow;     /* !=0: R exceeded the workspace's pair capacity; outputs are invalid */
+    uint32_t num_visible;
+    uint32_t reserved;
+} pg_status;
+
+const char* pg_version(void);
+const char* pg_last_error(void);
+
+/* Bytes of workspace needed for P Gaussians, a WxH image and at most pair_capacity pairs. */
+size_t pg_workspace_bytes(int32_t P, int32_t width, int32_t height, uint64_t pair_capacity);
+
+int pg_rasterize_forward(const pg_raster_settings* settings, const pg_gaussians* g,
+                         const pg_raster_outputs* out, void* workspace, size_t workspace_bytes,
+                         uint64_t pair_capacity, pg_stream_t stream);
+
+int pg_render_composed(const pg_raster_settings* settings, const pg_gaussians* g,
+                       const pg_object_table* objects, const pg_frame_outputs* out, void* workspace,
+                       size_t workspace_bytes, uint64_t pair_capacity, pg_stream_t stream);
+
+/* Asynchronously copies the workspace's status block to host_status (pinned host memory). */
+int pg_read_status(const void* workspace, pg_status* host_status, pg_stream_t stream);
+
+int pg_mark_visible(int32_t P, const float* means3D, const float* viewmatrix, uint8_t* present,
+                    pg_stream_t stream);
+
+/* poses_dev is a DEVICE array of K pose packets (e.g. the NCCL receive buffer of the per-frame pose
+ * broadcast); object k's Gaussians [first[k], first[k+1]) of the canonical arrays are written to
+ * scene rows scene_offset + [first[k], first[k+1]). `first` is HOST data. */
+int pg_pose_apply(int32_t num_objects, const int32_t* first, const pg_pose* poses_dev,
+                  const pg_canonical* canon, int32_t scene_offset, const pg_scene* scene,
+                  pg_stream_t stream);
+
+/* Test/debug: rebuild the reference's sorted 64-bit keys, point list and tile ranges of the last
+ * forward that used `workspace`.  keys/point_list hold >= num_rendered entries. */
+int pg_export_binning(const void* workspace, int32_t P, int32_t width, int32_t height,
+                      uint64_t pair_capacity, uint64_t* keys, uint32_t* point_list,
+                      uint32_t* ranges /*[tiles,2]*/, pg_stream_t stream);
+
+/* rgb [3,H,W] f32 -> [H,W,3] u8 ; depth [1,H,W] f32 metres -> [H,W] u16 millimetres. */
+int pg_pack_frame(int32_t width, int32_t height, const float* color, const float* depth,
+                  uint8_t* rgb_u8, uint16_t* depth_u16, pg_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PEGASUS_B200_H */

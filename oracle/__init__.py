@@ -420,7 +420,8 @@ def render(cam, cloud, bg, sh_degree=3, scaling_modifier=1.0):
     tanfovy = math.tan(cam["FoVy"] * 0.5)
     W, H = int(cam["image_width"]), int(cam["image_height"])
     if P == 0:
-        color = np.broadcast_to(_f32(bg).reshape(3, 1, 1), (3, H, W)).copy()
+        # upstream skips the kernels when P == 0: the zero-initialised images come back as they are
+        color = np.zeros((3, H, W), np.float32)
         return dict(render=color, depth=np.zeros((1, H, W), np.float32), radii=np.zeros(0, np.int32),
                     final_T=np.ones((H, W), np.float32))
     out = rasterize_forward(xyz, opacity, cam["world_view_transform"], cam["full_proj_transform"],

@@ -1,0 +1,115 @@
+"""ctypes binding of libpegasus_b200.so (include/pegasus_b200.h).
+
+There is no CPU fallback: if the library is missing it is built with nvcc; if that fails, or a
+CUDA call fails, a RuntimeError is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from . import build as _build
+
+PG_MAX_OBJECTS = 32
+PG_MAX_COLORS = 64
+
+_f = C.c_void_p  # device pointers travel as integers
+
+
+class RasterSettings(C.Structure):
+    _fields_ = [("image_height", C.c_int32), ("image_width", C.c_int32), ("tanfovx", C.c_float),
+                ("tanfovy", C.c_float), ("bg", _f), ("scale_modifier", C.c_float), ("viewmatrix", _f),
+                ("projmatrix", _f), ("sh_degree", C.c_int32), ("campos", _f), ("prefiltered", C.c_int32),
+                ("debug", C.c_int32)]
+
+
+class Gaussians(C.Structure):
+    _fields_ = [("P", C.c_int32), ("means3D", _f), ("shs", _f), ("sh_coeffs", C.c_int32),
+                ("colors_precomp", _f), ("opacities", _f), ("scales", _f), ("rotations", _f),
+                ("cov3D_precomp", _f)]
+
+
+class RasterOutputs(C.Structure):
+    _fields_ = [("color", _f), ("radii", _f), ("depth", _f), ("final_T", _f), ("n_contrib", _f)]
+
+
+class ObjectTable(C.Structure):
+    _fields_ = [("num_objects", C.c_int32), ("first", C.c_int32 * (PG_MAX_OBJECTS + 1)),
+                ("color_index", C.c_int32 * PG_MAX_OBJECTS), ("num_colors", C.c_int32),
+                ("colors", (C.c_float * 3) * PG_MAX_COLORS)]
+
+
+class FrameOutputs(C.Structure):
+    _fields_ = [("color", _f), ("radii", _f), ("depth", _f), ("final_T", _f), ("seg_color", _f),
+                ("sem_seg", _f), ("visible", _f), ("silhouette", _f)]
+
+
+class Pose(C.Structure):
+    _fields_ = [("R", C.c_float * 9), ("t", C.c_float * 3), ("pivot", C.c_float * 3), ("q", C.c_float * 4),
+                ("D1", C.c_float * 9), ("D2", C.c_float * 25), ("D3", C.c_float * 49),
+                ("rotate_sh", C.c_int32)]
+
+
+POSE_WORDS = C.sizeof(Pose) // 4  # 103
+
+
+class Canonical(C.Structure):
+    _fields_ = [("n_total", C.c_int32), ("xyz", _f), ("rotation", _f), ("features_rest", _f)]
+
+
+class Scene(C.Structure):
+    _fields_ = [("P", C.c_int32), ("means3D", _f), ("rotations", _f), ("shs", _f)]
+
+
+class Status(C.Structure):
+    _fields_ = [("num_rendered", C.c_uint32), ("overflow", C.c_uint32), ("num_visible", C.c_uint32),
+                ("reserved", C.c_uint32)]
+
+
+EXPORTS = ["pg_version", "pg_last_error", "pg_workspace_bytes", "pg_rasterize_forward",
+           "pg_render_composed", "pg_read_status", "pg_mark_visible", "pg_pose_apply",
+           "pg_export_binning", "pg_pack_frame"]
+
+_LIB = None
+
+
+def lib_path() -> str:
+    return _build.OUT
+
+
+def load():
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = _build.OUT
+    if not os.path.exists(path):
+        path = _build.build()  # raises if nvcc is unavailable or compilation fails
+    L = C.CDLL(path)
+    L.pg_version.restype = C.c_char_p
+    L.pg_last_error.restype = C.c_char_p
+    L.pg_workspace_bytes.restype = C.c_size_t
+    L.pg_workspace_bytes.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_uint64]
+    L.pg_rasterize_forward.argtypes = [C.POINTER(RasterSettings), C.POINTER(Gaussians),
+                                       C.POINTER(RasterOutputs), C.c_void_p, C.c_size_t, C.c_uint64,
+                                       C.c_void_p]
+    L.pg_render_composed.argtypes = [C.POINTER(RasterSettings), C.POINTER(Gaussians), C.POINTER(ObjectTable),
+                                     C.POINTER(FrameOutputs), C.c_void_p, C.c_size_t, C.c_uint64, C.c_void_p]
+    L.pg_read_status.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.pg_mark_visible.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.pg_pose_apply.argtypes = [C.c_int32, C.POINTER(C.c_int32), C.c_void_p, C.POINTER(Canonical), C.c_int32,
+                                C.POINTER(Scene), C.c_void_p]
+    L.pg_export_binning.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_uint64, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_void_p]
+    L.pg_pack_frame.argtypes = [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                C.c_void_p]
+    for name in ("pg_rasterize_forward", "pg_render_composed", "pg_read_status", "pg_mark_visible",
+                 "pg_pose_apply", "pg_export_binning", "pg_pack_frame"):
+        getattr(L, name).restype = C.c_int
+    _LIB = L
+    return L
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().pg_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"{what} failed (code {rc}): {msg}")

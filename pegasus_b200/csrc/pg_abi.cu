@@ -1,0 +1,251 @@
+// pg_abi.cu — extern "C" entry points of libpegasus_b200.so (see include/pegasus_b200.h) and the
+// per-frame launch sequence:
+//
+//   memset(workspace head)                      clear counters, histograms, look-back status
+//   preprocess_kernel                           A.1-A.5, writes GeomRec / depth key / tile rect / radii
+//   hist_kernel + scan_rows_kernel              digit histograms of the depth keys (4 x 8 bit)
+//   onesweep_pass_kernel x4                     P Gaussians by depth (stable; values = index)
+//   emit_kernel                                 scan(tiles_touched) + (tile, index) pairs in depth order
+//   tile_scan_kernel                            ranges[tile] + digit bases of the tile sort
+//   onesweep_pass_kernel x2                     R pairs by tile id (stable)  => reference order
+//   composite_kernel | composite_masks_kernel   A.7 (+ fused K+3 passes)
+//
+// Nothing here synchronises with the host: R stays on the device (grids are sized by the pair
+// capacity and surplus CTAs exit), overflow is reported through pg_read_status.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "pg_common.cuh"
+
+namespace pg {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+struct CompArgs;
+struct PoseDev;
+
+int launch_preprocess(const pg_raster_settings* s, const pg_gaussians* g, const pg_object_table* objs,
+                      int32_t* radii, GeomRec* recs, ushort4* rect, uint32_t* dkey, Counters* counters,
+                      cudaStream_t stream);
+int launch_mark_visible(int P, const float* means, const float* view, uint8_t* present, cudaStream_t stream);
+int launch_hist(const uint32_t* keys, uint32_t n, int npass, uint32_t* hist, cudaStream_t stream);
+int launch_onesweep_pass(bool iota, bool write_keys, const uint32_t* keys_in, uint32_t* keys_out,
+                         const uint32_t* vals_in, uint32_t* vals_out, const uint32_t* n_ptr,
+                         uint32_t n_imm, uint32_t max_tiles, int begin_bit, int num_bits,
+                         const uint32_t* bin_base, uint32_t* status, uint32_t* ticket,
+                         cudaStream_t stream);
+int launch_emit(const uint32_t* sorted_dkey, const uint32_t* perm, const ushort4* rects, uint32_t P,
+                uint32_t gx, uint32_t* tkeys, uint32_t* tvals, uint32_t R_cap, uint32_t* status,
+                uint32_t* tile_count, uint32_t n_env, uint32_t* tile_obj_count, Counters* counters,
+                cudaStream_t stream);
+int launch_tile_scan(const uint32_t* tile_count, uint32_t tiles, int bits_lo, int bits_hi, uint2* ranges,
+                     uint32_t* bins, cudaStream_t stream);
+int launch_export_keys(const uint2* ranges, uint32_t tiles, const uint32_t* point_list, const GeomRec* recs,
+                       uint64_t* keys, uint32_t* point_list_out, uint32_t* ranges_out, cudaStream_t stream);
+int launch_pose(int K, const int32_t* first, const PoseDev* poses_dev, const pg_canonical* canon,
+                int scene_offset, const pg_scene* scene, cudaStream_t stream);
+int launch_pack(int W, int H, const float* color, const float* depth, uint8_t* rgb_u8, uint16_t* depth_u16,
+                cudaStream_t stream);
+int launch_composite_from_abi(const uint2* ranges, const uint32_t* point_list, const GeomRec* recs, int W,
+                              int H, const float* bg, const pg_raster_outputs* ro, const pg_frame_outputs* fo,
+                              const pg_object_table* objs, uint32_t n_env, const uint32_t* tile_obj_count,
+                              cudaStream_t stream);
+
+template <typename T>
+static inline T* at(void* base, size_t off) {
+    return reinterpret_cast<T*>(reinterpret_cast<char*>(base) + off);
+}
+
+static int check_common(const pg_raster_settings* s, const pg_gaussians* g, uint64_t pair_capacity) {
+    if (!s || !g) { set_error("null settings/gaussians"); return PG_ERR_INVALID; }
+    if (g->P < 0 || s->image_width <= 0 || s->image_height <= 0) { set_error("bad sizes"); return PG_ERR_INVALID; }
+    if ((g->shs == nullptr) == (g->colors_precomp == nullptr)) {
+        set_error("Please provide excatly one of either SHs or precomputed colors!");
+        return PG_ERR_INVALID;
+    }
+    bool has_sr = g->scales != nullptr && g->rotations != nullptr;
+    bool any_sr = g->scales != nullptr || g->rotations != nullptr;
+    if ((!has_sr && g->cov3D_precomp == nullptr) || (any_sr && g->cov3D_precomp != nullptr)) {
+        set_error("Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!");
+        return PG_ERR_INVALID;
+    }
+    if (g->shs && (s->sh_degree < 0 || s->sh_degree > 3 || g->sh_coeffs < (s->sh_degree + 1) * (s->sh_degree + 1))) {
+        set_error("sh_degree %d needs %d coefficients, got %d", s->sh_degree, (s->sh_degree + 1) * (s->sh_degree + 1), g->sh_coeffs);
+        return PG_ERR_INVALID;
+    }
+    if (pair_capacity == 0 || pair_capacity > (1ull << 30)) { set_error("pair_capacity must be in [1, 2^30]"); return PG_ERR_INVALID; }
+    uint32_t gx = (s->image_width + PG_TILE - 1) / PG_TILE, gy = (s->image_height + PG_TILE - 1) / PG_TILE;
+    if (gx > 65535 || gy > 65535 || (uint64_t)gx * gy > (1u << 16)) {
+        set_error("image too large: at most 65536 tiles of 16x16 are supported");
+        return PG_ERR_INVALID;
+    }
+    return PG_OK;
+}
+
+// everything up to (and including) the tile sort
+static int run_binning(const pg_raster_settings* s, const pg_gaussians* g, const pg_object_table* objs,
+                       int32_t* radii, void* ws, const Layout& L, uint64_t R_cap, cudaStream_t stream) {
+    const int P = g->P;
+    const int W = s->image_width, H = s->image_height;
+    const uint32_t gx = (W + PG_TILE - 1) / PG_TILE;
+    Counters* counters = at<Counters>(ws, L.counters);
+    PG_CUDA_CHECK(cudaMemsetAsync(at<char>(ws, L.zero_begin), 0, L.zero_end - L.zero_begin, stream));
+    int rc = launch_preprocess(s, g, objs, radii, at<GeomRec>(ws, L.recs), at<ushort4>(ws, L.rect),
+                               at<uint32_t>(ws, L.dkey_a), counters, stream);
+    if (rc) return rc;
+    if (s->debug) PG_CUDA_CHECK(cudaStreamSynchronize(stream));
+    // depth sort: a -> b -> a -> b -> a
+    uint32_t* hist = at<uint32_t>(ws, L.hist_depth);
+    rc = launch_hist(at<uint32_t>(ws, L.dkey_a), (uint32_t)P, 4, hist, stream);
+    if (rc) return rc;
+    uint32_t* ka = at<uint32_t>(ws, L.dkey_a); uint32_t* kb = at<uint32_t>(ws, L.dkey_b);
+    uint32_t* va = at<uint32_t>(ws, L.dval_a); uint32_t* vb = at<uint32_t>(ws, L.dval_b);
+    uint32_t* st = at<uint32_t>(ws, L.status_depth);
+    for (int p = 0; p < 4; ++p) {
+        rc = launch_onesweep_pass(p == 0, true, ka, kb, va, vb, nullptr, (uint32_t)P, L.tilesP, 8 * p, 8,
+                                  hist + p * RADIX, st + (size_t)p * L.tilesP * RADIX,
+                                  &counters->tile_counter[p], stream);
+        if (rc) return rc;
+        uint32_t* t = ka; ka = kb; kb = t;
+        t = va; va = vb; vb = t;
+    }
+    if (s->debug) PG_CUDA_CHECK(cudaStreamSynchronize(stream));
+    // after 4 passes the sorted keys/permutation are back in (dkey_a, dval_a) == (ka, va)
+    const uint32_t n_env = (objs && objs->num_objects > 0) ? (uint32_t)objs->first[0] : (uint32_t)P;
+    rc = launch_emit(ka, va, at<ushort4>(ws, L.rect), (uint32_t)P, gx, at<uint32_t>(ws, L.tkey_a),
+                     at<uint32_t>(ws, L.tval_a), (uint32_t)R_cap, at<uint32_t>(ws, L.status_emit),
+                     at<uint32_t>(ws, L.tile_count), n_env, at<uint32_t>(ws, L.tile_obj_count), counters, stream);
+    if (rc) return rc;
+    const int bits = tile_bits(L.tiles);
+    const int bits_lo = (bits + 1) / 2, bits_hi = bits - bits_lo;
+    rc = launch_tile_scan(at<uint32_t>(ws, L.tile_count), L.tiles, bits_lo, bits_hi, at<uint2>(ws, L.ranges),
+                          at<uint32_t>(ws, L.bins_tile), stream);
+    if (rc) return rc;
+    uint32_t* bins = at<uint32_t>(ws, L.bins_tile);
+    uint32_t* stt = at<uint32_t>(ws, L.status_tile);
+    const bool two = bits_hi > 0;
+    // pass lo: a -> b ; pass hi: b -> a (values only).  With a single pass the result lands in b.
+    rc = launch_onesweep_pass(false, two, at<uint32_t>(ws, L.tkey_a), at<uint32_t>(ws, L.tkey_b),
+                              at<uint32_t>(ws, L.tval_a), at<uint32_t>(ws, L.tval_b), &counters->sort_n, 0,
+                              L.tilesR, 0, bits_lo, bins, stt, &counters->tile_counter[5], stream);
+    if (rc) return rc;
+    if (two) {
+        rc = launch_onesweep_pass(false, false, at<uint32_t>(ws, L.tkey_b), at<uint32_t>(ws, L.tkey_a),
+                                  at<uint32_t>(ws, L.tval_b), at<uint32_t>(ws, L.tval_a), &counters->sort_n, 0,
+                                  L.tilesR, bits_lo, bits_hi, bins + RADIX, stt + (size_t)L.tilesR * RADIX,
+                                  &counters->tile_counter[6], stream);
+        if (rc) return rc;
+    }
+    if (s->debug) PG_CUDA_CHECK(cudaStreamSynchronize(stream));
+    return PG_OK;
+}
+
+static inline const uint32_t* sorted_point_list(const void* ws, const Layout& L) {
+    const int bits = tile_bits(L.tiles);
+    const bool two = bits - (bits + 1) / 2 > 0;
+    return reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(ws) + (two ? L.tval_a : L.tval_b));
+}
+
+}  // namespace pg
+
+using namespace pg;
+
+extern "C" {
+
+const char* pg_version(void) { return "pegasus_b200 0.1 (sm_100a)"; }
+const char* pg_last_error(void) { return g_err; }
+
+size_t pg_workspace_bytes(int32_t P, int32_t width, int32_t height, uint64_t pair_capacity) {
+    if (P < 0 || width <= 0 || height <= 0) return 0;
+    return make_layout(P, width, height, pair_capacity).total;
+}
+
+int pg_rasterize_forward(const pg_raster_settings* s, const pg_gaussians* g, const pg_raster_outputs* out,
+                         void* ws, size_t ws_bytes, uint64_t pair_capacity, pg_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int rc = check_common(s, g, pair_capacity);
+    if (rc) return rc;
+    if (!out || !out->color || !out->radii || !out->depth || !ws) { set_error("null output/workspace"); return PG_ERR_INVALID; }
+    Layout L = make_layout(g->P, s->image_width, s->image_height, pair_capacity);
+    if (ws_bytes < L.total) { set_error("workspace too small: %zu < %zu", ws_bytes, L.total); return PG_ERR_WORKSPACE; }
+    rc = run_binning(s, g, nullptr, out->radii, ws, L, pair_capacity, stream);
+    if (rc) return rc;
+    return launch_composite_from_abi(at<uint2>(ws, L.ranges), sorted_point_list(ws, L), at<GeomRec>(ws, L.recs),
+                                     s->image_width, s->image_height, s->bg, out, nullptr, nullptr,
+                                     (uint32_t)g->P, at<uint32_t>(ws, L.tile_obj_count), stream);
+}
+
+int pg_render_composed(const pg_raster_settings* s, const pg_gaussians* g, const pg_object_table* objs,
+                       const pg_frame_outputs* out, void* ws, size_t ws_bytes, uint64_t pair_capacity,
+                       pg_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int rc = check_common(s, g, pair_capacity);
+    if (rc) return rc;
+    if (!objs || !out || !out->color || !out->radii || !out->depth || !ws) { set_error("null argument"); return PG_ERR_INVALID; }
+    if (objs->num_objects < 0 || objs->num_objects > PG_MAX_OBJECTS || objs->num_colors < 0 || objs->num_colors > PG_MAX_COLORS) {
+        set_error("too many objects/colours"); return PG_ERR_INVALID;
+    }
+    for (int k = 0; k < objs->num_objects; ++k) {
+        if (objs->first[k] > objs->first[k + 1] || objs->first[k] < 0 || objs->first[k + 1] > g->P ||
+            objs->color_index[k] < 0 || objs->color_index[k] >= objs->num_colors) {
+            set_error("bad object table entry %d", k); return PG_ERR_INVALID;
+        }
+    }
+    Layout L = make_layout(g->P, s->image_width, s->image_height, pair_capacity);
+    if (ws_bytes < L.total) { set_error("workspace too small: %zu < %zu", ws_bytes, L.total); return PG_ERR_WORKSPACE; }
+    rc = run_binning(s, g, objs, out->radii, ws, L, pair_capacity, stream);
+    if (rc) return rc;
+    const uint32_t n_env = objs->num_objects > 0 ? (uint32_t)objs->first[0] : (uint32_t)g->P;
+    if (out->silhouette && objs->num_colors > 0)
+        PG_CUDA_CHECK(cudaMemsetAsync(out->silhouette, 0, (size_t)objs->num_colors * s->image_width * s->image_height, stream));
+    return launch_composite_from_abi(at<uint2>(ws, L.ranges), sorted_point_list(ws, L), at<GeomRec>(ws, L.recs),
+                                     s->image_width, s->image_height, s->bg, nullptr, out, objs, n_env,
+                                     at<uint32_t>(ws, L.tile_obj_count), stream);
+}
+
+int pg_read_status(const void* ws, pg_status* host_status, pg_stream_t stream) {
+    if (!ws || !host_status) { set_error("null argument"); return PG_ERR_INVALID; }
+    PG_CUDA_CHECK(cudaMemcpyAsync(host_status, ws, sizeof(pg_status), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    return PG_OK;
+}
+
+int pg_mark_visible(int32_t P, const float* means3D, const float* viewmatrix, uint8_t* present, pg_stream_t stream) {
+    if (P < 0 || !means3D || !viewmatrix || !present) { set_error("null argument"); return PG_ERR_INVALID; }
+    return launch_mark_visible(P, means3D, viewmatrix, present, (cudaStream_t)stream);
+}
+
+int pg_pose_apply(int32_t K, const int32_t* first, const pg_pose* poses_dev, const pg_canonical* canon,
+                  int32_t scene_offset, const pg_scene* scene, pg_stream_t stream) {
+    if (K < 0 || K > PG_MAX_OBJECTS || !first || !poses_dev || !canon || !scene) { set_error("bad argument"); return PG_ERR_INVALID; }
+    for (int k = 0; k < K; ++k)
+        if (first[k] > first[k + 1] || first[k] < 0 || first[k + 1] > canon->n_total || scene_offset + first[k + 1] > scene->P) {
+            set_error("object %d does not fit", k); return PG_ERR_INVALID;
+        }
+    return launch_pose(K, first, reinterpret_cast<const PoseDev*>(poses_dev), canon, scene_offset, scene, (cudaStream_t)stream);
+}
+
+int pg_export_binning(const void* ws, int32_t P, int32_t width, int32_t height, uint64_t pair_capacity,
+                      uint64_t* keys, uint32_t* point_list, uint32_t* ranges, pg_stream_t stream) {
+    if (!ws || !keys || !point_list || !ranges) { set_error("null argument"); return PG_ERR_INVALID; }
+    Layout L = make_layout(P, width, height, pair_capacity);
+    const char* b = reinterpret_cast<const char*>(ws);
+    return launch_export_keys(reinterpret_cast<const uint2*>(b + L.ranges), L.tiles, sorted_point_list(ws, L),
+                              reinterpret_cast<const GeomRec*>(b + L.recs), keys, point_list, ranges,
+                              (cudaStream_t)stream);
+}
+
+int pg_pack_frame(int32_t width, int32_t height, const float* color, const float* depth, uint8_t* rgb_u8,
+                  uint16_t* depth_u16, pg_stream_t stream) {
+    if (width <= 0 || height <= 0 || (rgb_u8 && !color) || (depth_u16 && !depth)) { set_error("bad argument"); return PG_ERR_INVALID; }
+    return launch_pack(width, height, color, depth, rgb_u8, depth_u16, (cudaStream_t)stream);
+}
+
+}  // extern "C"

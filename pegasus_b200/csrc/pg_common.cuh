@@ -1,0 +1,149 @@
+// pg_common.cuh — shared device helpers and the workspace layout of libpegasus_b200.so (sm_100a).
+//
+// Numerical contract: every float op on the result path is an explicit
+// round-to-nearest intrinsic (__fmul_rn / __fadd_rn / __fsub_rn / __fmaf_rn / __fdiv_rn / __fsqrt_rn)
+// in the order nvcc -fmad=true contracts the upstream rasterizer's expressions into, so results are
+// reproducible bit-for-bit by the CPU oracle and independent of compiler contraction decisions.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/pegasus_b200.h"
+
+#define PG_TILE 16
+#define PG_SM_COUNT 148
+
+namespace pg {
+
+// ---- explicit IEEE helpers -------------------------------------------------------------------
+__device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float fma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+__device__ __forceinline__ float div(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ float sqrt(float a) { return __fsqrt_rn(a); }
+
+// exp(x), x <= 0: Cody-Waite + degree-6 polynomial out of FMAs only (no MUFU), <= 1.3 ulp.
+// Same sequence as orc_expf in oracle/pegasus_oracle.c.
+__device__ __forceinline__ float expf_exact(float x) {
+    const float L2E = 1.44269502162933349609375f;
+    const float MAGIC = 12582912.0f;
+    const float LN2_HI = 0.693145751953125f;
+    const float LN2_LO = 1.428606765330187045e-06f;
+    if (x < -80.0f) return 0.0f;
+    float z = fma(x, L2E, MAGIC);
+    float n = sub(z, MAGIC);
+    float r = fma(n, -LN2_HI, x);
+    r = fma(n, -LN2_LO, r);
+    float p = 0x1.6b5016p-10f;
+    p = fma(p, r, 0x1.126caep-7f);
+    p = fma(p, r, 0x1.55578ep-5f);
+    p = fma(p, r, 0x1.55540cp-3f);
+    p = fma(p, r, 0x1.fffffcp-2f);
+    p = fma(p, r, 1.0f);
+    p = fma(p, r, 1.0f);
+    int ni = __float_as_int(z) - 0x4B400000;
+    return __int_as_float(__float_as_int(p) + (ni << 23));
+}
+
+// ---- per-Gaussian record staged into shared memory by the compositing kernel (48 B) ----------
+struct __align__(16) GeomRec {
+    float4 a;  // x, y, conic.x, conic.y
+    float4 b;  // conic.z, opacity, depth, power_cut
+    float4 c;  // r, g, b, object id (as int bits; 0 = environment, k+1 = object k)
+};
+
+// ---- status block at the head of the workspace ------------------------------------------------
+struct Counters {
+    uint32_t num_rendered;   // R
+    uint32_t overflow;
+    uint32_t num_visible;
+    uint32_t sort_n;         // min(R, pair capacity): what the tile sort processes
+    uint32_t tile_counter[8];  // dynamic CTA-tile tickets: [0..3] depth-sort passes, [4] emit, [5..6] tile-sort passes
+};
+
+// Onesweep tile geometry
+constexpr int SORT_THREADS = 256;
+constexpr int SORT_IPT = 16;
+constexpr int SORT_TILE = SORT_THREADS * SORT_IPT;  // 4096 items per CTA-tile
+constexpr int RADIX = 256;
+constexpr int EMIT_CHUNK = 1024;
+
+struct Layout {
+    // all offsets in bytes from the workspace base; every region 256-B aligned
+    size_t counters;     // Counters
+    size_t zero_begin;   // [zero_begin, zero_end) is cleared at the start of every forward
+    size_t hist_depth;   // u32[4][256]  depth-sort digit histograms -> exclusive bases
+    size_t tile_count;   // u32[tiles]
+    size_t tile_obj_count; // u32[tiles] pairs whose Gaussian belongs to an object
+    size_t status_depth; // u32[4][tilesP][256]
+    size_t status_emit;  // u32[chunks]
+    size_t status_tile;  // u32[2][tilesR][256]
+    size_t zero_end;
+    size_t bins_tile;    // u32[2][256] exclusive bases of the two tile-sort passes
+    size_t ranges;       // uint2[tiles]
+    size_t recs;         // GeomRec[P]
+    size_t rect;         // ushort4[P]
+    size_t dkey_a, dkey_b, dval_a, dval_b;  // u32[P] depth-sort ping-pong
+    size_t tkey_a, tkey_b, tval_a, tval_b;  // u32[R_cap] tile-sort ping-pong
+    size_t total;
+    uint32_t tiles, tilesP, tilesR, chunks;
+};
+
+inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
+
+inline Layout make_layout(int P, int W, int H, uint64_t R_cap) {
+    Layout L;
+    uint32_t gx = (W + PG_TILE - 1) / PG_TILE, gy = (H + PG_TILE - 1) / PG_TILE;
+    L.tiles = gx * gy;
+    L.tilesP = (uint32_t)((P + SORT_TILE - 1) / SORT_TILE);
+    if (L.tilesP == 0) L.tilesP = 1;
+    L.tilesR = (uint32_t)((R_cap + SORT_TILE - 1) / SORT_TILE);
+    if (L.tilesR == 0) L.tilesR = 1;
+    L.chunks = (uint32_t)((P + EMIT_CHUNK - 1) / EMIT_CHUNK);
+    if (L.chunks == 0) L.chunks = 1;
+    size_t o = 0;
+    L.counters = o; o = align_up(o + sizeof(Counters));
+    L.zero_begin = L.counters;
+    L.hist_depth = o; o = align_up(o + 4 * RADIX * 4);
+    L.tile_count = o; o = align_up(o + (size_t)L.tiles * 4);
+    L.tile_obj_count = o; o = align_up(o + (size_t)L.tiles * 4);
+    L.status_depth = o; o = align_up(o + (size_t)4 * L.tilesP * RADIX * 4);
+    L.status_emit = o; o = align_up(o + (size_t)L.chunks * 4);
+    L.status_tile = o; o = align_up(o + (size_t)2 * L.tilesR * RADIX * 4);
+    L.zero_end = o;
+    L.bins_tile = o; o = align_up(o + 2 * RADIX * 4);
+    L.ranges = o; o = align_up(o + (size_t)L.tiles * 8);
+    L.recs = o; o = align_up(o + (size_t)P * sizeof(GeomRec));
+    L.rect = o; o = align_up(o + (size_t)P * 8);
+    L.dkey_a = o; o = align_up(o + (size_t)P * 4);
+    L.dkey_b = o; o = align_up(o + (size_t)P * 4);
+    L.dval_a = o; o = align_up(o + (size_t)P * 4);
+    L.dval_b = o; o = align_up(o + (size_t)P * 4);
+    L.tkey_a = o; o = align_up(o + (size_t)R_cap * 4);
+    L.tkey_b = o; o = align_up(o + (size_t)R_cap * 4);
+    L.tval_a = o; o = align_up(o + (size_t)R_cap * 4);
+    L.tval_b = o; o = align_up(o + (size_t)R_cap * 4);
+    L.total = o;
+    return L;
+}
+
+// number of bits needed to index `tiles` tile ids (>= 1)
+inline int tile_bits(uint32_t tiles) {
+    int b = 1;
+    while ((1u << b) < tiles) ++b;
+    return b;
+}
+
+void set_error(const char* fmt, ...);
+
+}  // namespace pg
+
+#define PG_CUDA_CHECK(expr)                                                              \
+    do {                                                                                 \
+        cudaError_t _e = (expr);                                                         \
+        if (_e != cudaSuccess) {                                                         \
+            pg::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return PG_ERR_CUDA;                                                          \
+        }                                                                                \
+    } while (0)

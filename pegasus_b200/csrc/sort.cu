@@ -1,0 +1,209 @@
+// sort.cu — hand-written onesweep LSD radix sort (u32 keys, u32 values, 8-bit digits, single pass per
+// digit with decoupled look-back) used twice per frame:
+//   1. P Gaussians by depth bits (4 passes, values = Gaussian index generated on the fly), and
+//   2. R (tile, Gaussian) pairs by tile id (2 passes of ceil(b/2)/floor(b/2) bits, b = bits of the
+//      tile count) — the pairs are emitted in depth order, so a stable sort on the tile id alone
+//      yields exactly the order the reference gets from sorting 64-bit tile|depth keys.
+// HBM-bound: each pass reads 8 B and writes 8 B per item (the last tile pass writes values only).
+//
+// CTA-tile = 256 threads x 16 items, warp-blocked so that rank order == memory order (stability).
+// Ranking: per-warp digit counters in shared memory + __match_any_sync multisplit.
+// CTA-tiles take tickets from an atomic counter, so a tile only ever waits on tiles that already run.
+#include "pg_common.cuh"
+
+namespace pg {
+
+constexpr uint32_t FLAG_AGG = 1u << 30;
+constexpr uint32_t FLAG_INCL = 2u << 30;
+constexpr uint32_t VAL_MASK = (1u << 30) - 1;
+
+// ---- digit histograms of up to 4 passes in one read of the keys --------------------------------
+__global__ void __launch_bounds__(256) hist_kernel(const uint32_t* __restrict__ keys, uint32_t n,
+                                                    int npass, uint32_t* __restrict__ hist /*[npass][256]*/) {
+    __shared__ uint32_t s_h[4][RADIX];
+    for (int i = threadIdx.x; i < 4 * RADIX; i += blockDim.x) (&s_h[0][0])[i] = 0;
+    __syncthreads();
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        uint32_t k = keys[i];
+#pragma unroll
+        for (int p = 0; p < 4; ++p)
+            if (p < npass) atomicAdd(&s_h[p][(k >> (8 * p)) & 255], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < npass * RADIX; i += blockDim.x) {
+        uint32_t c = (&s_h[0][0])[i];
+        if (c) atomicAdd(&hist[i], c);
+    }
+}
+
+// exclusive scan of each 256-entry row, in place. One CTA of 256 threads per row.
+__global__ void __launch_bounds__(256) scan_rows_kernel(uint32_t* __restrict__ hist) {
+    __shared__ uint32_t s_w[8];
+    uint32_t* row = hist + blockIdx.x * RADIX;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint32_t v = row[tid], x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    if (lane == 31) s_w[warp] = x;
+    __syncthreads();
+    uint32_t base = 0;
+    for (int w = 0; w < warp; ++w) base += s_w[w];
+    row[tid] = base + x - v;
+}
+
+template <bool IOTA, bool WRITE_KEYS>
+__global__ void __launch_bounds__(SORT_THREADS)
+onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, uint32_t* __restrict__ keys_out,
+                     const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ vals_out,
+                     const uint32_t* __restrict__ n_ptr, uint32_t n_imm, int begin_bit, int num_bits,
+                     const uint32_t* __restrict__ bin_base, uint32_t* __restrict__ status,
+                     uint32_t* __restrict__ ticket) {
+    constexpr int WARPS = SORT_THREADS / 32;
+    __shared__ uint32_t s_warp_hist[WARPS][RADIX];
+    __shared__ uint32_t s_bin_start[RADIX];
+    __shared__ uint32_t s_gbase[RADIX];
+    __shared__ uint32_t s_keys[SORT_TILE];
+    __shared__ uint32_t s_vals[SORT_TILE];
+    __shared__ uint32_t s_scan[WARPS];
+    __shared__ uint32_t s_tile;
+
+    const uint32_t n = n_ptr ? *n_ptr : n_imm;
+    const uint32_t num_tiles = (n + SORT_TILE - 1) / SORT_TILE;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+    for (int i = tid; i < WARPS * RADIX; i += SORT_THREADS) (&s_warp_hist[0][0])[i] = 0;
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    if (tile >= num_tiles) return;
+    const uint32_t base = tile * SORT_TILE;
+    const uint32_t tile_n = min((uint32_t)SORT_TILE, n - base);
+    const uint32_t mask = (1u << num_bits) - 1u;
+
+    uint32_t keys[SORT_IPT], vals[SORT_IPT], ranks[SORT_IPT];
+    const uint32_t wbase = base + warp * (32 * SORT_IPT) + lane;
+#pragma unroll
+    for (int i = 0; i < SORT_IPT; ++i) {
+        uint32_t idx = wbase + i * 32;
+        bool valid = idx < n;
+        keys[i] = valid ? keys_in[idx] : 0xFFFFFFFFu;
+        if (IOTA) vals[i] = idx;
+        else vals[i] = valid ? vals_in[idx] : 0u;
+    }
+    const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll
+    for (int i = 0; i < SORT_IPT; ++i) {
+        uint32_t idx = wbase + i * 32;
+        uint32_t d = idx < n ? ((keys[i] >> begin_bit) & mask) : mask;
+        uint32_t peers = __match_any_sync(0xffffffffu, d);
+        int leader = __ffs(peers) - 1;
+        uint32_t prev = 0;
+        if (lane == leader) {
+            prev = s_warp_hist[warp][d];
+            s_warp_hist[warp][d] = prev + __popc(peers);
+        }
+        prev = __shfl_sync(0xffffffffu, prev, leader);
+        ranks[i] = prev + __popc(peers & lt);
+        __syncwarp();
+    }
+    __syncthreads();
+    // digit `tid`: exclusive scan over warps, CTA count
+    uint32_t cta_count = 0;
+    {
+#pragma unroll
+        for (int w = 0; w < WARPS; ++w) {
+            uint32_t c = s_warp_hist[w][tid];
+            s_warp_hist[w][tid] = cta_count;
+            cta_count += c;
+        }
+    }
+    // exclusive scan of cta_count over the 256 digits
+    {
+        uint32_t x = cta_count;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) s_scan[warp] = x;
+        __syncthreads();
+        uint32_t wb = 0;
+        for (int w = 0; w < warp; ++w) wb += s_scan[w];
+        s_bin_start[tid] = wb + x - cta_count;
+    }
+    // decoupled look-back, one digit per thread
+    if ((uint32_t)tid <= mask) {
+        const uint32_t pad = SORT_TILE - tile_n;
+        const uint32_t pub = cta_count - ((uint32_t)tid == mask ? pad : 0u);
+        volatile uint32_t* st = status + (size_t)tile * RADIX + tid;
+        uint32_t excl = 0;
+        if (tile == 0) {
+            *st = pub | FLAG_INCL;
+        } else {
+            *st = pub | FLAG_AGG;
+            int t = (int)tile - 1;
+            while (true) {
+                uint32_t s = *(volatile uint32_t*)(status + (size_t)t * RADIX + tid);
+                uint32_t f = s >> 30;
+                if (f == 0) continue;
+                excl += s & VAL_MASK;
+                if (f == 2) break;
+                --t;
+            }
+            *st = ((excl + pub) & VAL_MASK) | FLAG_INCL;
+        }
+        s_gbase[tid] = bin_base[tid] + excl - s_bin_start[tid];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < SORT_IPT; ++i) {
+        uint32_t idx = wbase + i * 32;
+        uint32_t d = idx < n ? ((keys[i] >> begin_bit) & mask) : mask;
+        uint32_t pos = s_bin_start[d] + s_warp_hist[warp][d] + ranks[i];
+        s_keys[pos] = keys[i];
+        s_vals[pos] = vals[i];
+    }
+    __syncthreads();
+    for (uint32_t j = tid; j < tile_n; j += SORT_THREADS) {
+        uint32_t k = s_keys[j];
+        uint32_t d = (k >> begin_bit) & mask;
+        uint32_t dst = s_gbase[d] + j;
+        if (WRITE_KEYS) keys_out[dst] = k;
+        vals_out[dst] = s_vals[j];
+    }
+}
+
+int launch_hist(const uint32_t* keys, uint32_t n, int npass, uint32_t* hist, cudaStream_t stream) {
+    if (n == 0) return PG_OK;
+    int blocks = (int)min((uint32_t)(PG_SM_COUNT * 8), (n + 255u) / 256u);
+    hist_kernel<<<blocks, 256, 0, stream>>>(keys, n, npass, hist);
+    PG_CUDA_CHECK(cudaGetLastError());
+    scan_rows_kernel<<<npass, 256, 0, stream>>>(hist);
+    PG_CUDA_CHECK(cudaGetLastError());
+    return PG_OK;
+}
+
+// One onesweep pass.  max_tiles bounds the grid (tiles beyond the device-side count exit at once).
+int launch_onesweep_pass(bool iota, bool write_keys, const uint32_t* keys_in, uint32_t* keys_out,
+                         const uint32_t* vals_in, uint32_t* vals_out, const uint32_t* n_ptr,
+                         uint32_t n_imm, uint32_t max_tiles, int begin_bit, int num_bits,
+                         const uint32_t* bin_base, uint32_t* status, uint32_t* ticket,
+                         cudaStream_t stream) {
+    if (max_tiles == 0) return PG_OK;
+    dim3 grid(max_tiles), block(SORT_THREADS);
+    if (iota && write_keys)
+        onesweep_pass_kernel<true, true><<<grid, block, 0, stream>>>(keys_in, keys_out, vals_in, vals_out, n_ptr, n_imm, begin_bit, num_bits, bin_base, status, ticket);
+    else if (!iota && write_keys)
+        onesweep_pass_kernel<false, true><<<grid, block, 0, stream>>>(keys_in, keys_out, vals_in, vals_out, n_ptr, n_imm, begin_bit, num_bits, bin_base, status, ticket);
+    else if (!iota && !write_keys)
+        onesweep_pass_kernel<false, false><<<grid, block, 0, stream>>>(keys_in, keys_out, vals_in, vals_out, n_ptr, n_imm, begin_bit, num_bits, bin_base, status, ticket);
+    else
+        onesweep_pass_kernel<true, false><<<grid, block, 0, stream>>>(keys_in, keys_out, vals_in, vals_out, n_ptr, n_imm, begin_bit, num_bits, bin_base, status, ticket);
+    PG_CUDA_CHECK(cudaGetLastError());
+    return PG_OK;
+}
+
+}  // namespace pg
