@@ -404,16 +404,20 @@ def _sigmoid(x):
     return (1.0 / (1.0 + np.exp(-x.astype(np.float32)))).astype(np.float32)
 
 
-def render(cam, cloud, bg, sh_degree=3, scaling_modifier=1.0):
+def render(cam, cloud, bg, sh_degree=3, scaling_modifier=1.0, activated=False):
     """``render()`` of GSP/gaussian_renderer/__init__.py:19-103 on a dict cloud holding raw
-    (pre-activation) parameters, as a trained PLY does."""
+    (pre-activation) parameters, as a trained PLY does.  activated=True: opacity / scaling / rotation
+    already went through sigmoid / exp / normalize (lets a test hand over the exact device values)."""
     xyz = _f32(cloud["xyz"])
     P = xyz.shape[0]
-    opacity = _sigmoid(_f32(cloud["opacity"]))
-    scales = np.exp(_f32(cloud["scaling"])).astype(np.float32)
-    rot = _f32(cloud["rotation"])
-    nrm = np.maximum(np.sqrt((rot * rot).sum(axis=1, keepdims=True)), 1e-12).astype(np.float32)
-    rot = (rot / nrm).astype(np.float32)
+    if activated:
+        opacity, scales, rot = _f32(cloud["opacity"]), _f32(cloud["scaling"]), _f32(cloud["rotation"])
+    else:
+        opacity = _sigmoid(_f32(cloud["opacity"]))
+        scales = np.exp(_f32(cloud["scaling"])).astype(np.float32)
+        rot = _f32(cloud["rotation"])
+        nrm = np.maximum(np.sqrt((rot * rot).sum(axis=1, keepdims=True)), 1e-12).astype(np.float32)
+        rot = (rot / nrm).astype(np.float32)
     shs = np.concatenate((_f32(cloud["features_dc"]).reshape(P, 1, 3),
                           _f32(cloud["features_rest"]).reshape(P, 15, 3)), axis=1)
     tanfovx = math.tan(cam["FoVx"] * 0.5)
@@ -445,7 +449,7 @@ def empty_like_env(env):
     return {k: env[k][:0] for k in CLOUD_KEYS}
 
 
-def render_frame_reference(cam, env, objects, color_set, bg, sh_degree=3):
+def render_frame_reference(cam, env, objects, color_set, bg, sh_degree=3, activated=False):
     """One reference frame = K+3 rasterizations (pegasus.py:254-332, src/gs/render.py:14-129).
 
     objects: dict bullet_id -> posed cloud (insertion order = merge order).
@@ -456,7 +460,7 @@ def render_frame_reference(cam, env, objects, color_set, bg, sh_degree=3):
     scene = {k: env[k] for k in CLOUD_KEYS}
     for oid, obj in objects.items():
         scene = merge_gaussians(scene, obj)
-    pkg = render(cam, scene, bg, sh_degree)
+    pkg = render(cam, scene, bg, sh_degree, activated=activated)
     rgb = pkg["render"].transpose(1, 2, 0)
     depth = pkg["depth"].transpose(1, 2, 0)
     n_col = color_set.shape[0]
@@ -465,14 +469,14 @@ def render_frame_reference(cam, env, objects, color_set, bg, sh_degree=3):
     for oid, obj in objects.items():
         c = color_set[oid - 1]
         sc = merge_gaussians(empty_like_env(env), semantic_object(obj, c))
-        img = render(cam, sc, bg, sh_degree)["render"].transpose(1, 2, 0)
+        img = render(cam, sc, bg, sh_degree, activated=activated)["render"].transpose(1, 2, 0)
         dist = np.linalg.norm(img - c, axis=2)
         sil[dist <= 0.1, oid - 1] = 1
     # visible masks + semantic segmentation: all objects, no environment (src/gs/render.py:68-129)
     sc = empty_like_env(env)
     for oid, obj in objects.items():
         sc = merge_gaussians(sc, semantic_object(obj, color_set[oid - 1]))
-    seg = render(cam, sc, bg, sh_degree)["render"].transpose(1, 2, 0)
+    seg = render(cam, sc, bg, sh_degree, activated=activated)["render"].transpose(1, 2, 0)
     vis = np.zeros((H, W, n_col))
     for ci, c in enumerate(color_set):
         dist = np.linalg.norm(seg - c, axis=2)

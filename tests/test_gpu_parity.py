@@ -294,15 +294,16 @@ def test_composed_frame_matches_reference_k_plus_3_passes():
     # reference side: the oracle's K+3 passes on the object clouds the kernel just posed (isolates the
     # rasterizer from pose-kernel rounding, which has its own test)
     torch.cuda.synchronize()
+    def rows(lo, hi):
+        return dict(xyz=sc.means3D[lo:hi].cpu().numpy(), features_dc=sc.shs[lo:hi, 0:1, :].cpu().numpy(),
+                    features_rest=sc.shs[lo:hi, 1:, :].cpu().numpy(), opacity=sc.opacity[lo:hi, None].cpu().numpy(),
+                    scaling=sc.scales[lo:hi].cpu().numpy(), rotation=sc.rotations[lo:hi].cpu().numpy())
+    env_act = rows(0, sc.n_env)
     posed = {}
     lo = sc.n_env
     for oid in sc.object_ids:
         n = objs[oid]["xyz"].shape[0]
-        o = dict(objs[oid])
-        o["xyz"] = sc.means3D[lo:lo + n].cpu().numpy()
-        o["rotation"] = sc.rotations[lo:lo + n].cpu().numpy()
-        o["features_rest"] = sc.shs[lo:lo + n, 1:, :].cpu().numpy()
-        posed[oid] = o
+        posed[oid] = rows(lo, lo + n)
         lo += n
     for c in synth.orbit_cameras(2, 640, 480, seed=3100):
         cam = Camera(c["R"], c["T"], c["FoVx"], c["FoVy"], c["W"], c["H"])
@@ -311,7 +312,7 @@ def test_composed_frame_matches_reference_k_plus_3_passes():
         ocam["world_view_transform"] = cam.world_view_transform.cpu().numpy()
         ocam["full_proj_transform"] = cam.full_proj_transform.cpu().numpy()
         ocam["camera_center"] = cam.camera_center.cpu().numpy()
-        ref = oracle.render_frame_reference(ocam, env, posed, colors, bg)
+        ref = oracle.render_frame_reference(ocam, env_act, posed, colors, bg, activated=True)
         out = sc.render(cam, torch.zeros(3, device="cuda"))
         np.testing.assert_array_equal(out["radii"].cpu().numpy(), ref["radii"])
         stats = _compare_frame(out, ref, colors, sc.object_ids)
