@@ -65,7 +65,7 @@ typedef struct pg_raster_settings {
     int32_t sh_degree;
     const float* campos;     /* [3] */
     int32_t prefiltered;
-    int32_t debug;           /* !=0: synchronise and check after every stage */
+    int32_t debug;           /* bit 0: synchronise after every stage; bit 1: collect compositing statistics */
 } pg_raster_settings;
 
 /* Arguments of GaussianRasterizer.forward (GSP/gaussian_renderer/__init__.py:87-95). */
@@ -180,6 +180,18 @@ int pg_pose_apply(int32_t num_objects, const int32_t* first, const pg_pose* pose
 int pg_export_binning(const void* workspace, int32_t P, int32_t width, int32_t height,
                       uint64_t pair_capacity, uint64_t* keys, uint32_t* point_list,
                       uint32_t* ranges /*[tiles,2]*/, pg_stream_t stream);
+
+/* ---- opt-in profiling used by bench.py / tests (no effect on results) ------------------------------
+ * Stage boundaries of one forward: 0 clear, 1 preprocess, 2 depth sort, 3 emit, 4 tile scan,
+ * 5 tile sort, 6 compositing.  pg_profile_enable(n) records CUDA events on the caller's stream for
+ * the next n forwards; pg_profile_read(i, ms) returns frame i's per-stage milliseconds. */
+#define PG_NUM_STAGES 7
+int pg_profile_enable(int32_t max_frames);
+int32_t pg_profile_frames(void);
+int pg_profile_read(int32_t frame, float* stage_ms /*[PG_NUM_STAGES]*/);
+uint64_t pg_launch_count(void); /* kernels this library has launched in this process */
+/* settings.debug bit 1: {pairs evaluated, pairs reaching exp, pairs blended, 0} of the last forward */
+int pg_read_stats(const void* workspace, uint64_t* host_stats4, pg_stream_t stream);
 
 /* rgb [3,H,W] f32 -> [H,W,3] u8 ; depth [1,H,W] f32 metres -> [H,W] u16 millimetres. */
 int pg_pack_frame(int32_t width, int32_t height, const float* color, const float* depth,

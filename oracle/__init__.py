@@ -157,12 +157,29 @@ def composite(pre, bins, bg, W, H):
     return dict(color=color, depth=depth, final_T=final_T, n_contrib=n_contrib)
 
 
+def clip_to_tile_rows(pre, row0, row1):
+    """Restrict the tile rectangles of a preprocess result to tile rows [row0,row1) (bench sampling)."""
+    r = pre["rect"]
+    r[:, 1] = np.maximum(r[:, 1], row0)
+    r[:, 3] = np.minimum(r[:, 3], row1)
+    h = np.maximum(r[:, 3] - r[:, 1], 0)
+    tt = (np.maximum(r[:, 2] - r[:, 0], 0) * h).astype(np.uint32)
+    tt[pre["radii"] <= 0] = 0
+    pre["tiles_touched"][:] = tt
+    pre["radii"][tt == 0] = 0
+    r[tt == 0] = 0
+
+
 def rasterize_forward(means3D, opacities, viewmatrix, projmatrix, campos, bg, W, H, tanfovx,
                       tanfovy, sh_degree=3, shs=None, colors_precomp=None, scales=None,
-                      rotations=None, cov3D_precomp=None, scale_modifier=1.0):
-    """Full forward; returns every intermediate the parity tests compare."""
+                      rotations=None, cov3D_precomp=None, scale_modifier=1.0, band=None):
+    """Full forward; returns every intermediate the parity tests compare.
+    band=(row0,row1): bench sampling only — bin and composite tile rows [row0,row1) (other tiles
+    stay background); the per-Gaussian stage still runs on every Gaussian."""
     pre = preprocess(means3D, opacities, viewmatrix, projmatrix, campos, W, H, tanfovx, tanfovy,
                      sh_degree, shs, colors_precomp, scales, rotations, cov3D_precomp, scale_modifier)
+    if band is not None:
+        clip_to_tile_rows(pre, band[0], band[1])
     bins = binning(pre, W, H)
     img = composite(pre, bins, bg, W, H)
     out = {}
@@ -404,7 +421,7 @@ def _sigmoid(x):
     return (1.0 / (1.0 + np.exp(-x.astype(np.float32)))).astype(np.float32)
 
 
-def render(cam, cloud, bg, sh_degree=3, scaling_modifier=1.0, activated=False):
+def render(cam, cloud, bg, sh_degree=3, scaling_modifier=1.0, activated=False, band=None):
     """``render()`` of GSP/gaussian_renderer/__init__.py:19-103 on a dict cloud holding raw
     (pre-activation) parameters, as a trained PLY does.  activated=True: opacity / scaling / rotation
     already went through sigmoid / exp / normalize (lets a test hand over the exact device values)."""
@@ -430,7 +447,7 @@ def render(cam, cloud, bg, sh_degree=3, scaling_modifier=1.0, activated=False):
                     final_T=np.ones((H, W), np.float32))
     out = rasterize_forward(xyz, opacity, cam["world_view_transform"], cam["full_proj_transform"],
                             cam["camera_center"], bg, W, H, tanfovx, tanfovy, sh_degree, shs=shs,
-                            scales=scales, rotations=rot, scale_modifier=scaling_modifier)
+                            scales=scales, rotations=rot, scale_modifier=scaling_modifier, band=band)
     return dict(render=out["color"], depth=out["depth"], radii=out["radii"], final_T=out["final_T"],
                 raw=out)
 
@@ -449,7 +466,7 @@ def empty_like_env(env):
     return {k: env[k][:0] for k in CLOUD_KEYS}
 
 
-def render_frame_reference(cam, env, objects, color_set, bg, sh_degree=3, activated=False):
+def render_frame_reference(cam, env, objects, color_set, bg, sh_degree=3, activated=False, band=None):
     """One reference frame = K+3 rasterizations (pegasus.py:254-332, src/gs/render.py:14-129).
 
     objects: dict bullet_id -> posed cloud (insertion order = merge order).
@@ -460,7 +477,7 @@ def render_frame_reference(cam, env, objects, color_set, bg, sh_degree=3, activa
     scene = {k: env[k] for k in CLOUD_KEYS}
     for oid, obj in objects.items():
         scene = merge_gaussians(scene, obj)
-    pkg = render(cam, scene, bg, sh_degree, activated=activated)
+    pkg = render(cam, scene, bg, sh_degree, activated=activated, band=band)
     rgb = pkg["render"].transpose(1, 2, 0)
     depth = pkg["depth"].transpose(1, 2, 0)
     n_col = color_set.shape[0]
@@ -469,14 +486,14 @@ def render_frame_reference(cam, env, objects, color_set, bg, sh_degree=3, activa
     for oid, obj in objects.items():
         c = color_set[oid - 1]
         sc = merge_gaussians(empty_like_env(env), semantic_object(obj, c))
-        img = render(cam, sc, bg, sh_degree, activated=activated)["render"].transpose(1, 2, 0)
+        img = render(cam, sc, bg, sh_degree, activated=activated, band=band)["render"].transpose(1, 2, 0)
         dist = np.linalg.norm(img - c, axis=2)
         sil[dist <= 0.1, oid - 1] = 1
     # visible masks + semantic segmentation: all objects, no environment (src/gs/render.py:68-129)
     sc = empty_like_env(env)
     for oid, obj in objects.items():
         sc = merge_gaussians(sc, semantic_object(obj, color_set[oid - 1]))
-    seg = render(cam, sc, bg, sh_degree, activated=activated)["render"].transpose(1, 2, 0)
+    seg = render(cam, sc, bg, sh_degree, activated=activated, band=band)["render"].transpose(1, 2, 0)
     vis = np.zeros((H, W, n_col))
     for ci, c in enumerate(color_set):
         dist = np.linalg.norm(seg - c, axis=2)
@@ -484,3 +501,67 @@ def render_frame_reference(cam, env, objects, color_set, bg, sh_degree=3, activa
     sem = (np.ascontiguousarray(seg) * 255).astype("uint8")
     return dict(rgb=rgb, depth=depth, silhouette=sil, visible=vis, sem_seg=sem, seg_float=seg,
                 radii=pkg["radii"], raw=pkg.get("raw"))
+
+
+# --------------------------------------------------------------------------------------------
+# Bench support: the K+3 passes split into a per-frame fixed part (compose, activate, per-Gaussian
+# stage of every pass) and a per-band part (binning + compositing + mask tests of tile rows).
+# --------------------------------------------------------------------------------------------
+def _prepare(cam, cloud, sh_degree=3):
+    xyz = _f32(cloud["xyz"])
+    P = xyz.shape[0]
+    opacity = _sigmoid(_f32(cloud["opacity"]))
+    scales = np.exp(_f32(cloud["scaling"])).astype(np.float32)
+    rot = _f32(cloud["rotation"])
+    rot = (rot / np.maximum(np.sqrt((rot * rot).sum(axis=1, keepdims=True)), 1e-12)).astype(np.float32)
+    shs = np.concatenate((_f32(cloud["features_dc"]).reshape(P, 1, 3),
+                          _f32(cloud["features_rest"]).reshape(P, 15, 3)), axis=1)
+    W, H = int(cam["image_width"]), int(cam["image_height"])
+    return preprocess(xyz, opacity, cam["world_view_transform"], cam["full_proj_transform"], cam["camera_center"],
+                      W, H, math.tan(cam["FoVx"] * 0.5), math.tan(cam["FoVy"] * 0.5), sh_degree, shs=shs,
+                      scales=scales, rotations=rot)
+
+
+def _finish(pre, bg, W, H, band):
+    p = dict(pre)
+    for k in ("rect", "tiles_touched", "radii"):
+        p[k] = pre[k].copy()
+    if band is not None:
+        clip_to_tile_rows(p, band[0], band[1])
+    bins = binning(p, W, H)
+    return composite(p, bins, bg, W, H)
+
+
+def frame_reference_split(cam, env, objects, color_set, bg, bands, sh_degree=3):
+    """Same passes as render_frame_reference; returns (seconds of the fixed part, [seconds per band])."""
+    import time
+    W, H = int(cam["image_width"]), int(cam["image_height"])
+    t0 = time.perf_counter()
+    scene = {k: env[k] for k in CLOUD_KEYS}
+    for oid, obj in objects.items():
+        scene = merge_gaussians(scene, obj)
+    passes = [("rgb", _prepare(cam, scene, sh_degree), None)]
+    for oid, obj in objects.items():
+        c = color_set[oid - 1]
+        passes.append(("sil", _prepare(cam, merge_gaussians(empty_like_env(env), semantic_object(obj, c)), sh_degree), c))
+    for name in ("vis", "sem"):  # the reference renders the objects-only scene twice (src/gs/render.py:86,118)
+        sc = empty_like_env(env)
+        for oid, obj in objects.items():
+            sc = merge_gaussians(sc, semantic_object(obj, color_set[oid - 1]))
+        passes.append((name, _prepare(cam, sc, sh_degree), None))
+    t_fixed = time.perf_counter() - t0
+    t_bands = []
+    for band in bands:
+        t0 = time.perf_counter()
+        y0, y1 = band[0] * 16, min(H, band[1] * 16)
+        for name, pre, c in passes:
+            img = _finish(pre, bg, W, H, band)["color"][:, y0:y1, :].transpose(1, 2, 0)
+            if name == "sil":
+                _ = np.linalg.norm(img - c, axis=2) <= 0.1
+            elif name == "vis":
+                for cc in color_set:
+                    _ = np.linalg.norm(img - cc, axis=2) <= 0.1
+            elif name == "sem":
+                _ = (np.ascontiguousarray(img) * 255).astype("uint8")
+        t_bands.append(time.perf_counter() - t0)
+    return t_fixed, t_bands

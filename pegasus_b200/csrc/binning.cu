@@ -215,6 +215,7 @@ int launch_emit(const uint32_t* sorted_dkey, const uint32_t* perm, const ushort4
     if (chunks == 0) return PG_OK;
     emit_kernel<<<chunks, 256, 0, stream>>>(sorted_dkey, perm, rects, P, gx, tkeys, tvals, R_cap, status,
                                             tile_count, n_env, tile_obj_count, counters);
+    count_launch(1);
     PG_CUDA_CHECK(cudaGetLastError());
     return PG_OK;
 }
@@ -222,6 +223,7 @@ int launch_emit(const uint32_t* sorted_dkey, const uint32_t* perm, const ushort4
 int launch_tile_scan(const uint32_t* tile_count, uint32_t tiles, int bits_lo, int bits_hi, uint2* ranges,
                      uint32_t* bins, cudaStream_t stream) {
     tile_scan_kernel<<<1, 1024, 0, stream>>>(tile_count, tiles, bits_lo, bits_hi, ranges, bins);
+    count_launch(1);
     PG_CUDA_CHECK(cudaGetLastError());
     return PG_OK;
 }
@@ -229,6 +231,7 @@ int launch_tile_scan(const uint32_t* tile_count, uint32_t tiles, int bits_lo, in
 int launch_export_keys(const uint2* ranges, uint32_t tiles, const uint32_t* point_list, const GeomRec* recs,
                        uint64_t* keys, uint32_t* point_list_out, uint32_t* ranges_out, cudaStream_t stream) {
     export_keys_kernel<<<tiles, 128, 0, stream>>>(ranges, tiles, point_list, recs, keys, point_list_out, ranges_out);
+    count_launch(1);
     PG_CUDA_CHECK(cudaGetLastError());
     return PG_OK;
 }

@@ -73,10 +73,14 @@ struct CompArgs {
     uint8_t* sem_seg;
     uint8_t* visible;
     uint8_t* silhouette;
+    unsigned long long* stats;  // non-null: count pairs evaluated / exp'd / blended
 };
 
 // alpha of one (pixel, Gaussian) pair; returns false when the pair is skipped (A.7 `continue`s)
-__device__ __forceinline__ bool pair_alpha(const float4 A, const float4 B, float pfx, float pfy, float& alpha) {
+template <bool STATS>
+__device__ __forceinline__ bool pair_alpha(const float4 A, const float4 B, float pfx, float pfy, float& alpha,
+                                           uint32_t& n_eval, uint32_t& n_exp) {
+    if (STATS) ++n_eval;
     float dx = sub(A.x, pfx), dy = sub(A.y, pfy);
     float u = mul(A.z, dx);
     float v = mul(B.x, dy);
@@ -86,10 +90,26 @@ __device__ __forceinline__ bool pair_alpha(const float4 A, const float4 B, float
     float power = fma(s, -0.5f, -bxy);
     if (power > 0.0f) return false;
     if (power < B.w) return false;  // alpha < 1/255 guaranteed (B.w = -5.55 when opacity <= 1)
+    if (STATS) ++n_exp;
     alpha = fminf(0.99f, mul(B.y, expf_exact(power)));
     return !(alpha < 1.0f / 255.0f);
 }
 
+__device__ __forceinline__ void flush_stats(unsigned long long* stats, uint32_t n_eval, uint32_t n_exp, uint32_t n_blend) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        n_eval += __shfl_xor_sync(0xffffffffu, n_eval, o);
+        n_exp += __shfl_xor_sync(0xffffffffu, n_exp, o);
+        n_blend += __shfl_xor_sync(0xffffffffu, n_blend, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&stats[0], (unsigned long long)n_eval);
+        atomicAdd(&stats[1], (unsigned long long)n_exp);
+        atomicAdd(&stats[2], (unsigned long long)n_blend);
+    }
+}
+
+template <bool STATS>
 __global__ void __launch_bounds__(256) composite_kernel(const CompArgs a) {
     __shared__ GeomRec s_rec[2][256];
     __shared__ __align__(8) uint64_t s_bar[2];
@@ -123,6 +143,7 @@ __global__ void __launch_bounds__(256) composite_kernel(const CompArgs a) {
 
     float T = 1.0f, C0 = 0.0f, C1 = 0.0f, C2 = 0.0f, D = 0.0f;
     uint32_t contributor = 0, last = 0;
+    uint32_t n_eval = 0, n_exp = 0, n_blend = 0;
     bool done = !inside;
     int issued = 0;
     if (rounds > 0) { issue(0); issued = 1; }
@@ -137,9 +158,10 @@ __global__ void __launch_bounds__(256) composite_kernel(const CompArgs a) {
             const float4 A = sr[j].a;
             const float4 B = sr[j].b;
             float alpha;
-            if (!pair_alpha(A, B, pfx, pfy, alpha)) continue;
+            if (!pair_alpha<STATS>(A, B, pfx, pfy, alpha, n_eval, n_exp)) continue;
             float test_T = mul(T, sub(1.0f, alpha));
             if (test_T < 0.0001f) { done = true; continue; }
+            if (STATS) ++n_blend;
             const float4 Cc = sr[j].c;
             C0 = fma(mul(Cc.x, alpha), T, C0);
             C1 = fma(mul(Cc.y, alpha), T, C1);
@@ -162,6 +184,7 @@ __global__ void __launch_bounds__(256) composite_kernel(const CompArgs a) {
         if (a.out_final_T) a.out_final_T[pix] = T;
         if (a.out_n_contrib) a.out_n_contrib[pix] = last;
     }
+    if (STATS) flush_stats(a.stats, n_eval, n_exp, n_blend);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -169,7 +192,7 @@ __global__ void __launch_bounds__(256) composite_kernel(const CompArgs a) {
 // Phase 1 walks every entry until the main chain of all 256 pixels has terminated; phase 2 scans
 // the remaining indices (4 B each), keeps object entries only and composites those.
 // ------------------------------------------------------------------------------------------------
-template <int KMAX>
+template <int KMAX, bool STATS>
 __global__ void __launch_bounds__(256) composite_masks_kernel(const CompArgs a) {
     __shared__ GeomRec s_rec[2][256];
     __shared__ __align__(8) uint64_t s_bar[2];
@@ -200,6 +223,7 @@ __global__ void __launch_bounds__(256) composite_masks_kernel(const CompArgs a) 
 #pragma unroll
     for (int k = 0; k < KMAX; ++k) Tk[k] = 1.0f;
     bool done_main = !inside, done_o = !inside;
+    uint32_t n_eval = 0, n_exp = 0, n_blend = 0;
     uint32_t done_k = inside ? 0u : 0xFFFFFFFFu;
 
     // blend one staged record into every live chain of this pixel
@@ -209,7 +233,8 @@ __global__ void __launch_bounds__(256) composite_masks_kernel(const CompArgs a) 
         const bool o_live = obj > 0 && !done_o;
         if (!(main_live || k_live || o_live)) return;
         float alpha;
-        if (!pair_alpha(rec.a, rec.b, pfx, pfy, alpha)) return;
+        if (!pair_alpha<STATS>(rec.a, rec.b, pfx, pfy, alpha, n_eval, n_exp)) return;
+        if (STATS) ++n_blend;
         const float om = sub(1.0f, alpha);
         if (main_live) {
             float test_T = mul(T, om);
@@ -366,20 +391,27 @@ __global__ void __launch_bounds__(256) composite_masks_kernel(const CompArgs a) 
             }
         }
     }
+    if (STATS) flush_stats(a.stats, n_eval, n_exp, n_blend);
 }
 
 int launch_composite(const CompArgs& a, int gy, bool masks, cudaStream_t stream) {
     dim3 grid(a.gx, gy), block(256);
+    const bool st = a.stats != nullptr;
     if (!masks) {
-        composite_kernel<<<grid, block, 0, stream>>>(a);
+        if (st) composite_kernel<true><<<grid, block, 0, stream>>>(a);
+        else composite_kernel<false><<<grid, block, 0, stream>>>(a);
     } else if (a.num_objects <= 8) {
-        composite_masks_kernel<8><<<grid, block, 0, stream>>>(a);
+        if (st) composite_masks_kernel<8, true><<<grid, block, 0, stream>>>(a);
+        else composite_masks_kernel<8, false><<<grid, block, 0, stream>>>(a);
     } else if (a.num_objects <= 16) {
-        composite_masks_kernel<16><<<grid, block, 0, stream>>>(a);
+        if (st) composite_masks_kernel<16, true><<<grid, block, 0, stream>>>(a);
+        else composite_masks_kernel<16, false><<<grid, block, 0, stream>>>(a);
     } else {
-        composite_masks_kernel<32><<<grid, block, 0, stream>>>(a);
+        if (st) composite_masks_kernel<32, true><<<grid, block, 0, stream>>>(a);
+        else composite_masks_kernel<32, false><<<grid, block, 0, stream>>>(a);
     }
     PG_CUDA_CHECK(cudaGetLastError());
+    count_launch(1);
     return PG_OK;
 }
 
@@ -391,9 +423,10 @@ namespace pg {
 int launch_composite_from_abi(const uint2* ranges, const uint32_t* point_list, const GeomRec* recs, int W,
                               int H, const float* bg, const pg_raster_outputs* ro, const pg_frame_outputs* fo,
                               const pg_object_table* objs, uint32_t n_env, const uint32_t* tile_obj_count,
-                              cudaStream_t stream) {
+                              unsigned long long* stats, cudaStream_t stream) {
     CompArgs a;
     memset(&a, 0, sizeof(a));
+    a.stats = stats;
     a.ranges = ranges; a.point_list = point_list; a.recs = recs;
     a.W = W; a.H = H; a.gx = (W + PG_TILE - 1) / PG_TILE;
     const int gy = (H + PG_TILE - 1) / PG_TILE;

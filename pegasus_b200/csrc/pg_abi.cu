@@ -12,9 +12,11 @@
 //
 // Nothing here synchronises with the host: R stays on the device (grids are sized by the pair
 // capacity and surplus CTAs exit), overflow is reported through pg_read_status.
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <vector>
 
 #include "pg_common.cuh"
 
@@ -57,7 +59,27 @@ int launch_pack(int W, int H, const float* color, const float* depth, uint8_t* r
 int launch_composite_from_abi(const uint2* ranges, const uint32_t* point_list, const GeomRec* recs, int W,
                               int H, const float* bg, const pg_raster_outputs* ro, const pg_frame_outputs* fo,
                               const pg_object_table* objs, uint32_t n_env, const uint32_t* tile_obj_count,
-                              cudaStream_t stream);
+                              unsigned long long* stats, cudaStream_t stream);
+
+// ---- opt-in profiling (bench / tests): CUDA events at stage boundaries, launch counter ----------
+static std::atomic<unsigned long long> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+
+constexpr int kStageEvents = PG_NUM_STAGES + 1;
+static std::vector<cudaEvent_t> g_events;  // [max_frames][kStageEvents]
+static int g_prof_max = 0;
+static std::atomic<int> g_prof_frames{0};
+static thread_local int t_prof_frame = -1;  // slot of the forward in flight on this thread
+
+static void prof_begin_frame() {
+    t_prof_frame = -1;
+    if (g_prof_max == 0) return;
+    int f = g_prof_frames.fetch_add(1);
+    if (f < g_prof_max) t_prof_frame = f;
+}
+static void prof_mark(int stage_boundary, cudaStream_t stream) {
+    if (t_prof_frame >= 0) cudaEventRecord(g_events[(size_t)t_prof_frame * kStageEvents + stage_boundary], stream);
+}
 
 template <typename T>
 static inline T* at(void* base, size_t off) {
@@ -97,11 +119,15 @@ static int run_binning(const pg_raster_settings* s, const pg_gaussians* g, const
     const int W = s->image_width, H = s->image_height;
     const uint32_t gx = (W + PG_TILE - 1) / PG_TILE;
     Counters* counters = at<Counters>(ws, L.counters);
+    prof_begin_frame();
+    prof_mark(0, stream);
     PG_CUDA_CHECK(cudaMemsetAsync(at<char>(ws, L.zero_begin), 0, L.zero_end - L.zero_begin, stream));
+    prof_mark(1, stream);
     int rc = launch_preprocess(s, g, objs, radii, at<GeomRec>(ws, L.recs), at<ushort4>(ws, L.rect),
                                at<uint32_t>(ws, L.dkey_a), counters, stream);
     if (rc) return rc;
-    if (s->debug) PG_CUDA_CHECK(cudaStreamSynchronize(stream));
+    prof_mark(2, stream);
+    if (s->debug & 1) PG_CUDA_CHECK(cudaStreamSynchronize(stream));
     // depth sort: a -> b -> a -> b -> a
     uint32_t* hist = at<uint32_t>(ws, L.hist_depth);
     rc = launch_hist(at<uint32_t>(ws, L.dkey_a), (uint32_t)P, 4, hist, stream);
@@ -117,18 +143,21 @@ static int run_binning(const pg_raster_settings* s, const pg_gaussians* g, const
         uint32_t* t = ka; ka = kb; kb = t;
         t = va; va = vb; vb = t;
     }
-    if (s->debug) PG_CUDA_CHECK(cudaStreamSynchronize(stream));
+    prof_mark(3, stream);
+    if (s->debug & 1) PG_CUDA_CHECK(cudaStreamSynchronize(stream));
     // after 4 passes the sorted keys/permutation are back in (dkey_a, dval_a) == (ka, va)
     const uint32_t n_env = (objs && objs->num_objects > 0) ? (uint32_t)objs->first[0] : (uint32_t)P;
     rc = launch_emit(ka, va, at<ushort4>(ws, L.rect), (uint32_t)P, gx, at<uint32_t>(ws, L.tkey_a),
                      at<uint32_t>(ws, L.tval_a), (uint32_t)R_cap, at<uint32_t>(ws, L.status_emit),
                      at<uint32_t>(ws, L.tile_count), n_env, at<uint32_t>(ws, L.tile_obj_count), counters, stream);
     if (rc) return rc;
+    prof_mark(4, stream);
     const int bits = tile_bits(L.tiles);
     const int bits_lo = (bits + 1) / 2, bits_hi = bits - bits_lo;
     rc = launch_tile_scan(at<uint32_t>(ws, L.tile_count), L.tiles, bits_lo, bits_hi, at<uint2>(ws, L.ranges),
                           at<uint32_t>(ws, L.bins_tile), stream);
     if (rc) return rc;
+    prof_mark(5, stream);
     uint32_t* bins = at<uint32_t>(ws, L.bins_tile);
     uint32_t* stt = at<uint32_t>(ws, L.status_tile);
     const bool two = bits_hi > 0;
@@ -144,7 +173,8 @@ static int run_binning(const pg_raster_settings* s, const pg_gaussians* g, const
                                   &counters->tile_counter[6], stream);
         if (rc) return rc;
     }
-    if (s->debug) PG_CUDA_CHECK(cudaStreamSynchronize(stream));
+    prof_mark(6, stream);
+    if (s->debug & 1) PG_CUDA_CHECK(cudaStreamSynchronize(stream));
     return PG_OK;
 }
 
@@ -178,9 +208,12 @@ int pg_rasterize_forward(const pg_raster_settings* s, const pg_gaussians* g, con
     if (ws_bytes < L.total) { set_error("workspace too small: %zu < %zu", ws_bytes, L.total); return PG_ERR_WORKSPACE; }
     rc = run_binning(s, g, nullptr, out->radii, ws, L, pair_capacity, stream);
     if (rc) return rc;
-    return launch_composite_from_abi(at<uint2>(ws, L.ranges), sorted_point_list(ws, L), at<GeomRec>(ws, L.recs),
-                                     s->image_width, s->image_height, s->bg, out, nullptr, nullptr,
-                                     (uint32_t)g->P, at<uint32_t>(ws, L.tile_obj_count), stream);
+    rc = launch_composite_from_abi(at<uint2>(ws, L.ranges), sorted_point_list(ws, L), at<GeomRec>(ws, L.recs),
+                                   s->image_width, s->image_height, s->bg, out, nullptr, nullptr,
+                                   (uint32_t)g->P, at<uint32_t>(ws, L.tile_obj_count),
+                                   (s->debug & 2) ? at<Counters>(ws, L.counters)->stats : nullptr, stream);
+    prof_mark(7, stream);
+    return rc;
 }
 
 int pg_render_composed(const pg_raster_settings* s, const pg_gaussians* g, const pg_object_table* objs,
@@ -206,9 +239,12 @@ int pg_render_composed(const pg_raster_settings* s, const pg_gaussians* g, const
     const uint32_t n_env = objs->num_objects > 0 ? (uint32_t)objs->first[0] : (uint32_t)g->P;
     if (out->silhouette && objs->num_colors > 0)
         PG_CUDA_CHECK(cudaMemsetAsync(out->silhouette, 0, (size_t)objs->num_colors * s->image_width * s->image_height, stream));
-    return launch_composite_from_abi(at<uint2>(ws, L.ranges), sorted_point_list(ws, L), at<GeomRec>(ws, L.recs),
-                                     s->image_width, s->image_height, s->bg, nullptr, out, objs, n_env,
-                                     at<uint32_t>(ws, L.tile_obj_count), stream);
+    rc = launch_composite_from_abi(at<uint2>(ws, L.ranges), sorted_point_list(ws, L), at<GeomRec>(ws, L.recs),
+                                   s->image_width, s->image_height, s->bg, nullptr, out, objs, n_env,
+                                   at<uint32_t>(ws, L.tile_obj_count),
+                                   (s->debug & 2) ? at<Counters>(ws, L.counters)->stats : nullptr, stream);
+    prof_mark(7, stream);
+    return rc;
 }
 
 int pg_read_status(const void* ws, pg_status* host_status, pg_stream_t stream) {
@@ -240,6 +276,37 @@ int pg_export_binning(const void* ws, int32_t P, int32_t width, int32_t height, 
     return launch_export_keys(reinterpret_cast<const uint2*>(b + L.ranges), L.tiles, sorted_point_list(ws, L),
                               reinterpret_cast<const GeomRec*>(b + L.recs), keys, point_list, ranges,
                               (cudaStream_t)stream);
+}
+
+int pg_read_stats(const void* ws, uint64_t* host_stats4, pg_stream_t stream) {
+    if (!ws || !host_stats4) { set_error("null argument"); return PG_ERR_INVALID; }
+    const char* src = reinterpret_cast<const char*>(ws) + offsetof(Counters, stats);
+    PG_CUDA_CHECK(cudaMemcpyAsync(host_stats4, src, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    return PG_OK;
+}
+
+uint64_t pg_launch_count(void) { return (uint64_t)g_launches.load(); }
+
+int pg_profile_enable(int32_t max_frames) {
+    for (cudaEvent_t e : g_events) cudaEventDestroy(e);
+    g_events.clear();
+    g_prof_max = 0;
+    g_prof_frames.store(0);
+    if (max_frames <= 0) return PG_OK;
+    g_events.resize((size_t)max_frames * kStageEvents);
+    for (auto& e : g_events) PG_CUDA_CHECK(cudaEventCreate(&e));
+    g_prof_max = max_frames;
+    return PG_OK;
+}
+
+int32_t pg_profile_frames(void) { int f = g_prof_frames.load(); return f < g_prof_max ? f : g_prof_max; }
+
+int pg_profile_read(int32_t frame, float* stage_ms) {
+    if (frame < 0 || frame >= pg_profile_frames() || !stage_ms) { set_error("bad profile frame"); return PG_ERR_INVALID; }
+    cudaEvent_t* ev = &g_events[(size_t)frame * kStageEvents];
+    PG_CUDA_CHECK(cudaEventSynchronize(ev[PG_NUM_STAGES]));
+    for (int i = 0; i < PG_NUM_STAGES; ++i) PG_CUDA_CHECK(cudaEventElapsedTime(&stage_ms[i], ev[i], ev[i + 1]));
+    return PG_OK;
 }
 
 int pg_pack_frame(int32_t width, int32_t height, const float* color, const float* depth, uint8_t* rgb_u8,

@@ -60,6 +60,7 @@ struct Counters {
     uint32_t num_visible;
     uint32_t sort_n;         // min(R, pair capacity): what the tile sort processes
     uint32_t tile_counter[8];  // dynamic CTA-tile tickets: [0..3] depth-sort passes, [4] emit, [5..6] tile-sort passes
+    unsigned long long stats[4];  // debug&2: pairs evaluated, pairs reaching exp, pairs blended (all chains), spare
 };
 
 // Onesweep tile geometry
@@ -136,6 +137,7 @@ inline int tile_bits(uint32_t tiles) {
 }
 
 void set_error(const char* fmt, ...);
+void count_launch(int n);
 
 }  // namespace pg
 

@@ -171,6 +171,7 @@ int launch_pose(int K, const int32_t* first, const PoseDev* poses_dev, const pg_
     }
     dim3 grid((n_max + 255) / 256, K);
     pose_kernel<<<grid, 256, smem, stream>>>(a);
+    count_launch(1);
     PG_CUDA_CHECK(cudaGetLastError());
     return PG_OK;
 }
@@ -202,6 +203,7 @@ int launch_pack(int W, int H, const float* color, const float* depth, uint8_t* r
     size_t HW = (size_t)W * H;
     if (HW == 0) return PG_OK;
     pack_kernel<<<(unsigned)((HW + 255) / 256), 256, 0, stream>>>(W, H, color, depth, rgb_u8, depth_u16);
+    count_launch(1);
     PG_CUDA_CHECK(cudaGetLastError());
     return PG_OK;
 }

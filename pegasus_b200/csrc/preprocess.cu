@@ -280,6 +280,7 @@ int launch_preprocess(const pg_raster_settings* s, const pg_gaussians* g, const 
     a.radii = radii; a.recs = recs; a.rect = rect; a.dkey = dkey; a.counters = counters;
     if (a.P == 0) return PG_OK;
     preprocess_kernel<<<(a.P + 255) / 256, 256, 0, stream>>>(a);
+    count_launch(1);
     PG_CUDA_CHECK(cudaGetLastError());
     return PG_OK;
 }
@@ -287,6 +288,7 @@ int launch_preprocess(const pg_raster_settings* s, const pg_gaussians* g, const 
 int launch_mark_visible(int P, const float* means, const float* view, uint8_t* present, cudaStream_t stream) {
     if (P == 0) return PG_OK;
     mark_visible_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, means, view, present);
+    count_launch(1);
     PG_CUDA_CHECK(cudaGetLastError());
     return PG_OK;
 }

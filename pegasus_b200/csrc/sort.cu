@@ -182,6 +182,7 @@ int launch_hist(const uint32_t* keys, uint32_t n, int npass, uint32_t* hist, cud
     hist_kernel<<<blocks, 256, 0, stream>>>(keys, n, npass, hist);
     PG_CUDA_CHECK(cudaGetLastError());
     scan_rows_kernel<<<npass, 256, 0, stream>>>(hist);
+    count_launch(2);
     PG_CUDA_CHECK(cudaGetLastError());
     return PG_OK;
 }
@@ -203,6 +204,7 @@ int launch_onesweep_pass(bool iota, bool write_keys, const uint32_t* keys_in, ui
     else
         onesweep_pass_kernel<true, false><<<grid, block, 0, stream>>>(keys_in, keys_out, vals_in, vals_out, n_ptr, n_imm, begin_bit, num_bits, bin_base, status, ticket);
     PG_CUDA_CHECK(cudaGetLastError());
+    count_launch(1);
     return PG_OK;
 }
 

@@ -105,7 +105,7 @@ def make_settings_struct(rs: GaussianRasterizationSettings, device, keep: list) 
     s.sh_degree = int(rs.sh_degree)
     s.campos = cam.data_ptr()
     s.prefiltered = int(bool(rs.prefiltered))
-    s.debug = int(bool(rs.debug))
+    s.debug = int(rs.debug)  # bit 0: sync after every stage, bit 1: collect compositing statistics
     return s
 
 

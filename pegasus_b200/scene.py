@@ -171,7 +171,7 @@ class ComposedScene:
         return out
 
     def render(self, cam, bg: torch.Tensor, masks: bool = True, out: Optional[Dict] = None, sh_degree: int = 3,
-               sync_check: bool = True, pair_capacity: Optional[int] = None) -> Dict[str, torch.Tensor]:
+               sync_check: bool = True, pair_capacity: Optional[int] = None, debug: int = 0) -> Dict[str, torch.Tensor]:
         """One frame: RGB + depth (+ seg render, sem-seg, visible and silhouette masks when
         masks=True) — everything the reference's K+3 passes produce (src/gs/render.py:14-129)."""
         L = _lib.load()
@@ -180,7 +180,7 @@ class ComposedScene:
             out = self.alloc_outputs(W, H, masks)
         keep = []
         with torch.cuda.device(self.device):
-            s = make_settings_struct(self.settings_for(cam, bg, sh_degree), self.device, keep)
+            s = make_settings_struct(self.settings_for(cam, bg, sh_degree, debug=debug), self.device, keep)
             g = _lib.Gaussians(self.P, self.means3D.data_ptr(), self.shs.data_ptr(), 16, None,
                                self.opacity.data_ptr(), self.scales.data_ptr(), self.rotations.data_ptr(), None)
             fo = _lib.FrameOutputs(out["color"].data_ptr(), out["radii"].data_ptr(), out["depth"].data_ptr(),
@@ -219,6 +219,17 @@ class ComposedScene:
                 _PAIR_CAPACITY_HINT[(W, H)] = cap
             out["pair_capacity"] = cap
         return out
+
+    def read_stats(self) -> Dict[str, int]:
+        """Compositing statistics of the last render(debug=2); synchronises."""
+        L = _lib.load()
+        ws = workspace_for(self.device)
+        host = torch.zeros(4, dtype=torch.int64).pin_memory()
+        stream = torch.cuda.current_stream(self.device)
+        _lib.check(L.pg_read_stats(C.c_void_p(ws.buf.data_ptr()), C.c_void_p(host.data_ptr()),
+                                   C.c_void_p(stream.cuda_stream)), "pg_read_stats")
+        stream.synchronize()
+        return dict(pairs_evaluated=int(host[0]), pairs_exp=int(host[1]), pairs_blended=int(host[2]))
 
     def read_status(self) -> Dict[str, int]:
         """Status of the last (possibly still running) render on this device; synchronises."""
