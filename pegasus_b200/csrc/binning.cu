@@ -15,13 +15,16 @@ constexpr uint32_t E_VAL_MASK = (1u << 30) - 1;
 
 __global__ void __launch_bounds__(256)
 emit_kernel(const uint32_t* __restrict__ sorted_dkey, const uint32_t* __restrict__ perm,
-            const ushort4* __restrict__ rects, uint32_t P, uint32_t gx, uint32_t* __restrict__ tkeys,
+            const ushort4* __restrict__ rects, const GeomRec* __restrict__ recs, uint32_t P, uint32_t gx,
+            int W, int H, uint32_t* __restrict__ tkeys,
             uint32_t* __restrict__ tvals, uint32_t R_cap, uint32_t* __restrict__ status,
             uint32_t* __restrict__ tile_count, uint32_t n_env, uint32_t* __restrict__ tile_obj_count,
             Counters* __restrict__ counters) {
     __shared__ uint32_t s_g[EMIT_CHUNK];
     __shared__ ushort4 s_rect[EMIT_CHUNK];
     __shared__ uint32_t s_off[EMIT_CHUNK];
+    __shared__ float4 s_ga[EMIT_CHUNK];  // x, y, conic.x, conic.y
+    __shared__ float2 s_gb[EMIT_CHUNK];  // conic.z, cut
     __shared__ uint32_t s_scan[8];
     __shared__ uint32_t s_chunk, s_base;
 
@@ -43,6 +46,9 @@ emit_kernel(const uint32_t* __restrict__ sorted_dkey, const uint32_t* __restrict
         if (s < P && sorted_dkey[s] != 0xFFFFFFFFu) {
             g = perm[s];
             r = rects[g];
+            const float4 ra = recs[g].a, rb = recs[g].b;
+            s_ga[tid * 4 + j] = ra;
+            s_gb[tid * 4 + j] = make_float2(rb.x, rb.w);
         }
         tt[j] = (uint32_t)(r.z - r.x) * (uint32_t)(r.w - r.y);
         s_g[tid * 4 + j] = g;
@@ -110,19 +116,27 @@ emit_kernel(const uint32_t* __restrict__ sorted_dkey, const uint32_t* __restrict
         if (n == 0) continue;
         const uint32_t g = s_g[q];
         const uint32_t off = s_off[q];
+        const float4 ga = s_ga[q];
+        const float2 gb = s_gb[q];
         const float inv = __frcp_rn((float)w_);
         for (uint32_t t = lane; t < n; t += 32) {
             uint32_t row = (uint32_t)__float2uint_rz(((float)t + 0.5f) * inv);
             int rem = (int)t - (int)(row * w_);
             if (rem < 0) { --row; rem += (int)w_; }
             else if (rem >= (int)w_) { ++row; rem -= (int)w_; }
-            const uint32_t tile = (r.y + row) * gx + r.x + (uint32_t)rem;
+            const uint32_t tyi = r.y + row, txi = r.x + (uint32_t)rem;
+            const uint32_t tile = tyi * gx + txi;
             const uint32_t dst = off + t;
             if (dst < R_cap) {
+                // can this Gaussian reach alpha >= 1/255 at any pixel centre of the tile?
+                const float x0 = (float)(txi * PG_TILE), y0 = (float)(tyi * PG_TILE);
+                const float x1 = (float)min((int)(txi * PG_TILE + PG_TILE - 1), W - 1);
+                const float y1 = (float)min((int)(tyi * PG_TILE + PG_TILE - 1), H - 1);
+                const bool culled = block_culled(ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, x0, x1, y0, y1);
                 tkeys[dst] = tile;
-                tvals[dst] = g;
+                tvals[dst] = culled ? (g | PG_CULL_FLAG) : g;
                 atomicAdd(&tile_count[tile], 1u);
-                if (g >= n_env) atomicAdd(&tile_obj_count[tile], 1u);
+                if (g >= n_env && !culled) atomicAdd(&tile_obj_count[tile], 1u);
             }
         }
     }
@@ -201,19 +215,19 @@ __global__ void export_keys_kernel(const uint2* __restrict__ ranges, uint32_t ti
     uint2 r = ranges[tile];
     if (threadIdx.x == 0) { ranges_out[2 * tile] = r.x; ranges_out[2 * tile + 1] = r.y; }
     for (uint32_t i = r.x + threadIdx.x; i < r.y; i += blockDim.x) {
-        uint32_t g = point_list[i];
+        uint32_t g = point_list[i] & ~PG_CULL_FLAG;
         keys[i] = ((uint64_t)tile << 32) | __float_as_uint(recs[g].b.z);
         point_list_out[i] = g;
     }
 }
 
-int launch_emit(const uint32_t* sorted_dkey, const uint32_t* perm, const ushort4* rects, uint32_t P,
-                uint32_t gx, uint32_t* tkeys, uint32_t* tvals, uint32_t R_cap, uint32_t* status,
+int launch_emit(const uint32_t* sorted_dkey, const uint32_t* perm, const ushort4* rects, const GeomRec* recs,
+                uint32_t P, uint32_t gx, int W, int H, uint32_t* tkeys, uint32_t* tvals, uint32_t R_cap, uint32_t* status,
                 uint32_t* tile_count, uint32_t n_env, uint32_t* tile_obj_count, Counters* counters,
                 cudaStream_t stream) {
     uint32_t chunks = (P + EMIT_CHUNK - 1) / EMIT_CHUNK;
     if (chunks == 0) return PG_OK;
-    emit_kernel<<<chunks, 256, 0, stream>>>(sorted_dkey, perm, rects, P, gx, tkeys, tvals, R_cap, status,
+    emit_kernel<<<chunks, 256, 0, stream>>>(sorted_dkey, perm, rects, recs, P, gx, W, H, tkeys, tvals, R_cap, status,
                                             tile_count, n_env, tile_obj_count, counters);
     count_launch(1);
     PG_CUDA_CHECK(cudaGetLastError());

@@ -1,19 +1,27 @@
-// composite.cu — per-tile front-to-back alpha compositing.
+// composite.cu — per-tile front-to-back alpha compositing, one CTA of 256
+// threads per 16x16 tile, each warp owning an 8x4 pixel block.
 //
-// One CTA (256 threads, 16x16 pixels; each warp owns an 8x4 pixel block) per tile.  The tile's sorted
-// Gaussian indices are read coalesced, and each index's 48-byte record {xy, conic, opacity, depth,
-// rgb, object id} is GATHERED into shared memory by its own TMA bulk copy (cp.async.bulk, 48 B,
-// completion on an mbarrier) into a 2-stage ring: batch r+1 lands while batch r is composited, no
-// registers or scoreboard slots are held by the loads.  All lanes then walk the staged batch with
-// broadcast 16-byte shared loads.
+// Walk of a tile's sorted list, per batch of up to 256 entries:
+//   1. ids are read coalesced (4 B each); entries the binning stage proved invisible for the whole
+//      tile (PG_CULL_FLAG) and, once every main chain has terminated, environment entries are
+//      dropped by a ballot compaction — they are never fetched;
+//   2. each surviving id's 48-byte record {xy, conic, opacity, depth, cut|object, rgb} is GATHERED
+//      into shared memory by its own TMA bulk copy (cp.async.bulk + mbarrier, 2-stage ring: batch
+//      k+1 lands while batch k is composited);
+//   3. every warp tests the batch against its 8x4 pixel block LANE-PARALLEL (lane l tests entry
+//      32c+l: exact minimum of the conic's quadratic form over the block vs. the entry's alpha<1/255
+//      cut) and ballots the hits into 8 masks;
+//   4. the warp walks only its hits, in list order, with broadcast 16-byte shared loads.
+// Culling is conservative (a margin covers float rounding), so every (pixel, Gaussian) pair that
+// the reference would blend is blended with the reference's operation order: results are unchanged.
 //
-// composite_kernel        : the reference's single pass -> color, depth (+ final_T, n_contrib).
-// composite_masks_kernel  : the reference's K+3 passes in one walk -> RGB + depth, the objects-only
-//                           flat-colour render (visible masks, sem-seg) and one transmittance chain
-//                           per object (silhouettes).  alpha is evaluated once per (pixel, Gaussian).
+// KMAX == 0 : the reference's single pass -> color, depth (+ final_T, n_contrib).
+// KMAX  > 0 : the reference's K+3 passes in one walk -> RGB + depth, the objects-only flat-colour
+//             render (visible masks, sem-seg) and one transmittance chain per object (silhouettes);
+//             alpha is evaluated once per (pixel, Gaussian).
 //
-// Compute-bound (FP32 pipe): ~12 FP32 ops to reject a pair, ~40 to blend one (exp is a 12-op FMA
-// polynomial so that results are bit-reproducible on the CPU oracle).
+// Issue-bound on the FP32/ALU pipes (exp is a 12-op FMA polynomial so that results are
+// bit-reproducible on the CPU oracle).
 #include <cstring>
 
 #include "pg_common.cuh"
@@ -30,18 +38,22 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                  : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
-        "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra WAIT_DONE;\n"
-        "bra WAIT_LOOP;\n"
-        "WAIT_DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
         : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    while (!mbar_try_wait(bar, parity)) __nanosleep(32);  // do not burn issue slots other warps need
 }
 // 1-D TMA bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
@@ -54,7 +66,7 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 
 struct CompArgs {
     const uint2* ranges;
-    const uint32_t* point_list;
+    const uint32_t* point_list;  // bit 31 = PG_CULL_FLAG
     const GeomRec* recs;
     int W, H, gx;
     const float* bg;
@@ -64,7 +76,7 @@ struct CompArgs {
     uint32_t* out_n_contrib;
     // masks
     uint32_t n_env;                 // Gaussian indices >= n_env belong to objects
-    const uint32_t* tile_obj_count; // [tiles] number of object pairs per tile
+    const uint32_t* tile_obj_count; // [tiles] number of un-culled object pairs per tile
     int num_objects, num_colors;
     float eff_color[PG_MAX_OBJECTS][3];  // colour the rasterizer produces for object k's flat SH
     float set_color[PG_MAX_COLORS][3];   // colour set the masks are tested against
@@ -89,7 +101,7 @@ __device__ __forceinline__ bool pair_alpha(const float4 A, const float4 B, float
     float bxy = mul(mul(A.w, dx), dy);
     float power = fma(s, -0.5f, -bxy);
     if (power > 0.0f) return false;
-    if (power < B.w) return false;  // alpha < 1/255 guaranteed (B.w = -5.55 when opacity <= 1)
+    if (power < B.w) return false;  // alpha < 1/255 guaranteed below the per-Gaussian cut
     if (STATS) ++n_exp;
     alpha = fminf(0.99f, mul(B.y, expf_exact(power)));
     return !(alpha < 1.0f / 255.0f);
@@ -109,246 +121,263 @@ __device__ __forceinline__ void flush_stats(unsigned long long* stats, uint32_t 
     }
 }
 
-template <bool STATS>
-__global__ void __launch_bounds__(256) composite_kernel(const CompArgs a) {
-    __shared__ GeomRec s_rec[2][256];
-    __shared__ __align__(8) uint64_t s_bar[2];
+// Warp-specialised: warp 8 is the PRODUCER (TMA-prefetches the tile's ids in 2 KB chunks, drops
+// culled / no-longer-needed entries by ballot compaction, gathers each surviving 48-byte record into
+// a 4-stage shared-memory ring with cp.async whose completion arrives on the stage's `full`
+// mbarrier); warps 0..7 are
+// CONSUMERS, each owning an 8x4 pixel block: wait `full`, cull the batch lane-parallel against the
+// block, walk the hits, arrive on `empty`.  No CTA-wide barrier in the steady state; a consumer whose
+// 32 pixels are finished keeps releasing stages, the producer stops when all 8 have finished.
+constexpr int COMP_STAGES = 4;
+constexpr int COMP_BATCH = 256;
+constexpr int COMP_THREADS = 288;
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int tile = blockIdx.y * a.gx + blockIdx.x;
-    const int px = blockIdx.x * PG_TILE + (warp & 1) * 8 + (lane & 7);
-    const int py = blockIdx.y * PG_TILE + (warp >> 1) * 4 + (lane >> 3);
-    const bool inside = px < a.W && py < a.H;
-    const float pfx = (float)px, pfy = (float)py;
-    const uint2 range = a.ranges[tile];
-    const int n = (int)(range.y - range.x);
-    const int rounds = (n + 255) >> 8;
+constexpr int COMP_IDCHUNK = 512;
+constexpr int COMP_PEND = 1024;
 
-    if (tid == 0) {
-        mbar_init(&s_bar[0], 1);
-        mbar_init(&s_bar[1], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
+struct CompSmem {
+    GeomRec rec[COMP_STAGES][COMP_BATCH];
+    uint32_t pos[COMP_STAGES][COMP_BATCH];  // 1-based list position of each staged entry (n_contrib)
+    uint32_t ids[2][COMP_IDCHUNK];          // producer: raw id chunks, TMA double buffer
+    uint32_t pend[COMP_PEND];               // producer: compacted ids not yet staged (circular)
+    uint32_t pendpos[COMP_PEND];
+    unsigned long long full[COMP_STAGES];
+    unsigned long long empty[COMP_STAGES];
+    unsigned long long idbar[2];
+    int cnt[COMP_STAGES];
+    int warps_done;       // consumers whose pixels are completely finished
+    int warps_main_done;  // consumers whose main chains are all finished
+};
 
-    auto issue = [&](int r) {
-        const int cnt = min(256, n - (r << 8));
-        uint64_t* bar = &s_bar[r & 1];
-        if (tid == 0) mbar_expect_tx(bar, (uint32_t)cnt * (uint32_t)sizeof(GeomRec));
-        if (tid < cnt) {
-            const uint32_t g = a.point_list[range.x + (r << 8) + tid];
-            bulk_g2s(&s_rec[r & 1][tid], a.recs + g, sizeof(GeomRec), bar);
-        }
-    };
-
-    float T = 1.0f, C0 = 0.0f, C1 = 0.0f, C2 = 0.0f, D = 0.0f;
-    uint32_t contributor = 0, last = 0;
-    uint32_t n_eval = 0, n_exp = 0, n_blend = 0;
-    bool done = !inside;
-    int issued = 0;
-    if (rounds > 0) { issue(0); issued = 1; }
-    int r = 0;
-    for (; r < rounds; ++r) {
-        if (r + 1 < rounds) { issue(r + 1); issued = r + 2; }
-        mbar_wait(&s_bar[r & 1], (uint32_t)((r >> 1) & 1));
-        const int cnt = min(256, n - (r << 8));
-        const GeomRec* sr = s_rec[r & 1];
-        for (int j = 0; j < cnt && !done; ++j) {
-            contributor++;
-            const float4 A = sr[j].a;
-            const float4 B = sr[j].b;
-            float alpha;
-            if (!pair_alpha<STATS>(A, B, pfx, pfy, alpha, n_eval, n_exp)) continue;
-            float test_T = mul(T, sub(1.0f, alpha));
-            if (test_T < 0.0001f) { done = true; continue; }
-            if (STATS) ++n_blend;
-            const float4 Cc = sr[j].c;
-            C0 = fma(mul(Cc.x, alpha), T, C0);
-            C1 = fma(mul(Cc.y, alpha), T, C1);
-            C2 = fma(mul(Cc.z, alpha), T, C2);
-            D = fma(mul(B.z, alpha), T, D);
-            T = test_T;
-            last = contributor;
-        }
-        if (__syncthreads_and(done)) { ++r; break; }
-    }
-    // never leave with a bulk copy still in flight into our shared memory
-    if (issued > r) mbar_wait(&s_bar[r & 1], (uint32_t)((r >> 1) & 1));
-
-    if (inside) {
-        const size_t HW = (size_t)a.W * a.H, pix = (size_t)py * a.W + px;
-        a.out_color[pix] = fma(T, a.bg[0], C0);
-        a.out_color[HW + pix] = fma(T, a.bg[1], C1);
-        a.out_color[2 * HW + pix] = fma(T, a.bg[2], C2);
-        a.out_depth[pix] = D;
-        if (a.out_final_T) a.out_final_T[pix] = T;
-        if (a.out_n_contrib) a.out_n_contrib[pix] = last;
-    }
-    if (STATS) flush_stats(a.stats, n_eval, n_exp, n_blend);
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// ------------------------------------------------------------------------------------------------
-// Fused K+3 passes.  Chains per pixel: main (all Gaussians), objects-only, and one per object.
-// Phase 1 walks every entry until the main chain of all 256 pixels has terminated; phase 2 scans
-// the remaining indices (4 B each), keeps object entries only and composites those.
-// ------------------------------------------------------------------------------------------------
 template <int KMAX, bool STATS>
-__global__ void __launch_bounds__(256) composite_masks_kernel(const CompArgs a) {
-    __shared__ GeomRec s_rec[2][256];
-    __shared__ __align__(8) uint64_t s_bar[2];
-    __shared__ uint32_t s_ids[512];
-    __shared__ uint32_t s_wcnt[8];
+__global__ void __launch_bounds__(COMP_THREADS) composite_kernel(const CompArgs a) {
+    constexpr bool MASKS = KMAX > 0;
+    constexpr int KREG = MASKS ? KMAX : 1;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    CompSmem& sm = *reinterpret_cast<CompSmem*>(smem_raw);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int tile = blockIdx.y * a.gx + blockIdx.x;
-    const int px = blockIdx.x * PG_TILE + (warp & 1) * 8 + (lane & 7);
-    const int py = blockIdx.y * PG_TILE + (warp >> 1) * 4 + (lane >> 3);
-    const bool inside = px < a.W && py < a.H;
-    const float pfx = (float)px, pfy = (float)py;
     const uint2 range = a.ranges[tile];
     const int n = (int)(range.y - range.x);
-    const int K = a.num_objects;
-    int obj_left = (int)a.tile_obj_count[tile];  // object entries of this tile not yet walked
+    const uint32_t lt = (1u << lane) - 1u;
 
     if (tid == 0) {
-        mbar_init(&s_bar[0], 1);
-        mbar_init(&s_bar[1], 1);
+        for (int s = 0; s < COMP_STAGES; ++s) {
+            mbar_init(reinterpret_cast<uint64_t*>(&sm.full[s]), 33);
+            mbar_init(reinterpret_cast<uint64_t*>(&sm.empty[s]), 8);
+        }
+        mbar_init(reinterpret_cast<uint64_t*>(&sm.idbar[0]), 1);
+        mbar_init(reinterpret_cast<uint64_t*>(&sm.idbar[1]), 1);
+        sm.warps_done = 0;
+        sm.warps_main_done = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+
+    if (warp == 8) {
+        // =========================== PRODUCER ===========================
+        int obj_left = MASKS ? (int)a.tile_obj_count[tile] : 0;  // un-culled object entries not yet compacted
+        // id chunks are fetched by TMA from a 16-byte aligned base; entries outside [range.x, range.y) are ignored
+        const uint32_t a0 = range.x & ~3u;
+        const int span = (int)(range.y - a0);
+        const int nchunks = n > 0 ? (span + COMP_IDCHUNK - 1) / COMP_IDCHUNK : 0;
+        auto fetch_ids = [&](int ci) {
+            if (lane == 0) {
+                const int left = span - ci * COMP_IDCHUNK;
+                const uint32_t bytes = (uint32_t)((min(left, COMP_IDCHUNK) + 3) & ~3) * 4u;
+                uint64_t* bar = reinterpret_cast<uint64_t*>(&sm.idbar[ci & 1]);
+                mbar_expect_tx(bar, bytes);
+                bulk_g2s(sm.ids[ci & 1], a.point_list + a0 + (size_t)ci * COMP_IDCHUNK, bytes, bar);
+            }
+        };
+        if (nchunks > 0) fetch_ids(0);
+        if (nchunks > 1) fetch_ids(1);
+        int ci = 0, head = 0, fill = 0;
+        for (int it = 0;; ++it) {
+            const int s = it % COMP_STAGES;
+            if (it >= COMP_STAGES)
+                mbar_wait(reinterpret_cast<uint64_t*>(&sm.empty[s]), (uint32_t)(((it / COMP_STAGES) - 1) & 1));
+            const bool all_done = *(volatile int*)&sm.warps_done == 8;
+            const bool mode_all = !MASKS || *(volatile int*)&sm.warps_main_done < 8;
+            while (!all_done && fill < COMP_BATCH && ci < nchunks && (mode_all || obj_left > 0)) {
+                mbar_wait(reinterpret_cast<uint64_t*>(&sm.idbar[ci & 1]), (uint32_t)((ci >> 1) & 1));
+                const uint32_t* src = sm.ids[ci & 1];
+                const uint32_t g0 = a0 + (uint32_t)ci * COMP_IDCHUNK;
+#pragma unroll 4
+                for (int u = 0; u < COMP_IDCHUNK / 32; ++u) {
+                    const uint32_t gi = g0 + u * 32 + lane;
+                    const uint32_t v = src[u * 32 + lane];
+                    const bool live = gi >= range.x && gi < range.y && !(v & PG_CULL_FLAG);
+                    const bool is_obj = MASKS && live && v >= a.n_env;
+                    const bool keep = live && (mode_all || is_obj);
+                    const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+                    if (keep) {
+                        const int slot = (head + fill + __popc(bal & lt)) & (COMP_PEND - 1);
+                        sm.pend[slot] = v;
+                        sm.pendpos[slot] = gi - range.x + 1u;
+                    }
+                    fill += __popc(bal);
+                    if (MASKS) obj_left -= __popc(__ballot_sync(0xffffffffu, is_obj));
+                }
+                __syncwarp();
+                if (ci + 2 < nchunks) fetch_ids(ci + 2);
+                ++ci;
+            }
+            __syncwarp();
+            const int cnt = all_done ? 0 : min(fill, COMP_BATCH);
+            if (lane == 0) sm.cnt[s] = cnt;
+            if (!MASKS)
+                for (int e = lane; e < cnt; e += 32) sm.pos[s][e] = sm.pendpos[(head + e) & (COMP_PEND - 1)];
+            __syncwarp();
+            // full[s] expects 33 arrivals: lane 0's release-arrive (publishes cnt / pos) + one per lane that
+            // fires when that lane's cp.async gathers have landed
+            if (lane == 0) mbar_arrive(&sm.full[s]);
+            if (cnt == 0) {
+                mbar_arrive(&sm.full[s]);  // end marker: plain arrivals
+                break;
+            }
+            // gather: 3 x 16-byte cp.async per record (per-lane addresses issue as ordinary SIMT instructions;
+            // a per-record TMA bulk copy needs uniform operands and serialises over the 32 lanes)
+            for (int e = lane; e < cnt; e += 32) {
+                const char* src = reinterpret_cast<const char*>(a.recs + sm.pend[(head + e) & (COMP_PEND - 1)]);
+                const uint32_t dst = smem_u32(&sm.rec[s][e]);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16), "l"(src + 16) : "memory");
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 32), "l"(src + 32) : "memory");
+            }
+            asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&sm.full[s])) : "memory");
+            head = (head + cnt) & (COMP_PEND - 1);
+            fill -= cnt;
+            __syncwarp();
+        }
+        // drain id chunks that were fetched but never consumed (never exit with a copy in flight)
+        for (int c2 = ci; c2 < min(nchunks, ci + 2); ++c2)
+            mbar_wait(reinterpret_cast<uint64_t*>(&sm.idbar[c2 & 1]), (uint32_t)((c2 >> 1) & 1));
+        return;
+    }
+
+    // =========================== CONSUMERS ===========================
+    const int wx0 = blockIdx.x * PG_TILE + (warp & 1) * 8, wy0 = blockIdx.y * PG_TILE + (warp >> 1) * 4;
+    const int px = wx0 + (lane & 7), py = wy0 + (lane >> 3);
+    const bool inside = px < a.W && py < a.H;
+    const float pfx = (float)px, pfy = (float)py;
+    // pixel-centre extent of this warp's block, clipped to the image
+    const float bx0 = (float)wx0, bx1 = (float)min(wx0 + 7, a.W - 1);
+    const float by0 = (float)wy0, by1 = (float)min(wy0 + 3, a.H - 1);
+    const int K = MASKS ? a.num_objects : 0;
+    const uint32_t all_k = K >= 32 ? 0xFFFFFFFFu : ((1u << K) - 1u);
 
     float T = 1.0f, C0 = 0.0f, C1 = 0.0f, C2 = 0.0f, D = 0.0f;
     float To = 1.0f, S0 = 0.0f, S1 = 0.0f, S2 = 0.0f;
-    float Tk[KMAX];
+    float Tk[KREG];
 #pragma unroll
-    for (int k = 0; k < KMAX; ++k) Tk[k] = 1.0f;
-    bool done_main = !inside, done_o = !inside;
+    for (int k = 0; k < KREG; ++k) Tk[k] = 1.0f;
+    bool done_main = !inside, done_o = !inside || !MASKS;
+    uint32_t done_k = (inside && MASKS) ? 0u : 0xFFFFFFFFu;
+    uint32_t last = 0;
     uint32_t n_eval = 0, n_exp = 0, n_blend = 0;
-    uint32_t done_k = inside ? 0u : 0xFFFFFFFFu;
+    bool w_main_done = false, w_done = false;  // warp-uniform, already reported to the producer
 
-    // blend one staged record into every live chain of this pixel
-    auto blend = [&](const GeomRec& rec, bool main_live) {
-        const int obj = __float_as_int(rec.c.w);  // warp-uniform
-        const bool k_live = obj > 0 && !((done_k >> (obj - 1)) & 1u);
-        const bool o_live = obj > 0 && !done_o;
-        if (!(main_live || k_live || o_live)) return;
-        float alpha;
-        if (!pair_alpha<STATS>(rec.a, rec.b, pfx, pfy, alpha, n_eval, n_exp)) return;
-        if (STATS) ++n_blend;
-        const float om = sub(1.0f, alpha);
-        if (main_live) {
-            float test_T = mul(T, om);
-            if (test_T < 0.0001f) done_main = true;
-            else {
-                C0 = fma(mul(rec.c.x, alpha), T, C0);
-                C1 = fma(mul(rec.c.y, alpha), T, C1);
-                C2 = fma(mul(rec.c.z, alpha), T, C2);
-                D = fma(mul(rec.b.z, alpha), T, D);
-                T = test_T;
-            }
-        }
-        if (obj > 0) {
-            if (o_live) {
-                float test_T = mul(To, om);
-                if (test_T < 0.0001f) done_o = true;
-                else {
-                    S0 = fma(mul(a.eff_color[obj - 1][0], alpha), To, S0);
-                    S1 = fma(mul(a.eff_color[obj - 1][1], alpha), To, S1);
-                    S2 = fma(mul(a.eff_color[obj - 1][2], alpha), To, S2);
-                    To = test_T;
+    for (int it = 0;; ++it) {
+        const int s = it % COMP_STAGES;
+        mbar_wait(reinterpret_cast<uint64_t*>(&sm.full[s]), (uint32_t)((it / COMP_STAGES) & 1));
+        const int cnt = *(volatile int*)&sm.cnt[s];
+        if (cnt == 0) break;
+        if (!w_done) {
+            const GeomRec* sr = sm.rec[s];
+            bool wm = !w_main_done;
+            // ---- per 32-entry chunk: lane-parallel cull against this warp's pixel block, then walk
+            //      the hits in list order (one loop body: the kernel must stay inside the I-cache)
+#pragma unroll 1
+            for (int c0 = 0; c0 < cnt; c0 += 32) {
+                const int e = c0 + lane;
+                bool hit = false, is_obj = false;
+                if (e < cnt) {
+                    const float4 A = sr[e].a;
+                    const float4 B = sr[e].b;
+                    is_obj = MASKS && (__float_as_int(B.w) & 63) > 0;
+                    hit = (wm || is_obj) && !block_culled(A.x, A.y, A.z, A.w, B.x, B.w, bx0, bx1, by0, by1);
                 }
-            }
-            if (k_live) {
+                uint32_t mm = __ballot_sync(0xffffffffu, hit);
+                const uint32_t mo = MASKS ? __ballot_sync(0xffffffffu, hit && is_obj) : 0u;
+#pragma unroll 1
+                while (mm) {
+                    const int j = c0 + __ffs(mm) - 1;
+                    mm &= mm - 1;
+                    const float4 B = sr[j].b;
+                    const int obj = MASKS ? (__float_as_int(B.w) & 63) : 0;  // warp-uniform
+                    const bool main_live = !done_main;
+                    const bool k_live = MASKS && obj > 0 && !((done_k >> (obj - 1)) & 1u);
+                    const bool o_live = MASKS && obj > 0 && !done_o;
+                    if (main_live || k_live || o_live) {
+                        const float4 A = sr[j].a;
+                        float alpha;
+                        if (pair_alpha<STATS>(A, B, pfx, pfy, alpha, n_eval, n_exp)) {
+                            if (STATS) ++n_blend;
+                            const float om = sub(1.0f, alpha);
+                            if (main_live) {
+                                const float test_T = mul(T, om);
+                                if (test_T < 0.0001f) done_main = true;
+                                else {
+                                    const float4 Cc = sr[j].c;
+                                    C0 = fma(mul(Cc.x, alpha), T, C0);
+                                    C1 = fma(mul(Cc.y, alpha), T, C1);
+                                    C2 = fma(mul(Cc.z, alpha), T, C2);
+                                    D = fma(mul(B.z, alpha), T, D);
+                                    T = test_T;
+                                    if (!MASKS) last = sm.pos[s][j];
+                                }
+                            }
+                            if (MASKS && obj > 0) {
+                                if (o_live) {
+                                    const float test_T = mul(To, om);
+                                    if (test_T < 0.0001f) done_o = true;
+                                    else {
+                                        S0 = fma(mul(a.eff_color[obj - 1][0], alpha), To, S0);
+                                        S1 = fma(mul(a.eff_color[obj - 1][1], alpha), To, S1);
+                                        S2 = fma(mul(a.eff_color[obj - 1][2], alpha), To, S2);
+                                        To = test_T;
+                                    }
+                                }
+                                if (k_live) {
 #pragma unroll
-                for (int k = 0; k < KMAX; ++k) {
-                    if (k == obj - 1) {  // uniform across the warp
-                        float test_T = mul(Tk[k], om);
-                        if (test_T < 0.0001f) done_k |= 1u << k;
-                        else Tk[k] = test_T;
+                                    for (int k = 0; k < KREG; ++k) {
+                                        if (k == obj - 1) {  // uniform across the warp
+                                            const float test_T = mul(Tk[k], om);
+                                            if (test_T < 0.0001f) done_k |= 1u << k;
+                                            else Tk[k] = test_T;
+                                        }
+                                    }
+                                }
+                            }
+                        }
+                    }
+                    // warp-level progress: drop environment hits once every main chain is done
+                    if (wm && __all_sync(0xffffffffu, done_main)) {
+                        wm = false;
+                        mm = MASKS ? (mm & mo) : 0u;
                     }
                 }
+                if (!wm && !MASKS) break;
+            }
+            // ---- report progress to the producer
+            if (!w_main_done && __all_sync(0xffffffffu, done_main)) {
+                w_main_done = true;
+                if (lane == 0) atomicAdd(&sm.warps_main_done, 1);
+            }
+            const bool pix_done = done_main && (!MASKS || (done_o && (done_k & all_k) == all_k));
+            if (__all_sync(0xffffffffu, pix_done)) {
+                w_done = true;
+                if (lane == 0) atomicAdd(&sm.warps_done, 1);
             }
         }
-    };
-    const uint32_t all_k = K >= 32 ? 0xFFFFFFFFu : ((1u << K) - 1u);
-
-    // ---------------- phase 1: every entry, until all main chains are done ----------------
-    auto issue = [&](int r) {
-        const int cnt = min(256, n - (r << 8));
-        uint64_t* bar = &s_bar[r & 1];
-        if (tid == 0) mbar_expect_tx(bar, (uint32_t)cnt * (uint32_t)sizeof(GeomRec));
-        if (tid < cnt) {
-            const uint32_t g = a.point_list[range.x + (r << 8) + tid];
-            bulk_g2s(&s_rec[r & 1][tid], a.recs + g, sizeof(GeomRec), bar);
-        }
-    };
-    const int rounds = (n + 255) >> 8;
-    int issued = 0, r = 0;
-    uint32_t par0 = 0, par1 = 0;  // phase parity of the two barriers
-    if (rounds > 0) { issue(0); issued = 1; }
-    bool all_main_done = false;
-    for (; r < rounds; ++r) {
-        if (r + 1 < rounds) { issue(r + 1); issued = r + 2; }
-        if (r & 1) { mbar_wait(&s_bar[1], par1); par1 ^= 1; } else { mbar_wait(&s_bar[0], par0); par0 ^= 1; }
-        const int cnt = min(256, n - (r << 8));
-        const GeomRec* sr = s_rec[r & 1];
-        int seen_obj = 0;
-        for (int j = 0; j < cnt; ++j) {
-            seen_obj += __float_as_int(sr[j].c.w) > 0 ? 1 : 0;
-            blend(sr[j], !done_main);
-        }
-        obj_left -= seen_obj;
-        all_main_done = __syncthreads_and(done_main);
-        if (all_main_done) { ++r; break; }
-    }
-    if (issued > r) {  // drain the prefetched batch we are not going to use in phase 1
-        if (r & 1) { mbar_wait(&s_bar[1], par1); par1 ^= 1; } else { mbar_wait(&s_bar[0], par0); par0 ^= 1; }
-    }
-    __syncthreads();
-
-    // ---------------- phase 2: object entries only ----------------
-    int pos = r << 8;  // first entry not walked in phase 1
-    if (pos < n && obj_left > 0 && K > 0) {
-        int fill = 0;
-        bool pix_done = done_o && (done_k & all_k) == all_k;
-        while (true) {
-            // scan ids until >= 256 object entries are buffered or the list ends
-            while (fill < 256 && pos < n && fill < obj_left) {
-                const int idx = pos + tid;
-                uint32_t g = 0;
-                bool is_obj = false;
-                if (idx < n) { g = a.point_list[range.x + idx]; is_obj = g >= a.n_env; }
-                const uint32_t bal = __ballot_sync(0xffffffffu, is_obj);
-                if (lane == 0) s_wcnt[warp] = __popc(bal);
-                __syncthreads();
-                int wb = 0, tot = 0;
-#pragma unroll
-                for (int w = 0; w < 8; ++w) { int c = (int)s_wcnt[w]; if (w < warp) wb += c; tot += c; }
-                if (is_obj) s_ids[fill + wb + __popc(bal & ((1u << lane) - 1u))] = g;
-                fill += tot;
-                pos += 256;
-                __syncthreads();
-            }
-            if (fill == 0) break;
-            const int cnt = min(fill, 256);
-            if (tid == 0) mbar_expect_tx(&s_bar[0], (uint32_t)cnt * (uint32_t)sizeof(GeomRec));
-            if (tid < cnt) bulk_g2s(&s_rec[0][tid], a.recs + s_ids[tid], sizeof(GeomRec), &s_bar[0]);
-            mbar_wait(&s_bar[0], par0); par0 ^= 1;
-            if (!pix_done) {
-                for (int j = 0; j < cnt; ++j) blend(s_rec[0][j], false);
-                pix_done = done_o && (done_k & all_k) == all_k;
-            }
-            obj_left -= cnt;
-            // shift the tail of the id buffer down
-            const int rest = fill - cnt;
-            uint32_t keep = 0;
-            if (tid < rest) keep = s_ids[cnt + tid];
-            const bool all_done = __syncthreads_and(pix_done);
-            if (tid < rest) s_ids[tid] = keep;
-            fill = rest;
-            __syncthreads();
-            if (all_done || (obj_left <= 0 && fill == 0)) break;
-        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.empty[s]);
     }
 
     if (inside) {
@@ -359,34 +388,37 @@ __global__ void __launch_bounds__(256) composite_masks_kernel(const CompArgs a) 
         a.out_color[2 * HW + pix] = fma(T, bg2, C2);
         a.out_depth[pix] = D;
         if (a.out_final_T) a.out_final_T[pix] = T;
-        const float s0 = fma(To, bg0, S0), s1 = fma(To, bg1, S1), s2 = fma(To, bg2, S2);
-        if (a.seg_color) {
-            a.seg_color[pix] = s0; a.seg_color[HW + pix] = s1; a.seg_color[2 * HW + pix] = s2;
-        }
-        if (a.sem_seg) {
-            a.sem_seg[3 * pix] = (uint8_t)(int)mul(s0, 255.0f);
-            a.sem_seg[3 * pix + 1] = (uint8_t)(int)mul(s1, 255.0f);
-            a.sem_seg[3 * pix + 2] = (uint8_t)(int)mul(s2, 255.0f);
-        }
-        if (a.visible) {
-            for (int c = 0; c < a.num_colors; ++c) {
-                float d0 = sub(s0, a.set_color[c][0]), d1 = sub(s1, a.set_color[c][1]), d2 = sub(s2, a.set_color[c][2]);
-                float dist = sqrt(add(add(mul(d0, d0), mul(d1, d1)), mul(d2, d2)));
-                a.visible[(size_t)c * HW + pix] = dist <= 0.1f ? 1 : 0;
+        if (!MASKS && a.out_n_contrib) a.out_n_contrib[pix] = last;
+        if (MASKS) {
+            const float s0 = fma(To, bg0, S0), s1 = fma(To, bg1, S1), s2 = fma(To, bg2, S2);
+            if (a.seg_color) {
+                a.seg_color[pix] = s0; a.seg_color[HW + pix] = s1; a.seg_color[2 * HW + pix] = s2;
             }
-        }
-        if (a.silhouette) {
-#pragma unroll
-            for (int k = 0; k < KMAX; ++k) {
-                if (k < K) {
-                    const int ci = a.color_index[k];
-                    const float w = sub(1.0f, Tk[k]);
-                    float i0 = fma(Tk[k], bg0, mul(a.eff_color[k][0], w));
-                    float i1 = fma(Tk[k], bg1, mul(a.eff_color[k][1], w));
-                    float i2 = fma(Tk[k], bg2, mul(a.eff_color[k][2], w));
-                    float d0 = sub(i0, a.set_color[ci][0]), d1 = sub(i1, a.set_color[ci][1]), d2 = sub(i2, a.set_color[ci][2]);
+            if (a.sem_seg) {
+                a.sem_seg[3 * pix] = (uint8_t)(int)mul(s0, 255.0f);
+                a.sem_seg[3 * pix + 1] = (uint8_t)(int)mul(s1, 255.0f);
+                a.sem_seg[3 * pix + 2] = (uint8_t)(int)mul(s2, 255.0f);
+            }
+            if (a.visible) {
+                for (int c = 0; c < a.num_colors; ++c) {
+                    float d0 = sub(s0, a.set_color[c][0]), d1 = sub(s1, a.set_color[c][1]), d2 = sub(s2, a.set_color[c][2]);
                     float dist = sqrt(add(add(mul(d0, d0), mul(d1, d1)), mul(d2, d2)));
-                    a.silhouette[(size_t)ci * HW + pix] = dist <= 0.1f ? 1 : 0;
+                    a.visible[(size_t)c * HW + pix] = dist <= 0.1f ? 1 : 0;
+                }
+            }
+            if (a.silhouette) {
+#pragma unroll
+                for (int kk = 0; kk < KREG; ++kk) {
+                    if (kk < K) {
+                        const int ci = a.color_index[kk];
+                        const float w = sub(1.0f, Tk[kk]);
+                        float i0 = fma(Tk[kk], bg0, mul(a.eff_color[kk][0], w));
+                        float i1 = fma(Tk[kk], bg1, mul(a.eff_color[kk][1], w));
+                        float i2 = fma(Tk[kk], bg2, mul(a.eff_color[kk][2], w));
+                        float d0 = sub(i0, a.set_color[ci][0]), d1 = sub(i1, a.set_color[ci][1]), d2 = sub(i2, a.set_color[ci][2]);
+                        float dist = sqrt(add(add(mul(d0, d0), mul(d1, d1)), mul(d2, d2)));
+                        a.silhouette[(size_t)ci * HW + pix] = dist <= 0.1f ? 1 : 0;
+                    }
                 }
             }
         }
@@ -394,30 +426,31 @@ __global__ void __launch_bounds__(256) composite_masks_kernel(const CompArgs a) 
     if (STATS) flush_stats(a.stats, n_eval, n_exp, n_blend);
 }
 
-int launch_composite(const CompArgs& a, int gy, bool masks, cudaStream_t stream) {
-    dim3 grid(a.gx, gy), block(256);
-    const bool st = a.stats != nullptr;
-    if (!masks) {
-        if (st) composite_kernel<true><<<grid, block, 0, stream>>>(a);
-        else composite_kernel<false><<<grid, block, 0, stream>>>(a);
-    } else if (a.num_objects <= 8) {
-        if (st) composite_masks_kernel<8, true><<<grid, block, 0, stream>>>(a);
-        else composite_masks_kernel<8, false><<<grid, block, 0, stream>>>(a);
-    } else if (a.num_objects <= 16) {
-        if (st) composite_masks_kernel<16, true><<<grid, block, 0, stream>>>(a);
-        else composite_masks_kernel<16, false><<<grid, block, 0, stream>>>(a);
-    } else {
-        if (st) composite_masks_kernel<32, true><<<grid, block, 0, stream>>>(a);
-        else composite_masks_kernel<32, false><<<grid, block, 0, stream>>>(a);
+template <int KMAX, bool STATS>
+static int launch_one(const CompArgs& a, dim3 grid, cudaStream_t stream) {
+    static bool attr_set = false;
+    const int smem = (int)sizeof(CompSmem);
+    if (!attr_set) {
+        PG_CUDA_CHECK(cudaFuncSetAttribute(composite_kernel<KMAX, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_set = true;
     }
+    composite_kernel<KMAX, STATS><<<grid, COMP_THREADS, smem, stream>>>(a);
+    return PG_OK;
+}
+
+int launch_composite(const CompArgs& a, int gy, bool masks, cudaStream_t stream) {
+    dim3 grid(a.gx, gy);
+    const bool st = a.stats != nullptr;
+    int rc;
+    if (!masks) rc = st ? launch_one<0, true>(a, grid, stream) : launch_one<0, false>(a, grid, stream);
+    else if (a.num_objects <= 8) rc = st ? launch_one<8, true>(a, grid, stream) : launch_one<8, false>(a, grid, stream);
+    else if (a.num_objects <= 16) rc = st ? launch_one<16, true>(a, grid, stream) : launch_one<16, false>(a, grid, stream);
+    else rc = st ? launch_one<32, true>(a, grid, stream) : launch_one<32, false>(a, grid, stream);
+    if (rc) return rc;
     PG_CUDA_CHECK(cudaGetLastError());
     count_launch(1);
     return PG_OK;
 }
-
-}  // namespace pg
-
-namespace pg {
 
 // Fills CompArgs from the ABI structs and launches the right kernel.
 int launch_composite_from_abi(const uint2* ranges, const uint32_t* point_list, const GeomRec* recs, int W,
@@ -440,6 +473,8 @@ int launch_composite_from_abi(const uint2* ranges, const uint32_t* point_list, c
     a.out_color = fo->color; a.out_depth = fo->depth; a.out_final_T = fo->final_T;
     a.seg_color = fo->seg_color; a.sem_seg = fo->sem_seg; a.visible = fo->visible; a.silhouette = fo->silhouette;
     a.num_objects = objs->num_objects; a.num_colors = objs->num_colors;
+    if (a.num_objects == 0 && !(fo->seg_color || fo->sem_seg || fo->visible || fo->silhouette))
+        return launch_composite(a, gy, false, stream);
     const volatile float C0 = 0.28209479177387814f;
     for (int c = 0; c < objs->num_colors; ++c)
         for (int ch = 0; ch < 3; ++ch) a.set_color[c][ch] = objs->colors[c][ch];

@@ -44,8 +44,8 @@ int launch_onesweep_pass(bool iota, bool write_keys, const uint32_t* keys_in, ui
                          uint32_t n_imm, uint32_t max_tiles, int begin_bit, int num_bits,
                          const uint32_t* bin_base, uint32_t* status, uint32_t* ticket,
                          cudaStream_t stream);
-int launch_emit(const uint32_t* sorted_dkey, const uint32_t* perm, const ushort4* rects, uint32_t P,
-                uint32_t gx, uint32_t* tkeys, uint32_t* tvals, uint32_t R_cap, uint32_t* status,
+int launch_emit(const uint32_t* sorted_dkey, const uint32_t* perm, const ushort4* rects, const GeomRec* recs,
+                uint32_t P, uint32_t gx, int W, int H, uint32_t* tkeys, uint32_t* tvals, uint32_t R_cap, uint32_t* status,
                 uint32_t* tile_count, uint32_t n_env, uint32_t* tile_obj_count, Counters* counters,
                 cudaStream_t stream);
 int launch_tile_scan(const uint32_t* tile_count, uint32_t tiles, int bits_lo, int bits_hi, uint2* ranges,
@@ -147,7 +147,8 @@ static int run_binning(const pg_raster_settings* s, const pg_gaussians* g, const
     if (s->debug & 1) PG_CUDA_CHECK(cudaStreamSynchronize(stream));
     // after 4 passes the sorted keys/permutation are back in (dkey_a, dval_a) == (ka, va)
     const uint32_t n_env = (objs && objs->num_objects > 0) ? (uint32_t)objs->first[0] : (uint32_t)P;
-    rc = launch_emit(ka, va, at<ushort4>(ws, L.rect), (uint32_t)P, gx, at<uint32_t>(ws, L.tkey_a),
+    rc = launch_emit(ka, va, at<ushort4>(ws, L.rect), at<GeomRec>(ws, L.recs), (uint32_t)P, gx, W, H,
+                     at<uint32_t>(ws, L.tkey_a),
                      at<uint32_t>(ws, L.tval_a), (uint32_t)R_cap, at<uint32_t>(ws, L.status_emit),
                      at<uint32_t>(ws, L.tile_count), n_env, at<uint32_t>(ws, L.tile_obj_count), counters, stream);
     if (rc) return rc;

@@ -46,10 +46,33 @@ __device__ __forceinline__ float expf_exact(float x) {
     return __int_as_float(__float_as_int(p) + (ni << 23));
 }
 
+// Bit 31 of a point-list value: the binning stage proved that this Gaussian cannot reach alpha >= 1/255
+// at any pixel centre of this tile; compositing drops the entry without fetching its record.
+#define PG_CULL_FLAG 0x80000000u
+
+// Conservative test: can a Gaussian with centre (gx,gy), conic (qa,qb,qc) and cut `cut`
+// (alpha < 1/255 wherever power < cut) be skipped for every pixel centre of [x0,x1]x[y0,y1]?
+// q(d) = 0.5*qa*dx^2 + qb*dx*dy + 0.5*qc*dy^2 is convex for a positive-definite conic, so its minimum
+// over the rectangle is 0 if the centre is inside, else it lies on the edges facing the centre,
+// where it has a closed form.  The 1e-4 relative + 1e-3 absolute margin dwarfs the rounding of both
+// this test and the compositing arithmetic; indefinite conics and NaNs are never culled.
+__device__ __forceinline__ bool block_culled(float gx, float gy, float qa, float qb, float qc, float cut,
+                                             float x0, float x1, float y0, float y1) {
+    const float xl = x0 - gx, xh = x1 - gx, yl = y0 - gy, yh = y1 - gy;
+    const float cx = fminf(fmaxf(0.0f, xl), xh), cy = fminf(fmaxf(0.0f, yl), yh);
+    const float dy1 = fminf(fmaxf(-qb * cx * __frcp_rn(qc), yl), yh);
+    const float dx2 = fminf(fmaxf(-qb * cy * __frcp_rn(qa), xl), xh);
+    const float q1 = 0.5f * (qa * cx * cx + qc * dy1 * dy1) + qb * cx * dy1;
+    const float q2 = 0.5f * (qa * dx2 * dx2 + qc * cy * cy) + qb * dx2 * cy;
+    const float qmin = fminf(q1, q2);
+    const bool pd = qa > 0.0f && qc > 0.0f && qa * qc - qb * qb > 0.0f;
+    return pd && (qmin * 0.9999f - 1e-3f > -cut);
+}
+
 // ---- per-Gaussian record staged into shared memory by the compositing kernel (48 B) ----------
 struct __align__(16) GeomRec {
     float4 a;  // x, y, conic.x, conic.y
-    float4 b;  // conic.z, opacity, depth, power_cut
+    float4 b;  // conic.z, opacity, depth, cut (power below which alpha < 1/255; low 6 mantissa bits = object id)
     float4 c;  // r, g, b, object id (as int bits; 0 = environment, k+1 = object k)
 };
 

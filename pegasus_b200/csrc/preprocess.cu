@@ -235,8 +235,14 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const PreArgs a) {
                     if (idx >= a.first[k] && idx < a.first[k + 1]) obj = k + 1;
                 GeomRec rec;
                 rec.a = make_float4(pixx, pixy, conx, cony);
-                // power below which alpha < 1/255 is certain when opacity <= 1 (exp(-5.55) < 1/255)
-                rec.b = make_float4(conz, op, pv[2], op <= 1.0f ? -5.55f : -80.0f);
+                // cut: alpha = min(.99, op*exp(power)) < 1/255 is certain for power < -(ln(255*op) + 0.01)
+                // (the 1 % margin dwarfs the error of logf and of the exp polynomial); never above 0.
+                // The object id rides in the low 6 mantissa bits (makes the cut at most 63 ulp more negative).
+                float cut = -80.0f;
+                if (op > 0.0f) cut = fminf(-(__logf(255.0f * op) + 0.01f), -1e-6f);
+                if (!(cut > -80.0f)) cut = -80.0f;
+                cut = __int_as_float((__float_as_int(cut) & ~63) | obj);
+                rec.b = make_float4(conz, op, pv[2], cut);
                 rec.c = make_float4(rgb[0], rgb[1], rgb[2], __int_as_float(obj));
                 a.recs[idx] = rec;
                 radius_out = ir;
