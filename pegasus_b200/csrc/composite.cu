@@ -15,8 +15,8 @@
 // Culling is conservative (a margin covers float rounding), so every (pixel, Gaussian) pair that
 // the reference would blend is blended with the reference's operation order: results are unchanged.
 //
-// KMAX == 0 : the reference's single pass -> color, depth (+ final_T, n_contrib).
-// KMAX  > 0 : the reference's K+3 passes in one walk -> RGB + depth, the objects-only flat-colour
+// MASKS == false : the reference's single pass -> color, depth (+ final_T, n_contrib).
+// MASKS == true  : the reference's K+3 passes in one walk -> RGB + depth, the objects-only flat-colour
 //             render (visible masks, sem-seg) and one transmittance chain per object (silhouettes);
 //             alpha is evaluated once per (pixel, Gaussian).
 //
@@ -88,25 +88,6 @@ struct CompArgs {
     unsigned long long* stats;  // non-null: count pairs evaluated / exp'd / blended
 };
 
-// alpha of one (pixel, Gaussian) pair; returns false when the pair is skipped (A.7 `continue`s)
-template <bool STATS>
-__device__ __forceinline__ bool pair_alpha(const float4 A, const float4 B, float pfx, float pfy, float& alpha,
-                                           uint32_t& n_eval, uint32_t& n_exp) {
-    if (STATS) ++n_eval;
-    float dx = sub(A.x, pfx), dy = sub(A.y, pfy);
-    float u = mul(A.z, dx);
-    float v = mul(B.x, dy);
-    float w = mul(dy, v);
-    float s = fma(dx, u, w);
-    float bxy = mul(mul(A.w, dx), dy);
-    float power = fma(s, -0.5f, -bxy);
-    if (power > 0.0f) return false;
-    if (power < B.w) return false;  // alpha < 1/255 guaranteed below the per-Gaussian cut
-    if (STATS) ++n_exp;
-    alpha = fminf(0.99f, mul(B.y, expf_exact(power)));
-    return !(alpha < 1.0f / 255.0f);
-}
-
 __device__ __forceinline__ void flush_stats(unsigned long long* stats, uint32_t n_eval, uint32_t n_exp, uint32_t n_blend) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -153,12 +134,34 @@ __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-template <int KMAX, bool STATS>
+// exp(x) for cut <= x <= 0 (cut >= -80.001): expf_exact without its x < -80 guard — identical results on
+// that range, and below it alpha = opacity * 2^-115 is skipped by the alpha < 1/255 test either way.
+__device__ __forceinline__ float expf_exact_nz(float x) {
+    const float L2E = 1.44269502162933349609375f;
+    const float MAGIC = 12582912.0f;
+    float z = fma(x, L2E, MAGIC);
+    float n = sub(z, MAGIC);
+    float r = fma(n, -0.693145751953125f, x);
+    r = fma(n, -1.428606765330187045e-06f, r);
+    float p = 0x1.6b5016p-10f;
+    p = fma(p, r, 0x1.126caep-7f);
+    p = fma(p, r, 0x1.55578ep-5f);
+    p = fma(p, r, 0x1.55540cp-3f);
+    p = fma(p, r, 0x1.fffffcp-2f);
+    p = fma(p, r, 1.0f);
+    p = fma(p, r, 1.0f);
+    return __int_as_float(__float_as_int(p) + (__float_as_int(z) << 23));  // MAGIC's low 9 bits are 0
+}
+
+// Dynamic shared memory after CompSmem (MASKS only): eff[PG_MAX_OBJECTS] float4 (colour the
+// rasterizer produces for object k's flat SH), then Tk[K][256] — the standalone transmittance of
+// object k at each of the tile's 256 pixels (silhouette chains), slot = warp * 32 + lane.
+template <bool MASKS, bool STATS>
 __global__ void __launch_bounds__(COMP_THREADS) composite_kernel(const CompArgs a) {
-    constexpr bool MASKS = KMAX > 0;
-    constexpr int KREG = MASKS ? KMAX : 1;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     CompSmem& sm = *reinterpret_cast<CompSmem*>(smem_raw);
+    float4* sm_eff = reinterpret_cast<float4*>(smem_raw + sizeof(CompSmem));
+    float* sm_tk = reinterpret_cast<float*>(smem_raw + sizeof(CompSmem) + PG_MAX_OBJECTS * sizeof(float4));
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int tile = blockIdx.y * a.gx + blockIdx.x;
@@ -177,6 +180,8 @@ __global__ void __launch_bounds__(COMP_THREADS) composite_kernel(const CompArgs 
         sm.warps_main_done = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    if (MASKS && tid < a.num_objects)
+        sm_eff[tid] = make_float4(a.eff_color[tid][0], a.eff_color[tid][1], a.eff_color[tid][2], 0.0f);
     __syncthreads();
 
     if (warp == 8) {
@@ -265,18 +270,19 @@ __global__ void __launch_bounds__(COMP_THREADS) composite_kernel(const CompArgs 
     const int wx0 = blockIdx.x * PG_TILE + (warp & 1) * 8, wy0 = blockIdx.y * PG_TILE + (warp >> 1) * 4;
     const int px = wx0 + (lane & 7), py = wy0 + (lane >> 3);
     const bool inside = px < a.W && py < a.H;
-    const float pfx = (float)px, pfy = (float)py;
+    float pfx = (float)px, pfy = (float)py;
+    asm volatile("" : "+f"(pfx), "+f"(pfy));  // keep them in registers: never rematerialise in the hit loop
     // pixel-centre extent of this warp's block, clipped to the image
     const float bx0 = (float)wx0, bx1 = (float)min(wx0 + 7, a.W - 1);
     const float by0 = (float)wy0, by1 = (float)min(wy0 + 3, a.H - 1);
     const int K = MASKS ? a.num_objects : 0;
     const uint32_t all_k = K >= 32 ? 0xFFFFFFFFu : ((1u << K) - 1u);
+    float* my_tk = sm_tk + (warp * 32 + lane);  // object k's chain at my_tk[k * 256]
+    if (MASKS)
+        for (int k = 0; k < K; ++k) my_tk[k * 256] = 1.0f;
 
     float T = 1.0f, C0 = 0.0f, C1 = 0.0f, C2 = 0.0f, D = 0.0f;
     float To = 1.0f, S0 = 0.0f, S1 = 0.0f, S2 = 0.0f;
-    float Tk[KREG];
-#pragma unroll
-    for (int k = 0; k < KREG; ++k) Tk[k] = 1.0f;
     bool done_main = !inside, done_o = !inside || !MASKS;
     uint32_t done_k = (inside && MASKS) ? 0u : 0xFFFFFFFFu;
     uint32_t last = 0;
@@ -292,81 +298,91 @@ __global__ void __launch_bounds__(COMP_THREADS) composite_kernel(const CompArgs 
             const GeomRec* sr = sm.rec[s];
             bool wm = !w_main_done;
             // ---- per 32-entry chunk: lane-parallel cull against this warp's pixel block, then walk
-            //      the hits in list order (one loop body: the kernel must stay inside the I-cache)
+            //      the hits in list order
 #pragma unroll 1
             for (int c0 = 0; c0 < cnt; c0 += 32) {
                 const int e = c0 + lane;
-                bool hit = false, is_obj = false;
+                // objects some pixel of this warp still needs (bit k-1): every object while an objects-only
+                // chain is alive, else those whose silhouette chain is alive somewhere.  Entries of other
+                // objects can no longer change any output of this block and are not walked.
+                uint32_t need = 0;
+                if (MASKS) need = __any_sync(0xffffffffu, !done_o) ? all_k : (__reduce_or_sync(0xffffffffu, ~done_k) & all_k);
+                if (MASKS && !wm && need == 0) break;
+                bool hit = false;
                 if (e < cnt) {
                     const float4 A = sr[e].a;
                     const float4 B = sr[e].b;
-                    is_obj = MASKS && (__float_as_int(B.w) & 63) > 0;
-                    hit = (wm || is_obj) && !block_culled(A.x, A.y, A.z, A.w, B.x, B.w, bx0, bx1, by0, by1);
+                    const int eo = MASKS ? (__float_as_int(B.w) & 63) : 0;
+                    const bool wanted = wm || (MASKS && eo > 0 && ((need >> ((uint32_t)(eo - 1) & 31u)) & 1u));
+                    hit = wanted && !block_culled(A.x, A.y, A.z, A.w, B.x, B.w, bx0, bx1, by0, by1);
                 }
                 uint32_t mm = __ballot_sync(0xffffffffu, hit);
-                const uint32_t mo = MASKS ? __ballot_sync(0xffffffffu, hit && is_obj) : 0u;
 #pragma unroll 1
                 while (mm) {
-                    const int j = c0 + __ffs(mm) - 1;
+                    const GeomRec* r = sr + (c0 + __ffs(mm) - 1);
                     mm &= mm - 1;
-                    const float4 B = sr[j].b;
+                    const float4 A = r->a;
+                    const float4 B = r->b;
+                    const float dx = sub(A.x, pfx), dy = sub(A.y, pfy);
+                    const float w = mul(dy, mul(B.x, dy));
+                    const float sq = fma(dx, mul(A.z, dx), w);
+                    const float bxy = mul(mul(A.w, dx), dy);
+                    const float power = fma(sq, -0.5f, -bxy);
                     const int obj = MASKS ? (__float_as_int(B.w) & 63) : 0;  // warp-uniform
-                    const bool main_live = !done_main;
-                    const bool k_live = MASKS && obj > 0 && !((done_k >> (obj - 1)) & 1u);
-                    const bool o_live = MASKS && obj > 0 && !done_o;
-                    if (main_live || k_live || o_live) {
-                        const float4 A = sr[j].a;
-                        float alpha;
-                        if (pair_alpha<STATS>(A, B, pfx, pfy, alpha, n_eval, n_exp)) {
-                            if (STATS) ++n_blend;
+                    bool live = true;  // STATS only: does any chain of this pixel still want this Gaussian?
+                    if (STATS) {
+                        live = !done_main || (MASKS && obj > 0 && (!done_o || !((done_k >> (obj - 1)) & 1u)));
+                        if (live) { ++n_eval; if (!(power > 0.0f) && !(power < B.w)) ++n_exp; }
+                    }
+                    // A.7: power > 0 skips; below the per-Gaussian cut alpha < 1/255 is certain (also a skip)
+                    if (!(power > 0.0f) && !(power < B.w)) {
+                        const float alpha = fminf(0.99f, mul(B.y, expf_exact_nz(power)));
+                        if (!(alpha < 1.0f / 255.0f)) {
+                            if (STATS && live) ++n_blend;
                             const float om = sub(1.0f, alpha);
-                            if (main_live) {
+                            if (!done_main) {
                                 const float test_T = mul(T, om);
                                 if (test_T < 0.0001f) done_main = true;
                                 else {
-                                    const float4 Cc = sr[j].c;
+                                    const float4 Cc = r->c;
                                     C0 = fma(mul(Cc.x, alpha), T, C0);
                                     C1 = fma(mul(Cc.y, alpha), T, C1);
                                     C2 = fma(mul(Cc.z, alpha), T, C2);
                                     D = fma(mul(B.z, alpha), T, D);
                                     T = test_T;
-                                    if (!MASKS) last = sm.pos[s][j];
+                                    if (!MASKS) last = sm.pos[s][r - sr];
                                 }
                             }
                             if (MASKS && obj > 0) {
-                                if (o_live) {
+                                if (!done_o) {
                                     const float test_T = mul(To, om);
                                     if (test_T < 0.0001f) done_o = true;
                                     else {
-                                        S0 = fma(mul(a.eff_color[obj - 1][0], alpha), To, S0);
-                                        S1 = fma(mul(a.eff_color[obj - 1][1], alpha), To, S1);
-                                        S2 = fma(mul(a.eff_color[obj - 1][2], alpha), To, S2);
+                                        const float4 ec = sm_eff[obj - 1];
+                                        S0 = fma(mul(ec.x, alpha), To, S0);
+                                        S1 = fma(mul(ec.y, alpha), To, S1);
+                                        S2 = fma(mul(ec.z, alpha), To, S2);
                                         To = test_T;
                                     }
                                 }
-                                if (k_live) {
-#pragma unroll
-                                    for (int k = 0; k < KREG; ++k) {
-                                        if (k == obj - 1) {  // uniform across the warp
-                                            const float test_T = mul(Tk[k], om);
-                                            if (test_T < 0.0001f) done_k |= 1u << k;
-                                            else Tk[k] = test_T;
-                                        }
-                                    }
+                                const uint32_t kb = (uint32_t)(obj - 1) & 31u;
+                                if (!((done_k >> kb) & 1u)) {
+                                    const float test_T = mul(my_tk[(obj - 1) * 256], om);
+                                    if (test_T < 0.0001f) done_k |= 1u << kb;
+                                    else my_tk[(obj - 1) * 256] = test_T;
                                 }
                             }
                         }
                     }
-                    // warp-level progress: drop environment hits once every main chain is done
-                    if (wm && __all_sync(0xffffffffu, done_main)) {
-                        wm = false;
-                        mm = MASKS ? (mm & mo) : 0u;
-                    }
                 }
-                if (!wm && !MASKS) break;
+                // warp-level progress: environment entries are no longer hits once every main chain is done
+                if (wm && __all_sync(0xffffffffu, done_main)) {
+                    wm = false;
+                    if (!MASKS) break;
+                }
             }
             // ---- report progress to the producer
-            if (!w_main_done && __all_sync(0xffffffffu, done_main)) {
+            if (!w_main_done && !wm) {
                 w_main_done = true;
                 if (lane == 0) atomicAdd(&sm.warps_main_done, 1);
             }
@@ -407,18 +423,17 @@ __global__ void __launch_bounds__(COMP_THREADS) composite_kernel(const CompArgs 
                 }
             }
             if (a.silhouette) {
-#pragma unroll
-                for (int kk = 0; kk < KREG; ++kk) {
-                    if (kk < K) {
-                        const int ci = a.color_index[kk];
-                        const float w = sub(1.0f, Tk[kk]);
-                        float i0 = fma(Tk[kk], bg0, mul(a.eff_color[kk][0], w));
-                        float i1 = fma(Tk[kk], bg1, mul(a.eff_color[kk][1], w));
-                        float i2 = fma(Tk[kk], bg2, mul(a.eff_color[kk][2], w));
-                        float d0 = sub(i0, a.set_color[ci][0]), d1 = sub(i1, a.set_color[ci][1]), d2 = sub(i2, a.set_color[ci][2]);
-                        float dist = sqrt(add(add(mul(d0, d0), mul(d1, d1)), mul(d2, d2)));
-                        a.silhouette[(size_t)ci * HW + pix] = dist <= 0.1f ? 1 : 0;
-                    }
+                for (int kk = 0; kk < K; ++kk) {
+                    const int ci = a.color_index[kk];
+                    const float tk = my_tk[kk * 256];
+                    const float4 ec = sm_eff[kk];
+                    const float w = sub(1.0f, tk);
+                    float i0 = fma(tk, bg0, mul(ec.x, w));
+                    float i1 = fma(tk, bg1, mul(ec.y, w));
+                    float i2 = fma(tk, bg2, mul(ec.z, w));
+                    float d0 = sub(i0, a.set_color[ci][0]), d1 = sub(i1, a.set_color[ci][1]), d2 = sub(i2, a.set_color[ci][2]);
+                    float dist = sqrt(add(add(mul(d0, d0), mul(d1, d1)), mul(d2, d2)));
+                    a.silhouette[(size_t)ci * HW + pix] = dist <= 0.1f ? 1 : 0;
                 }
             }
         }
@@ -426,15 +441,16 @@ __global__ void __launch_bounds__(COMP_THREADS) composite_kernel(const CompArgs 
     if (STATS) flush_stats(a.stats, n_eval, n_exp, n_blend);
 }
 
-template <int KMAX, bool STATS>
+template <bool MASKS, bool STATS>
 static int launch_one(const CompArgs& a, dim3 grid, cudaStream_t stream) {
-    static bool attr_set = false;
-    const int smem = (int)sizeof(CompSmem);
-    if (!attr_set) {
-        PG_CUDA_CHECK(cudaFuncSetAttribute(composite_kernel<KMAX, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_set = true;
+    static int attr_smem = 0;
+    const int smem = (int)sizeof(CompSmem) +
+                     (MASKS ? (int)(PG_MAX_OBJECTS * sizeof(float4)) + a.num_objects * 256 * (int)sizeof(float) : 0);
+    if (smem > attr_smem) {
+        PG_CUDA_CHECK(cudaFuncSetAttribute(composite_kernel<MASKS, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_smem = smem;
     }
-    composite_kernel<KMAX, STATS><<<grid, COMP_THREADS, smem, stream>>>(a);
+    composite_kernel<MASKS, STATS><<<grid, COMP_THREADS, smem, stream>>>(a);
     return PG_OK;
 }
 
@@ -442,10 +458,8 @@ int launch_composite(const CompArgs& a, int gy, bool masks, cudaStream_t stream)
     dim3 grid(a.gx, gy);
     const bool st = a.stats != nullptr;
     int rc;
-    if (!masks) rc = st ? launch_one<0, true>(a, grid, stream) : launch_one<0, false>(a, grid, stream);
-    else if (a.num_objects <= 8) rc = st ? launch_one<8, true>(a, grid, stream) : launch_one<8, false>(a, grid, stream);
-    else if (a.num_objects <= 16) rc = st ? launch_one<16, true>(a, grid, stream) : launch_one<16, false>(a, grid, stream);
-    else rc = st ? launch_one<32, true>(a, grid, stream) : launch_one<32, false>(a, grid, stream);
+    if (!masks) rc = st ? launch_one<false, true>(a, grid, stream) : launch_one<false, false>(a, grid, stream);
+    else rc = st ? launch_one<true, true>(a, grid, stream) : launch_one<true, false>(a, grid, stream);
     if (rc) return rc;
     PG_CUDA_CHECK(cudaGetLastError());
     count_launch(1);
