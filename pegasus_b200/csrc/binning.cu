@@ -71,32 +71,43 @@ emit_kernel(const uint32_t* __restrict__ sorted_dkey, const uint32_t* __restrict
         total += s_scan[w];
     }
     uint32_t excl = wb + x - local;
-    // chunk-level decoupled look-back (single value), thread 0
-    if (tid == 0) {
+    // chunk-level decoupled look-back (single value): warp 0 inspects 32 predecessors per step
+    if (warp == 0) {
         volatile uint32_t* st = status + chunk;
         uint32_t prev = 0;
-        uint32_t tot_c = min(total, E_VAL_MASK);
+        const uint32_t tot_c = min(total, E_VAL_MASK);
         if (chunk == 0) {
-            *st = tot_c | E_FLAG_INCL;
+            if (lane == 0) *st = tot_c | E_FLAG_INCL;
         } else {
-            *st = tot_c | E_FLAG_AGG;
-            int t = (int)chunk - 1;
+            if (lane == 0) *st = tot_c | E_FLAG_AGG;
+            int t = (int)chunk - 1;  // lane l looks at chunk t - l
             while (true) {
-                uint32_t s = *(volatile uint32_t*)(status + t);
-                uint32_t f = s >> 30;
-                if (f == 0) continue;
-                prev += s & E_VAL_MASK;
-                if (f == 2) break;
-                --t;
+                const int mine = t - lane;
+                const uint32_t sv = mine >= 0 ? *(volatile uint32_t*)(status + mine) : (2u << 30);
+                const uint32_t f = sv >> 30;
+                const uint32_t not_ready = __ballot_sync(0xffffffffu, f == 0);
+                const uint32_t incl = __ballot_sync(0xffffffffu, f == 2);
+                // usable prefix of the window: lanes below the first not-ready one, up to the first inclusive one
+                const int first_nr = not_ready ? __ffs(not_ready) - 1 : 32;
+                const int first_in = incl ? __ffs(incl) - 1 : 32;
+                const int take = min(first_nr, first_in + 1);  // lanes [0, take)
+                uint32_t v = lane < take ? (sv & E_VAL_MASK) : 0u;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                prev += v;
+                if (first_in < first_nr) break;
+                t -= take;
             }
-            *st = min(prev + tot_c, E_VAL_MASK) | E_FLAG_INCL;
+            if (lane == 0) *st = min(prev + tot_c, E_VAL_MASK) | E_FLAG_INCL;
         }
-        s_base = prev;
-        if (chunk == num_chunks - 1) {
-            uint64_t R = (uint64_t)prev + total;
-            counters->num_rendered = (uint32_t)min(R, (uint64_t)0xFFFFFFFFu);
-            counters->sort_n = (uint32_t)min(R, (uint64_t)R_cap);
-            if (R > R_cap) counters->overflow = 1;
+        if (lane == 0) {
+            s_base = prev;
+            if (chunk == num_chunks - 1) {
+                uint64_t R = (uint64_t)prev + total;
+                counters->num_rendered = (uint32_t)min(R, (uint64_t)0xFFFFFFFFu);
+                counters->sort_n = (uint32_t)min(R, (uint64_t)R_cap);
+                if (R > R_cap) counters->overflow = 1;
+            }
         }
     }
     __syncthreads();

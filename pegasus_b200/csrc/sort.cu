@@ -7,7 +7,7 @@
 // HBM-bound: each pass reads 8 B and writes 8 B per item (the last tile pass writes values only).
 //
 // CTA-tile = 256 threads x 16 items, warp-blocked so that rank order == memory order (stability).
-// Ranking: per-warp digit counters in shared memory + __match_any_sync multisplit.
+// Ranking: per-warp digit counters in shared memory + ballot multisplit (one vote per digit bit).
 // CTA-tiles take tickets from an atomic counter, so a tile only ever waits on tiles that already run.
 #include "pg_common.cuh"
 
@@ -56,15 +56,16 @@ __global__ void __launch_bounds__(256) scan_rows_kernel(uint32_t* __restrict__ h
 }
 
 template <bool IOTA, bool WRITE_KEYS>
-__global__ void __launch_bounds__(SORT_THREADS)
+__global__ void __launch_bounds__(SORT_THREADS, 4)
 onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, uint32_t* __restrict__ keys_out,
                      const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ vals_out,
                      const uint32_t* __restrict__ n_ptr, uint32_t n_imm, int begin_bit, int num_bits,
                      const uint32_t* __restrict__ bin_base, uint32_t* __restrict__ status,
                      uint32_t* __restrict__ ticket) {
     constexpr int WARPS = SORT_THREADS / 32;
-    __shared__ uint32_t s_warp_hist[WARPS][RADIX];
-    __shared__ uint32_t s_bin_start[RADIX];
+    // s_warp_pos[w][d]: first the number of digit-d items of warp w (early counts), then the running
+    // position inside the CTA-tile's digit-sorted staging buffer where warp w's next digit-d item goes
+    __shared__ uint32_t s_warp_pos[WARPS][RADIX];
     __shared__ uint32_t s_gbase[RADIX];
     __shared__ uint32_t s_keys[SORT_TILE];
     __shared__ uint32_t s_vals[SORT_TILE];
@@ -75,7 +76,7 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, uint32_t* __restrict_
     const uint32_t num_tiles = (n + SORT_TILE - 1) / SORT_TILE;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) s_tile = atomicAdd(ticket, 1u);
-    for (int i = tid; i < WARPS * RADIX; i += SORT_THREADS) (&s_warp_hist[0][0])[i] = 0;
+    for (int i = tid; i < WARPS * RADIX; i += SORT_THREADS) (&s_warp_pos[0][0])[i] = 0;
     __syncthreads();
     const uint32_t tile = s_tile;
     if (tile >= num_tiles) return;
@@ -83,7 +84,8 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, uint32_t* __restrict_
     const uint32_t tile_n = min((uint32_t)SORT_TILE, n - base);
     const uint32_t mask = (1u << num_bits) - 1u;
 
-    uint32_t keys[SORT_IPT], vals[SORT_IPT], ranks[SORT_IPT];
+    // ---- load (warp-blocked: item i of lane l is element wbase + 32 i, so rank order == memory order)
+    uint32_t keys[SORT_IPT], vals[SORT_IPT];
     const uint32_t wbase = base + warp * (32 * SORT_IPT) + lane;
 #pragma unroll
     for (int i = 0; i < SORT_IPT; ++i) {
@@ -93,34 +95,25 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, uint32_t* __restrict_
         if (IOTA) vals[i] = idx;
         else vals[i] = valid ? vals_in[idx] : 0u;
     }
-    const uint32_t lt = (1u << lane) - 1u;
+    // ---- early counts: per-warp digit histogram (padding items count as digit `mask`, sorted last)
 #pragma unroll
     for (int i = 0; i < SORT_IPT; ++i) {
         uint32_t idx = wbase + i * 32;
         uint32_t d = idx < n ? ((keys[i] >> begin_bit) & mask) : mask;
-        uint32_t peers = __match_any_sync(0xffffffffu, d);
-        int leader = __ffs(peers) - 1;
-        uint32_t prev = 0;
-        if (lane == leader) {
-            prev = s_warp_hist[warp][d];
-            s_warp_hist[warp][d] = prev + __popc(peers);
-        }
-        prev = __shfl_sync(0xffffffffu, prev, leader);
-        ranks[i] = prev + __popc(peers & lt);
-        __syncwarp();
+        atomicAdd(&s_warp_pos[warp][d], 1u);
     }
     __syncthreads();
-    // digit `tid`: exclusive scan over warps, CTA count
+    // ---- digit `tid`: CTA count, publish the aggregate EARLY (the ranking below overlaps the
+    //      predecessors' progress, so the look-back after it mostly finds inclusive prefixes)
     uint32_t cta_count = 0;
-    {
 #pragma unroll
-        for (int w = 0; w < WARPS; ++w) {
-            uint32_t c = s_warp_hist[w][tid];
-            s_warp_hist[w][tid] = cta_count;
-            cta_count += c;
-        }
-    }
-    // exclusive scan of cta_count over the 256 digits
+    for (int w = 0; w < WARPS; ++w) cta_count += s_warp_pos[w][tid];
+    const uint32_t pad = SORT_TILE - tile_n;
+    const uint32_t pub = cta_count - ((uint32_t)tid == mask ? pad : 0u);
+    volatile uint32_t* st = status + (size_t)tile * RADIX + tid;
+    if ((uint32_t)tid <= mask) *st = pub | (tile == 0 ? FLAG_INCL : FLAG_AGG);
+    // exclusive scan of cta_count over the digits -> start of each digit in the staging buffer
+    uint32_t bin_start;
     {
         uint32_t x = cta_count;
 #pragma unroll
@@ -132,41 +125,76 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, uint32_t* __restrict_
         __syncthreads();
         uint32_t wb = 0;
         for (int w = 0; w < warp; ++w) wb += s_scan[w];
-        s_bin_start[tid] = wb + x - cta_count;
+        bin_start = wb + x - cta_count;
     }
-    // decoupled look-back, one digit per thread
-    if ((uint32_t)tid <= mask) {
-        const uint32_t pad = SORT_TILE - tile_n;
-        const uint32_t pub = cta_count - ((uint32_t)tid == mask ? pad : 0u);
-        volatile uint32_t* st = status + (size_t)tile * RADIX + tid;
-        uint32_t excl = 0;
-        if (tile == 0) {
-            *st = pub | FLAG_INCL;
-        } else {
-            *st = pub | FLAG_AGG;
-            int t = (int)tile - 1;
-            while (true) {
-                uint32_t s = *(volatile uint32_t*)(status + (size_t)t * RADIX + tid);
-                uint32_t f = s >> 30;
-                if (f == 0) continue;
-                excl += s & VAL_MASK;
-                if (f == 2) break;
-                --t;
-            }
-            *st = ((excl + pub) & VAL_MASK) | FLAG_INCL;
+    {
+        uint32_t run = bin_start;
+#pragma unroll
+        for (int w = 0; w < WARPS; ++w) {
+            const uint32_t c = s_warp_pos[w][tid];
+            s_warp_pos[w][tid] = run;
+            run += c;
         }
-        s_gbase[tid] = bin_base[tid] + excl - s_bin_start[tid];
     }
     __syncthreads();
+    // ---- rank + scatter into the staging buffer: warp multisplit by explicit votes (one per digit
+    //      bit; inline PTX because nvcc turns the C++ idiom into MATCH.ANY, which is slower when the
+    //      32 digits differ), then one counter read per lane and one update per digit group
+    const uint32_t lt = (1u << lane) - 1u;
 #pragma unroll
     for (int i = 0; i < SORT_IPT; ++i) {
         uint32_t idx = wbase + i * 32;
         uint32_t d = idx < n ? ((keys[i] >> begin_bit) & mask) : mask;
-        uint32_t pos = s_bin_start[d] + s_warp_hist[warp][d] + ranks[i];
+        uint32_t peers = 0xffffffffu;
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            if (b < num_bits) {
+                uint32_t bal, bit = (d >> b) & 1u;
+                asm volatile("{\n.reg .pred p;\nsetp.ne.u32 p, %1, 0;\nvote.sync.ballot.b32 %0, p, 0xffffffff;\n}\n"
+                             : "=r"(bal) : "r"(bit));
+                peers &= bal ^ (bit - 1u);  // bit ? bal : ~bal
+            }
+        }
+        const uint32_t below = __popc(peers & lt);
+        const uint32_t pos = s_warp_pos[warp][d] + below;
+        __syncwarp();
+        if (below == 0) s_warp_pos[warp][d] = pos + __popc(peers);
+        __syncwarp();
         s_keys[pos] = keys[i];
         s_vals[pos] = vals[i];
     }
+    // ---- decoupled look-back, one digit per thread, LB_WIN predecessors in flight per step
+    if ((uint32_t)tid <= mask) {
+        uint32_t excl = 0;
+        if (tile != 0) {
+            constexpr int LB_WIN = 8;
+            int t = (int)tile - 1;
+            bool found = false;
+            while (!found) {
+                uint32_t sv[LB_WIN];
+#pragma unroll
+                for (int j = 0; j < LB_WIN; ++j)
+                    sv[j] = (t - j >= 0) ? *(volatile uint32_t*)(status + (size_t)(t - j) * RADIX + tid) : (2u << 30);
+                int used = 0;
+#pragma unroll
+                for (int j = 0; j < LB_WIN; ++j) {
+                    if (!found && used == j) {
+                        const uint32_t f = sv[j] >> 30;
+                        if (f != 0) {
+                            excl += sv[j] & VAL_MASK;
+                            ++used;
+                            if (f == 2) found = true;
+                        }
+                    }
+                }
+                t -= used;
+            }
+            *st = ((excl + pub) & VAL_MASK) | FLAG_INCL;
+        }
+        s_gbase[tid] = bin_base[tid] + excl - bin_start;
+    }
     __syncthreads();
+    // ---- coalesced store: staging position j of digit d goes to (global start of d) + (j - CTA start of d)
     for (uint32_t j = tid; j < tile_n; j += SORT_THREADS) {
         uint32_t k = s_keys[j];
         uint32_t d = (k >> begin_bit) & mask;
