@@ -290,7 +290,7 @@ def run_ours(args):
         if spec["dynamic"] and Kobj:
             scene.apply_pose_packets(pose_of(i))
         o = scene.render(view_of(i), bg, masks=True, out=out, sync_check=True)
-        max_R = max(max_R, o["num_rendered"])
+        max_R = max(max_R, o["num_stored"])
     cap = int(max_R * 1.05) + 4096
     _PAIR_CAPACITY_HINT[(Wd, Hd)] = cap
     # compositing statistics per view (untimed): pairs evaluated / exp'd / blended
@@ -300,7 +300,7 @@ def run_ours(args):
             scene.apply_pose_packets(pose_of(i))
         scene.render(view_of(i), bg, masks=True, out=out, sync_check=True, pair_capacity=cap, debug=2)
         st = scene.read_stats()
-        st.update(num_rendered=out["num_rendered"], num_visible=out["num_visible"])
+        st.update(num_rendered=out["num_rendered"], num_visible=out["num_visible"], num_stored=out["num_stored"])
         stats.append(st)
 
     def frame(i, sync_check=False):
@@ -425,14 +425,15 @@ def run_ours(args):
     mean_stage = stage_ms.mean(axis=0)
     mR = float(np.mean([s["num_rendered"] for s in stats]))
     mV = float(np.mean([s["num_visible"] for s in stats]))
+    mS = float(np.mean([s["num_stored"] for s in stats]))  # pairs that can contribute: stored + sorted
     ev_, ex_, bl_ = (float(np.mean([s[k] for s in stats])) for k in ("pairs_evaluated", "pairs_exp", "pairs_blended"))
     tiles = ((Wd + 15) // 16) * ((Hd + 15) // 16)
     alg_bytes = {
         "preprocess": 284.0 * mV + 16.0 * (P - mV),
         "depth_sort": (4.0 + 4 * 16.0) * P,
-        "emit": 16.0 * P + 8.0 * mR,
+        "emit": 4.0 * P + 76.0 * mV + 8.0 * mS,
         "tile_scan": 4.0 * tiles + 8.0 * tiles,
-        "tile_sort": (16.0 + 12.0) * mR,
+        "tile_sort": (16.0 + 12.0) * mS,
     }
     # FP32 work of compositing: 11 flop to evaluate a pair, +27 when it reaches exp(), +14 when blended
     comp_flop = 11.0 * ev_ + 27.0 * ex_ + 14.0 * bl_
@@ -483,7 +484,7 @@ def run_ours(args):
             "config": dict({k: spec[k] for k in ("workload", "env_n", "objects", "obj_n", "views", "width", "height")},
                            parallelism=f"view-parallel x{world} (scene replicated, frames round-robin, pose packets NCCL-broadcast)",
                            cache="inputs larger than L2 (scene parameters 0.7 GB per frame vs 126 MB L2)",
-                           pair_capacity=cap, pairs_per_frame=mR, visible_per_frame=mV),
+                           pair_capacity=cap, pairs_per_frame=mR, stored_pairs_per_frame=mS, visible_per_frame=mV),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / K_steps, "checksum": checksum},

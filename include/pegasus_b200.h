@@ -65,7 +65,9 @@ typedef struct pg_raster_settings {
     int32_t sh_degree;
     const float* campos;     /* [3] */
     int32_t prefiltered;
-    int32_t debug;           /* bit 0: synchronise after every stage; bit 1: collect compositing statistics */
+    int32_t debug;           /* bit 0: synchronise after every stage; bit 1: collect compositing statistics;
+                              * bit 2: keep the reference's complete (tile, Gaussian) pair lists instead of only the
+                              * pairs that can contribute (same images; for pg_export_binning / n_contrib parity) */
 } pg_raster_settings;
 
 /* Arguments of GaussianRasterizer.forward (GSP/gaussian_renderer/__init__.py:87-95). */
@@ -87,7 +89,8 @@ typedef struct pg_raster_outputs {
     int32_t* radii;      /* [P] */
     float* depth;        /* [1,H,W] */
     float* final_T;      /* [H,W] optional: transmittance; alpha = 1 - final_T */
-    uint32_t* n_contrib; /* [H,W] optional */
+    uint32_t* n_contrib; /* [H,W] optional: position of the last contributor in the reference's tile list;
+                          * requesting it implies debug bit 2 */
 } pg_raster_outputs;
 
 /* Objects of a composed scene: Gaussians [first[k], first[k+1]) belong to object k, everything
@@ -142,10 +145,10 @@ typedef struct pg_scene {
 } pg_scene;
 
 typedef struct pg_status {
-    uint32_t num_rendered; /* R = number of (tile, Gaussian) pairs of the last forward */
-    uint32_t overflow;     /* !=0: R exceeded the workspace's pair capacity; outputs are invalid */
+    uint32_t num_rendered; /* the reference's R: sum of the tile rectangles of all visible Gaussians */
+    uint32_t overflow;     /* !=0: the stored pairs exceeded the workspace's pair capacity; outputs are invalid */
     uint32_t num_visible;
-    uint32_t reserved;
+    uint32_t num_stored;   /* pairs actually stored and sorted (== R with debug bit 2), clamped to the capacity */
 } pg_status;
 
 const char* pg_version(void);
@@ -175,8 +178,9 @@ int pg_pose_apply(int32_t num_objects, const int32_t* first, const pg_pose* pose
                   const pg_canonical* canon, int32_t scene_offset, const pg_scene* scene,
                   pg_stream_t stream);
 
-/* Test/debug: rebuild the reference's sorted 64-bit keys, point list and tile ranges of the last
- * forward that used `workspace`.  keys/point_list hold >= num_rendered entries. */
+/* Test/debug: rebuild the sorted 64-bit keys, point list and tile ranges of the last forward that
+ * used `workspace` — the reference's when that forward ran with debug bit 2, else the stored
+ * sub-lists.  keys/point_list hold >= num_stored entries. */
 int pg_export_binning(const void* workspace, int32_t P, int32_t width, int32_t height,
                       uint64_t pair_capacity, uint64_t* keys, uint32_t* point_list,
                       uint32_t* ranges /*[tiles,2]*/, pg_stream_t stream);

@@ -63,7 +63,7 @@ class Scene(C.Structure):
 
 class Status(C.Structure):
     _fields_ = [("num_rendered", C.c_uint32), ("overflow", C.c_uint32), ("num_visible", C.c_uint32),
-                ("reserved", C.c_uint32)]
+                ("num_stored", C.c_uint32)]
 
 
 EXPORTS = ["pg_version", "pg_last_error", "pg_workspace_bytes", "pg_rasterize_forward",

@@ -2,10 +2,12 @@
 //   emit_kernel      : fused inclusive scan of tiles_touched (decoupled look-back over 1024-Gaussian
 //                      chunks, in DEPTH order) + key duplication: writes (tile id, Gaussian index)
 //                      pairs and counts pairs per tile.  12 B read per Gaussian, 8 B written per pair.
-//   tile_scan_kernel : exclusive scan of the per-tile counts -> ranges[tile] (identifyTileRanges
-//                      without touching the sorted keys) + exclusive digit bases of both tile-sort passes.
+//   tile_scan_kernel : exclusive digit bases of both tile-sort passes from the histograms emit
+//                      accumulated (shared memory per CTA, one flush).
+//   ranges_kernel    : identifyTileRanges on the sorted tile ids.
 //   export_keys_kernel (tests only): rebuilds the reference's 64-bit tile|depth keys.
 #include "pg_common.cuh"
+#include "tile_cull.h"
 
 namespace pg {
 
@@ -13,20 +15,85 @@ constexpr uint32_t E_FLAG_AGG = 1u << 30;
 constexpr uint32_t E_FLAG_INCL = 2u << 30;
 constexpr uint32_t E_VAL_MASK = (1u << 30) - 1;
 
+struct EmitSmem {
+    float4 ga[EMIT_CHUNK];  // x, y, conic.x, conic.y
+    ushort4 rect[EMIT_CHUNK];
+    float2 gb[EMIT_CHUNK];  // conic.z, cut
+    uint32_t g[EMIT_CHUNK];
+    uint32_t cnt[EMIT_CHUNK];
+    uint32_t off[EMIT_CHUNK];
+    uint32_t hist[2][RADIX];
+    uint32_t rowpre[8][32];
+    short2 rowrun[8][32];
+    uint32_t scan[8];
+    uint32_t chunk, base;
+};
+
+constexpr int EMIT_SMALL = 16;  // entries with at most this many pairs are written by their own thread
+
+// One stored pair.  flag: the tile cannot receive a contribution (KEEP_ALL lists only).
+// The digit histograms of the two tile-sort passes are accumulated in shared memory (s_hist[0]: low
+// digit, s_hist[1]: high digit) and flushed once per CTA; per-tile ranges come from the sorted keys.
+// COOP: called by a converged warp whose lanes hold consecutive pairs of ONE Gaussian — the high digit
+// is then almost always warp-uniform and is added once per warp instead of 32 same-address atomics.
+template <bool COOP>
+__device__ __forceinline__ void emit_pair(bool valid, uint32_t dst, uint32_t tile, uint32_t g, bool flag,
+                                          uint32_t n_env, int bits_lo, uint32_t* __restrict__ tkeys,
+                                          uint32_t* __restrict__ tvals, uint32_t* __restrict__ tile_obj_count,
+                                          uint32_t (*s_hist)[RADIX]) {
+    const uint32_t dlo = tile & ((1u << bits_lo) - 1u), dhi = tile >> bits_lo;
+    if (valid) {
+        tkeys[dst] = tile;
+        tvals[dst] = flag ? (g | PG_CULL_FLAG) : g;
+        atomicAdd(&s_hist[0][dlo], 1u);
+        if (g >= n_env && !flag) atomicAdd(&tile_obj_count[tile], 1u);
+    }
+    if (COOP) {
+        const uint32_t vm = __ballot_sync(0xffffffffu, valid);
+        if (vm) {
+            const int leader = __ffs(vm) - 1;
+            const uint32_t d0 = __shfl_sync(0xffffffffu, dhi, leader);
+            if (__all_sync(0xffffffffu, !valid || dhi == d0)) {
+                if ((int)(threadIdx.x & 31) == leader) atomicAdd(&s_hist[1][d0], (uint32_t)__popc(vm));
+            } else if (valid) {
+                atomicAdd(&s_hist[1][dhi], 1u);
+            }
+        }
+    } else if (valid) {
+        atomicAdd(&s_hist[1][dhi], 1u);
+    }
+}
+
+// KEEP_ALL = false (default): only (tile, Gaussian) pairs that can contribute are stored — per tile a
+//            subsequence, in the same order, of the reference's list.
+// KEEP_ALL = true : every tile of every rectangle is stored exactly as the reference's duplicateWithKeys
+//            does (pairs that cannot contribute carry PG_CULL_FLAG): pg_export_binning / n_contrib parity.
+// Phases: (0) gather the chunk's 1024 depth-ordered entries into shared memory; (A) one thread per
+// entry counts its pairs with the closed-form tile-row test of tile_cull.h; (B) CTA scan + decoupled
+// look-back -> output offsets; (C1) entries with <= EMIT_SMALL pairs are written by their own thread,
+// (C2) larger ones by their whole warp, lanes over pairs (coalesced), rows found by binary search.
+template <bool KEEP_ALL>
 __global__ void __launch_bounds__(256)
 emit_kernel(const uint32_t* __restrict__ sorted_dkey, const uint32_t* __restrict__ perm,
             const ushort4* __restrict__ rects, const GeomRec* __restrict__ recs, uint32_t P, uint32_t gx,
             int W, int H, uint32_t* __restrict__ tkeys,
             uint32_t* __restrict__ tvals, uint32_t R_cap, uint32_t* __restrict__ status,
-            uint32_t* __restrict__ tile_count, uint32_t n_env, uint32_t* __restrict__ tile_obj_count,
-            Counters* __restrict__ counters) {
-    __shared__ uint32_t s_g[EMIT_CHUNK];
-    __shared__ ushort4 s_rect[EMIT_CHUNK];
-    __shared__ uint32_t s_off[EMIT_CHUNK];
-    __shared__ float4 s_ga[EMIT_CHUNK];  // x, y, conic.x, conic.y
-    __shared__ float2 s_gb[EMIT_CHUNK];  // conic.z, cut
-    __shared__ uint32_t s_scan[8];
-    __shared__ uint32_t s_chunk, s_base;
+            uint32_t* __restrict__ hist_tile /*[2][256]*/, int bits_lo, uint32_t n_env,
+            uint32_t* __restrict__ tile_obj_count, Counters* __restrict__ counters) {
+    extern __shared__ __align__(16) unsigned char emit_smem_raw[];
+    EmitSmem& sm = *reinterpret_cast<EmitSmem*>(emit_smem_raw);
+    uint32_t (*s_hist)[RADIX] = sm.hist;
+    uint32_t* s_g = sm.g;
+    ushort4* s_rect = sm.rect;
+    uint32_t* s_cnt = sm.cnt;
+    uint32_t* s_off = sm.off;
+    float4* s_ga = sm.ga;
+    float2* s_gb = sm.gb;
+    uint32_t (*s_rowpre)[32] = sm.rowpre;
+    short2 (*s_rowrun)[32] = sm.rowrun;
+    uint32_t* s_scan = sm.scan;
+    uint32_t& s_chunk = sm.chunk;
+    uint32_t& s_base = sm.base;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) s_chunk = atomicAdd(&counters->tile_counter[4], 1u);
@@ -34,9 +101,9 @@ emit_kernel(const uint32_t* __restrict__ sorted_dkey, const uint32_t* __restrict
     const uint32_t chunk = s_chunk;
     const uint32_t num_chunks = (P + EMIT_CHUNK - 1) / EMIT_CHUNK;
     if (chunk >= num_chunks) return;
+    for (int i = tid; i < 2 * RADIX; i += 256) (&s_hist[0][0])[i] = 0;
 
-    // blocked: thread owns 4 consecutive sorted positions
-    uint32_t tt[4], local = 0;
+    // ---- (0) gather: thread owns 4 consecutive sorted positions (blocked, the scan order)
     const uint32_t s0 = chunk * EMIT_CHUNK + tid * 4;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -50,12 +117,37 @@ emit_kernel(const uint32_t* __restrict__ sorted_dkey, const uint32_t* __restrict
             s_ga[tid * 4 + j] = ra;
             s_gb[tid * 4 + j] = make_float2(rb.x, rb.w);
         }
-        tt[j] = (uint32_t)(r.z - r.x) * (uint32_t)(r.w - r.y);
         s_g[tid * 4 + j] = g;
         s_rect[tid * 4 + j] = r;
-        local += tt[j];
     }
-    // block exclusive scan of `local`
+    // ---- (A) count
+    uint32_t local = 0;
+    unsigned long long local_full = 0;
+#pragma unroll 1
+    for (int j = 0; j < 4; ++j) {
+        const int q = tid * 4 + j;
+        const ushort4 r = s_rect[q];
+        const uint32_t n = (uint32_t)(r.z - r.x) * (uint32_t)(r.w - r.y);
+        uint32_t cnt = n;
+        if (!KEEP_ALL && n > 0) {
+            const float4 ga = s_ga[q];
+            const float2 gb = s_gb[q];
+            const CullGauss cg = cull_setup(ga.x, ga.y, ga.z, ga.w, gb.x, gb.y);
+            cnt = 0;
+            for (int ty = r.y; ty < r.w; ++ty) {
+                int ta, tb;
+                cnt += (uint32_t)cull_row_run(cg, ty, r.x, r.z, W, H, &ta, &tb);
+            }
+        }
+        s_cnt[q] = cnt;
+        local += cnt;
+        local_full += n;
+    }
+    // the reference's R = sum of all rectangle areas (what pg_status.num_rendered reports)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) local_full += __shfl_xor_sync(0xffffffffu, local_full, o);
+    if (lane == 0 && local_full) atomicAdd(&counters->rendered_full, local_full);
+    // ---- (B) block exclusive scan of `local`
     uint32_t x = local;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -104,7 +196,6 @@ emit_kernel(const uint32_t* __restrict__ sorted_dkey, const uint32_t* __restrict
             s_base = prev;
             if (chunk == num_chunks - 1) {
                 uint64_t R = (uint64_t)prev + total;
-                counters->num_rendered = (uint32_t)min(R, (uint64_t)0xFFFFFFFFu);
                 counters->sort_n = (uint32_t)min(R, (uint64_t)R_cap);
                 if (R > R_cap) counters->overflow = 1;
             }
@@ -112,108 +203,134 @@ emit_kernel(const uint32_t* __restrict__ sorted_dkey, const uint32_t* __restrict
     }
     __syncthreads();
     const uint32_t base = s_base;
-    uint32_t o = base + excl;
+    {
+        uint32_t o = base + excl;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        s_off[tid * 4 + j] = o;
-        o += tt[j];
+        for (int j = 0; j < 4; ++j) {
+            s_off[tid * 4 + j] = o;
+            o += s_cnt[tid * 4 + j];
+        }
     }
-    __syncthreads();
-    // warp w expands Gaussians [w*128, w*128+128): lanes over the tiles of one rectangle
-    for (int q = warp * 128; q < warp * 128 + 128; ++q) {
+    // ---- (C1) small entries: own thread, tile rows in order (y outer, x inner = the reference's order)
+#pragma unroll 1
+    for (int j = 0; j < 4; ++j) {
+        const int q = tid * 4 + j;
+        const uint32_t cnt = s_cnt[q];
+        if (cnt == 0 || cnt > (uint32_t)EMIT_SMALL) continue;
         const ushort4 r = s_rect[q];
-        const uint32_t w_ = r.z - r.x, h_ = r.w - r.y;
-        const uint32_t n = w_ * h_;
-        if (n == 0) continue;
         const uint32_t g = s_g[q];
-        const uint32_t off = s_off[q];
         const float4 ga = s_ga[q];
         const float2 gb = s_gb[q];
-        const float inv = __frcp_rn((float)w_);
-        for (uint32_t t = lane; t < n; t += 32) {
-            uint32_t row = (uint32_t)__float2uint_rz(((float)t + 0.5f) * inv);
-            int rem = (int)t - (int)(row * w_);
-            if (rem < 0) { --row; rem += (int)w_; }
-            else if (rem >= (int)w_) { ++row; rem -= (int)w_; }
-            const uint32_t tyi = r.y + row, txi = r.x + (uint32_t)rem;
-            const uint32_t tile = tyi * gx + txi;
-            const uint32_t dst = off + t;
-            if (dst < R_cap) {
-                // can this Gaussian reach alpha >= 1/255 at any pixel centre of the tile?
-                const float x0 = (float)(txi * PG_TILE), y0 = (float)(tyi * PG_TILE);
-                const float x1 = (float)min((int)(txi * PG_TILE + PG_TILE - 1), W - 1);
-                const float y1 = (float)min((int)(tyi * PG_TILE + PG_TILE - 1), H - 1);
-                const bool culled = block_culled(ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, x0, x1, y0, y1);
-                tkeys[dst] = tile;
-                tvals[dst] = culled ? (g | PG_CULL_FLAG) : g;
-                atomicAdd(&tile_count[tile], 1u);
-                if (g >= n_env && !culled) atomicAdd(&tile_obj_count[tile], 1u);
+        const CullGauss cg = cull_setup(ga.x, ga.y, ga.z, ga.w, gb.x, gb.y);
+        uint32_t dst = s_off[q];
+        for (int ty = r.y; ty < r.w; ++ty) {
+            int ta, tb;
+            cull_row_run(cg, ty, r.x, r.z, W, H, &ta, &tb);
+            const int xa = KEEP_ALL ? (int)r.x : ta, xb = KEEP_ALL ? (int)r.z : tb;
+            for (int tx = xa; tx < xb; ++tx, ++dst)
+                emit_pair<false>(dst < R_cap, dst, (uint32_t)ty * gx + (uint32_t)tx, g, KEEP_ALL && !(tx >= ta && tx < tb),
+                                 n_env, bits_lo, tkeys, tvals, tile_obj_count, s_hist);
+        }
+    }
+    __syncthreads();  // s_off of every entry is visible to its warp mates
+    // ---- (C2) large entries: the whole warp, lanes over pairs
+#pragma unroll 1
+    for (int j = 0; j < 4; ++j) {
+        uint32_t big = __ballot_sync(0xffffffffu, s_cnt[tid * 4 + j] > (uint32_t)EMIT_SMALL);
+        while (big) {
+            const int src = __ffs(big) - 1;
+            big &= big - 1;
+            const int q = (warp * 32 + src) * 4 + j;
+            const ushort4 r = s_rect[q];
+            const uint32_t g = s_g[q];
+            const float4 ga = s_ga[q];
+            const float2 gb = s_gb[q];
+            const CullGauss cg = cull_setup(ga.x, ga.y, ga.z, ga.w, gb.x, gb.y);
+            uint32_t off = s_off[q];
+            const int rows = r.w - r.y;
+            for (int row0 = 0; row0 < rows; row0 += 32) {
+                const int row = row0 + lane;
+                int ta = r.x, tb = r.x;
+                uint32_t len = 0;
+                if (row < rows) {
+                    const int c = cull_row_run(cg, r.y + row, r.x, r.z, W, H, &ta, &tb);
+                    len = KEEP_ALL ? (uint32_t)(r.z - r.x) : (uint32_t)c;
+                }
+                uint32_t incl = len;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += y;
+                }
+                const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
+                s_rowpre[warp][lane] = incl - len;
+                s_rowrun[warp][lane] = make_short2((short)ta, (short)tb);
+                __syncwarp();
+                for (uint32_t p0 = 0; p0 < tot; p0 += 32) {
+                    const uint32_t p = p0 + lane;
+                    const bool valid = p < tot && off + p < R_cap;
+                    // largest i with rowpre[i] <= p (its row is non-empty)
+                    int i = 0;
+#pragma unroll
+                    for (int step = 16; step > 0; step >>= 1)
+                        if (s_rowpre[warp][i + step] <= p) i += step;
+                    const short2 run = s_rowrun[warp][i];
+                    const int col = (int)(p - s_rowpre[warp][i]);
+                    const int tx = (KEEP_ALL ? (int)r.x : (int)run.x) + col;
+                    const int ty = r.y + row0 + i;
+                    emit_pair<true>(valid, off + p, (uint32_t)ty * gx + (uint32_t)tx, g,
+                                    KEEP_ALL && !(tx >= run.x && tx < run.y), n_env, bits_lo, tkeys, tvals,
+                                    tile_obj_count, s_hist);
+                }
+                off += tot;
+                __syncwarp();
             }
         }
+    }
+    // ---- flush the CTA's digit histograms
+    __syncthreads();
+    for (int i = tid; i < 2 * RADIX; i += 256) {
+        const uint32_t c = (&s_hist[0][0])[i];
+        if (c) atomicAdd(&hist_tile[i], c);
     }
 }
 
-// ranges + digit bases from per-tile counts. One CTA, 1024 threads.
-__global__ void __launch_bounds__(1024)
-tile_scan_kernel(const uint32_t* __restrict__ tile_count, uint32_t tiles, int bits_lo, int bits_hi,
-                 uint2* __restrict__ ranges, uint32_t* __restrict__ bins /*[2][256]*/) {
-    __shared__ uint32_t s_lo[RADIX], s_hi[RADIX];
-    __shared__ uint32_t s_scan[32];
-    __shared__ uint32_t s_carry;
+// exclusive scans of the two tile-sort digit histograms -> bases; finalises pg_status.num_rendered.
+// One CTA of 512 threads: warps 0..7 scan the low-digit row, warps 8..15 the high-digit row.
+__global__ void __launch_bounds__(512)
+tile_scan_kernel(const uint32_t* __restrict__ hist /*[2][256]*/, uint32_t* __restrict__ bins /*[2][256]*/,
+                 Counters* __restrict__ counters) {
+    __shared__ uint32_t s_scan[16];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid < RADIX) { s_lo[tid] = 0; s_hi[tid] = 0; }
-    if (tid == 0) s_carry = 0;
+    if (tid == 0) {
+        const unsigned long long full = counters->rendered_full;  // emit has finished (stream order)
+        counters->num_rendered = full > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)full;
+    }
+    uint32_t v = hist[tid], x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    if (lane == 31) s_scan[warp] = x;
     __syncthreads();
-    const uint32_t mask_lo = (1u << bits_lo) - 1u;
-    for (uint32_t b = 0; b < tiles; b += 1024) {
-        uint32_t t = b + tid;
-        uint32_t c = t < tiles ? tile_count[t] : 0u;
-        uint32_t x = c;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
-            if (lane >= o) x += y;
-        }
-        if (lane == 31) s_scan[warp] = x;
-        __syncthreads();
-        uint32_t wb = 0, tot = 0;
-        for (int w = 0; w < 32; ++w) {
-            uint32_t v = s_scan[w];
-            if (w < warp) wb += v;
-            tot += v;
-        }
-        uint32_t start = s_carry + wb + x - c;
-        if (t < tiles) {
-            ranges[t] = c ? make_uint2(start, start + c) : make_uint2(0u, 0u);
-            if (c) {
-                atomicAdd(&s_lo[t & mask_lo], c);
-                atomicAdd(&s_hi[t >> bits_lo], c);
-            }
-        }
-        __syncthreads();
-        if (tid == 0) s_carry += tot;
-        __syncthreads();
+    uint32_t wb = 0;
+    const int w0 = tid < RADIX ? 0 : 8;
+    for (int w = w0; w < warp; ++w) wb += s_scan[w];
+    bins[tid] = wb + x - v;
+}
+
+// identifyTileRanges on the sorted tile ids: ranges[tile] = [first, last + 1); tiles without pairs keep
+// the (0, 0) of the per-frame clear.  n lives on the device (stored pairs).
+__global__ void __launch_bounds__(256)
+ranges_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ n_ptr, uint2* __restrict__ ranges) {
+    const uint32_t n = *n_ptr;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint32_t k = keys[i];
+        if (i == 0 || keys[i - 1] != k) ranges[k].x = i;
+        if (i == n - 1 || keys[i + 1] != k) ranges[k].y = i + 1;
     }
-    // exclusive scans of the two 256-bin histograms: warps 0..7 -> lo, warps 8..15 -> hi
-    if (tid < 2 * RADIX) {
-        uint32_t* h = tid < RADIX ? s_lo : s_hi;
-        int i = tid & (RADIX - 1);
-        uint32_t v = h[i], x = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
-            if (lane >= o) x += y;
-        }
-        if (lane == 31) s_scan[warp] = x;
-        __syncwarp();
-        // per-histogram warp totals live in s_scan[0..7] / s_scan[8..15]
-        asm volatile("bar.sync 1, 512;");
-        uint32_t wb = 0;
-        int w0 = tid < RADIX ? 0 : 8;
-        for (int w = w0; w < warp; ++w) wb += s_scan[w];
-        bins[tid] = wb + x - v;
-    }
-    (void)bits_hi;
 }
 
 // tests only: keys[i] = (tile << 32) | depth_bits[point_list[i]], tile from ranges
@@ -232,22 +349,40 @@ __global__ void export_keys_kernel(const uint2* __restrict__ ranges, uint32_t ti
     }
 }
 
-int launch_emit(const uint32_t* sorted_dkey, const uint32_t* perm, const ushort4* rects, const GeomRec* recs,
+int launch_emit(bool keep_all, const uint32_t* sorted_dkey, const uint32_t* perm, const ushort4* rects, const GeomRec* recs,
                 uint32_t P, uint32_t gx, int W, int H, uint32_t* tkeys, uint32_t* tvals, uint32_t R_cap, uint32_t* status,
-                uint32_t* tile_count, uint32_t n_env, uint32_t* tile_obj_count, Counters* counters,
+                uint32_t* hist_tile, int bits_lo, uint32_t n_env, uint32_t* tile_obj_count, Counters* counters,
                 cudaStream_t stream) {
     uint32_t chunks = (P + EMIT_CHUNK - 1) / EMIT_CHUNK;
     if (chunks == 0) return PG_OK;
-    emit_kernel<<<chunks, 256, 0, stream>>>(sorted_dkey, perm, rects, recs, P, gx, W, H, tkeys, tvals, R_cap, status,
-                                            tile_count, n_env, tile_obj_count, counters);
+    static bool attr_set = false;
+    if (!attr_set) {
+        PG_CUDA_CHECK(cudaFuncSetAttribute(emit_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EmitSmem)));
+        PG_CUDA_CHECK(cudaFuncSetAttribute(emit_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EmitSmem)));
+        attr_set = true;
+    }
+    if (keep_all)
+        emit_kernel<true><<<chunks, 256, sizeof(EmitSmem), stream>>>(sorted_dkey, perm, rects, recs, P, gx, W, H, tkeys, tvals, R_cap, status,
+                                                      hist_tile, bits_lo, n_env, tile_obj_count, counters);
+    else
+        emit_kernel<false><<<chunks, 256, sizeof(EmitSmem), stream>>>(sorted_dkey, perm, rects, recs, P, gx, W, H, tkeys, tvals, R_cap, status,
+                                                       hist_tile, bits_lo, n_env, tile_obj_count, counters);
     count_launch(1);
     PG_CUDA_CHECK(cudaGetLastError());
     return PG_OK;
 }
 
-int launch_tile_scan(const uint32_t* tile_count, uint32_t tiles, int bits_lo, int bits_hi, uint2* ranges,
-                     uint32_t* bins, cudaStream_t stream) {
-    tile_scan_kernel<<<1, 1024, 0, stream>>>(tile_count, tiles, bits_lo, bits_hi, ranges, bins);
+int launch_tile_scan(const uint32_t* hist_tile, uint32_t* bins, Counters* counters, cudaStream_t stream) {
+    tile_scan_kernel<<<1, 512, 0, stream>>>(hist_tile, bins, counters);
+    count_launch(1);
+    PG_CUDA_CHECK(cudaGetLastError());
+    return PG_OK;
+}
+
+int launch_ranges(const uint32_t* sorted_tile_keys, const uint32_t* n_ptr, uint32_t max_n, uint2* ranges, cudaStream_t stream) {
+    if (max_n == 0) return PG_OK;
+    const uint32_t blocks = min((max_n + 255u) / 256u, (uint32_t)(PG_SM_COUNT * 16));
+    ranges_kernel<<<blocks, 256, 0, stream>>>(sorted_tile_keys, n_ptr, ranges);
     count_launch(1);
     PG_CUDA_CHECK(cudaGetLastError());
     return PG_OK;

@@ -5,9 +5,10 @@
 //   preprocess_kernel                           A.1-A.5, writes GeomRec / depth key / tile rect / radii
 //   hist_kernel + scan_rows_kernel              digit histograms of the depth keys (4 x 8 bit)
 //   onesweep_pass_kernel x4                     P Gaussians by depth (stable; values = index)
-//   emit_kernel                                 scan(tiles_touched) + (tile, index) pairs in depth order
-//   tile_scan_kernel                            ranges[tile] + digit bases of the tile sort
-//   onesweep_pass_kernel x2                     R pairs by tile id (stable)  => reference order
+//   emit_kernel                                 tile-row culling + scan + (tile, index) pairs in depth order
+//   tile_scan_kernel                            digit bases of the tile sort
+//   onesweep_pass_kernel x2                     stored pairs by tile id (stable)  => reference order
+//   ranges_kernel                               ranges[tile] from the sorted tile ids
 //   composite_kernel | composite_masks_kernel   A.7 (+ fused K+3 passes)
 //
 // Nothing here synchronises with the host: R stays on the device (grids are sized by the pair
@@ -44,12 +45,12 @@ int launch_onesweep_pass(bool iota, bool write_keys, const uint32_t* keys_in, ui
                          uint32_t n_imm, uint32_t max_tiles, int begin_bit, int num_bits,
                          const uint32_t* bin_base, uint32_t* status, uint32_t* ticket,
                          cudaStream_t stream);
-int launch_emit(const uint32_t* sorted_dkey, const uint32_t* perm, const ushort4* rects, const GeomRec* recs,
+int launch_emit(bool keep_all, const uint32_t* sorted_dkey, const uint32_t* perm, const ushort4* rects, const GeomRec* recs,
                 uint32_t P, uint32_t gx, int W, int H, uint32_t* tkeys, uint32_t* tvals, uint32_t R_cap, uint32_t* status,
-                uint32_t* tile_count, uint32_t n_env, uint32_t* tile_obj_count, Counters* counters,
+                uint32_t* hist_tile, int bits_lo, uint32_t n_env, uint32_t* tile_obj_count, Counters* counters,
                 cudaStream_t stream);
-int launch_tile_scan(const uint32_t* tile_count, uint32_t tiles, int bits_lo, int bits_hi, uint2* ranges,
-                     uint32_t* bins, cudaStream_t stream);
+int launch_tile_scan(const uint32_t* hist_tile, uint32_t* bins, Counters* counters, cudaStream_t stream);
+int launch_ranges(const uint32_t* sorted_tile_keys, const uint32_t* n_ptr, uint32_t max_n, uint2* ranges, cudaStream_t stream);
 int launch_export_keys(const uint2* ranges, uint32_t tiles, const uint32_t* point_list, const GeomRec* recs,
                        uint64_t* keys, uint32_t* point_list_out, uint32_t* ranges_out, cudaStream_t stream);
 int launch_pose(int K, const int32_t* first, const PoseDev* poses_dev, const pg_canonical* canon,
@@ -114,7 +115,7 @@ static int check_common(const pg_raster_settings* s, const pg_gaussians* g, uint
 
 // everything up to (and including) the tile sort
 static int run_binning(const pg_raster_settings* s, const pg_gaussians* g, const pg_object_table* objs,
-                       int32_t* radii, void* ws, const Layout& L, uint64_t R_cap, cudaStream_t stream) {
+                       int32_t* radii, void* ws, const Layout& L, uint64_t R_cap, bool keep_all, cudaStream_t stream) {
     const int P = g->P;
     const int W = s->image_width, H = s->image_height;
     const uint32_t gx = (W + PG_TILE - 1) / PG_TILE;
@@ -147,33 +148,36 @@ static int run_binning(const pg_raster_settings* s, const pg_gaussians* g, const
     if (s->debug & 1) PG_CUDA_CHECK(cudaStreamSynchronize(stream));
     // after 4 passes the sorted keys/permutation are back in (dkey_a, dval_a) == (ka, va)
     const uint32_t n_env = (objs && objs->num_objects > 0) ? (uint32_t)objs->first[0] : (uint32_t)P;
-    rc = launch_emit(ka, va, at<ushort4>(ws, L.rect), at<GeomRec>(ws, L.recs), (uint32_t)P, gx, W, H,
-                     at<uint32_t>(ws, L.tkey_a),
-                     at<uint32_t>(ws, L.tval_a), (uint32_t)R_cap, at<uint32_t>(ws, L.status_emit),
-                     at<uint32_t>(ws, L.tile_count), n_env, at<uint32_t>(ws, L.tile_obj_count), counters, stream);
-    if (rc) return rc;
-    prof_mark(4, stream);
     const int bits = tile_bits(L.tiles);
     const int bits_lo = (bits + 1) / 2, bits_hi = bits - bits_lo;
-    rc = launch_tile_scan(at<uint32_t>(ws, L.tile_count), L.tiles, bits_lo, bits_hi, at<uint2>(ws, L.ranges),
-                          at<uint32_t>(ws, L.bins_tile), stream);
+    rc = launch_emit(keep_all, ka, va, at<ushort4>(ws, L.rect), at<GeomRec>(ws, L.recs), (uint32_t)P, gx, W, H,
+                     at<uint32_t>(ws, L.tkey_a),
+                     at<uint32_t>(ws, L.tval_a), (uint32_t)R_cap, at<uint32_t>(ws, L.status_emit),
+                     at<uint32_t>(ws, L.hist_tile), bits_lo, n_env, at<uint32_t>(ws, L.tile_obj_count), counters, stream);
+    if (rc) return rc;
+    prof_mark(4, stream);
+    rc = launch_tile_scan(at<uint32_t>(ws, L.hist_tile), at<uint32_t>(ws, L.bins_tile), counters, stream);
     if (rc) return rc;
     prof_mark(5, stream);
     uint32_t* bins = at<uint32_t>(ws, L.bins_tile);
     uint32_t* stt = at<uint32_t>(ws, L.status_tile);
     const bool two = bits_hi > 0;
-    // pass lo: a -> b ; pass hi: b -> a (values only).  With a single pass the result lands in b.
-    rc = launch_onesweep_pass(false, two, at<uint32_t>(ws, L.tkey_a), at<uint32_t>(ws, L.tkey_b),
+    // pass lo: a -> b ; pass hi: b -> a.  With a single pass the result lands in b.  The sorted tile
+    // ids are kept: ranges_kernel finds the tile boundaries in them.
+    rc = launch_onesweep_pass(false, true, at<uint32_t>(ws, L.tkey_a), at<uint32_t>(ws, L.tkey_b),
                               at<uint32_t>(ws, L.tval_a), at<uint32_t>(ws, L.tval_b), &counters->sort_n, 0,
                               L.tilesR, 0, bits_lo, bins, stt, &counters->tile_counter[5], stream);
     if (rc) return rc;
     if (two) {
-        rc = launch_onesweep_pass(false, false, at<uint32_t>(ws, L.tkey_b), at<uint32_t>(ws, L.tkey_a),
+        rc = launch_onesweep_pass(false, true, at<uint32_t>(ws, L.tkey_b), at<uint32_t>(ws, L.tkey_a),
                                   at<uint32_t>(ws, L.tval_b), at<uint32_t>(ws, L.tval_a), &counters->sort_n, 0,
                                   L.tilesR, bits_lo, bits_hi, bins + RADIX, stt + (size_t)L.tilesR * RADIX,
                                   &counters->tile_counter[6], stream);
         if (rc) return rc;
     }
+    rc = launch_ranges(at<uint32_t>(ws, two ? L.tkey_a : L.tkey_b), &counters->sort_n, (uint32_t)R_cap,
+                       at<uint2>(ws, L.ranges), stream);
+    if (rc) return rc;
     prof_mark(6, stream);
     if (s->debug & 1) PG_CUDA_CHECK(cudaStreamSynchronize(stream));
     return PG_OK;
@@ -207,7 +211,10 @@ int pg_rasterize_forward(const pg_raster_settings* s, const pg_gaussians* g, con
     if (!out || !out->color || !out->radii || !out->depth || !ws) { set_error("null output/workspace"); return PG_ERR_INVALID; }
     Layout L = make_layout(g->P, s->image_width, s->image_height, pair_capacity);
     if (ws_bytes < L.total) { set_error("workspace too small: %zu < %zu", ws_bytes, L.total); return PG_ERR_WORKSPACE; }
-    rc = run_binning(s, g, nullptr, out->radii, ws, L, pair_capacity, stream);
+    // the reference's complete pair lists are kept when asked for (debug bit 2) or needed (n_contrib
+    // is a position in the reference's list)
+    const bool keep_all = (s->debug & 4) != 0 || out->n_contrib != nullptr;
+    rc = run_binning(s, g, nullptr, out->radii, ws, L, pair_capacity, keep_all, stream);
     if (rc) return rc;
     rc = launch_composite_from_abi(at<uint2>(ws, L.ranges), sorted_point_list(ws, L), at<GeomRec>(ws, L.recs),
                                    s->image_width, s->image_height, s->bg, out, nullptr, nullptr,
@@ -235,7 +242,7 @@ int pg_render_composed(const pg_raster_settings* s, const pg_gaussians* g, const
     }
     Layout L = make_layout(g->P, s->image_width, s->image_height, pair_capacity);
     if (ws_bytes < L.total) { set_error("workspace too small: %zu < %zu", ws_bytes, L.total); return PG_ERR_WORKSPACE; }
-    rc = run_binning(s, g, objs, out->radii, ws, L, pair_capacity, stream);
+    rc = run_binning(s, g, objs, out->radii, ws, L, pair_capacity, (s->debug & 4) != 0, stream);
     if (rc) return rc;
     const uint32_t n_env = objs->num_objects > 0 ? (uint32_t)objs->first[0] : (uint32_t)g->P;
     if (out->silhouette && objs->num_colors > 0)

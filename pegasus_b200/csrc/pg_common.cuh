@@ -78,12 +78,13 @@ struct __align__(16) GeomRec {
 
 // ---- status block at the head of the workspace ------------------------------------------------
 struct Counters {
-    uint32_t num_rendered;   // R
+    uint32_t num_rendered;   // the reference's R (every tile of every rectangle), saturating
     uint32_t overflow;
     uint32_t num_visible;
-    uint32_t sort_n;         // min(R, pair capacity): what the tile sort processes
+    uint32_t sort_n;         // pairs stored = min(pairs kept by the binning stage, pair capacity): what the tile sort processes
     uint32_t tile_counter[8];  // dynamic CTA-tile tickets: [0..3] depth-sort passes, [4] emit, [5..6] tile-sort passes
     unsigned long long stats[4];  // debug&2: pairs evaluated, pairs reaching exp, pairs blended (all chains), spare
+    unsigned long long rendered_full;  // sum of all tile-rectangle areas = the reference's num_rendered
 };
 
 // Onesweep tile geometry
@@ -98,14 +99,14 @@ struct Layout {
     size_t counters;     // Counters
     size_t zero_begin;   // [zero_begin, zero_end) is cleared at the start of every forward
     size_t hist_depth;   // u32[4][256]  depth-sort digit histograms -> exclusive bases
-    size_t tile_count;   // u32[tiles]
+    size_t hist_tile;    // u32[2][256] digit histograms of the two tile-sort passes
+    size_t ranges;       // uint2[tiles] (cleared: tiles without pairs keep (0,0))
     size_t tile_obj_count; // u32[tiles] pairs whose Gaussian belongs to an object
     size_t status_depth; // u32[4][tilesP][256]
     size_t status_emit;  // u32[chunks]
     size_t status_tile;  // u32[2][tilesR][256]
     size_t zero_end;
     size_t bins_tile;    // u32[2][256] exclusive bases of the two tile-sort passes
-    size_t ranges;       // uint2[tiles]
     size_t recs;         // GeomRec[P]
     size_t rect;         // ushort4[P]
     size_t dkey_a, dkey_b, dval_a, dval_b;  // u32[P] depth-sort ping-pong
@@ -130,14 +131,14 @@ inline Layout make_layout(int P, int W, int H, uint64_t R_cap) {
     L.counters = o; o = align_up(o + sizeof(Counters));
     L.zero_begin = L.counters;
     L.hist_depth = o; o = align_up(o + 4 * RADIX * 4);
-    L.tile_count = o; o = align_up(o + (size_t)L.tiles * 4);
+    L.hist_tile = o; o = align_up(o + 2 * RADIX * 4);
+    L.ranges = o; o = align_up(o + (size_t)L.tiles * 8);
     L.tile_obj_count = o; o = align_up(o + (size_t)L.tiles * 4);
     L.status_depth = o; o = align_up(o + (size_t)4 * L.tilesP * RADIX * 4);
     L.status_emit = o; o = align_up(o + (size_t)L.chunks * 4);
     L.status_tile = o; o = align_up(o + (size_t)2 * L.tilesR * RADIX * 4);
     L.zero_end = o;
     L.bins_tile = o; o = align_up(o + 2 * RADIX * 4);
-    L.ranges = o; o = align_up(o + (size_t)L.tiles * 8);
     L.recs = o; o = align_up(o + (size_t)P * sizeof(GeomRec));
     L.rect = o; o = align_up(o + (size_t)P * 8);
     L.dkey_a = o; o = align_up(o + (size_t)P * 4);

@@ -111,8 +111,12 @@ def make_settings_struct(rs: GaussianRasterizationSettings, device, keep: list) 
 
 def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
                         raster_settings: GaussianRasterizationSettings, want_aux: bool = False,
-                        sync_check: bool = True):
-    """Forward rasterization through the C ABI.  Returns (color, radii, depth, aux)."""
+                        sync_check: bool = True, reference_lists: bool = False):
+    """Forward rasterization through the C ABI.  Returns (color, radii, depth, aux).
+
+    reference_lists=True keeps the reference's complete (tile, Gaussian) pair lists (debug bit 2 of the
+    C ABI) so that aux["n_contrib"] and pg_export_binning reproduce the reference's binning state; by
+    default only the pairs that can contribute are stored and sorted (identical images)."""
     if not means3D.is_cuda:
         raise RuntimeError("means3D must be a CUDA tensor: pegasus_b200 has no CPU path")
     device = means3D.device
@@ -120,6 +124,8 @@ def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales,
     keep = []
     with torch.cuda.device(device):
         s = make_settings_struct(raster_settings, device, keep)
+        if reference_lists:
+            s.debug |= 4
         P = int(means3D.shape[0])
         H, W = int(raster_settings.image_height), int(raster_settings.image_width)
         color = torch.zeros((3, H, W), dtype=torch.float32, device=device)
@@ -150,8 +156,10 @@ def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales,
         out.color, out.radii, out.depth = color.data_ptr(), radii.data_ptr(), depth.data_ptr()
         if want_aux:
             aux["final_T"] = torch.empty((H, W), dtype=torch.float32, device=device)
-            aux["n_contrib"] = torch.empty((H, W), dtype=torch.int32, device=device)
-            out.final_T, out.n_contrib = aux["final_T"].data_ptr(), aux["n_contrib"].data_ptr()
+            out.final_T = aux["final_T"].data_ptr()
+            if reference_lists:
+                aux["n_contrib"] = torch.empty((H, W), dtype=torch.int32, device=device)
+                out.n_contrib = aux["n_contrib"].data_ptr()
         ws = workspace_for(device)
         stream = torch.cuda.current_stream(device)
         cap = default_pair_capacity(P, W, H)
@@ -168,11 +176,13 @@ def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales,
             R, overflow = int(ws.status_host[0]) & 0xFFFFFFFF, int(ws.status_host[1])
             aux["num_rendered"] = R
             aux["num_visible"] = int(ws.status_host[2])
+            aux["num_stored"] = int(ws.status_host[3]) & 0xFFFFFFFF
             if not overflow:
                 break
-            if R >= (1 << 30):
-                raise RuntimeError(f"{R} (tile, Gaussian) pairs exceed the supported maximum of 2^30")
-            cap = int(min(max(R + R // 8, 2 * cap), 1 << 30))
+            if cap >= (1 << 30):
+                raise RuntimeError("the (tile, Gaussian) pairs exceed the supported maximum of 2^30")
+            # the stored count is not known after an overflow (R bounds it from above): grow geometrically
+            cap = int(min(max(2 * cap, 1 << 20), max(R + R // 8, 1 << 20), 1 << 30)) if R > cap else int(min(2 * cap, 1 << 30))
             _PAIR_CAPACITY_HINT[(W, H)] = cap
         aux["pair_capacity"] = cap
         return color, radii, depth, aux
@@ -180,6 +190,7 @@ def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales,
 
 class GaussianRasterizer(nn.Module):
     sync_check = True  # read back R after each call and transparently grow the workspace on overflow
+    reference_lists = False  # True: keep the reference's complete pair lists (aux["n_contrib"], export_binning)
 
     def __init__(self, raster_settings: GaussianRasterizationSettings):
         super().__init__()
@@ -210,6 +221,7 @@ class GaussianRasterizer(nn.Module):
         with torch.no_grad():
             color, radii, depth, aux = rasterize_gaussians(
                 means3D, means2D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp,
-                self.raster_settings, want_aux=True, sync_check=self.sync_check)
+                self.raster_settings, want_aux=True, sync_check=self.sync_check,
+                reference_lists=self.reference_lists)
         self.aux = aux
         return color, radii, depth

@@ -171,7 +171,8 @@ class ComposedScene:
         return out
 
     def render(self, cam, bg: torch.Tensor, masks: bool = True, out: Optional[Dict] = None, sh_degree: int = 3,
-               sync_check: bool = True, pair_capacity: Optional[int] = None, debug: int = 0) -> Dict[str, torch.Tensor]:
+               sync_check: bool = True, pair_capacity: Optional[int] = None, debug: int = 0,
+               reference_lists: bool = False) -> Dict[str, torch.Tensor]:
         """One frame: RGB + depth (+ seg render, sem-seg, visible and silhouette masks when
         masks=True) — everything the reference's K+3 passes produce (src/gs/render.py:14-129)."""
         L = _lib.load()
@@ -181,6 +182,8 @@ class ComposedScene:
         keep = []
         with torch.cuda.device(self.device):
             s = make_settings_struct(self.settings_for(cam, bg, sh_degree, debug=debug), self.device, keep)
+            if reference_lists:
+                s.debug |= 4  # keep the reference's complete pair lists (export_binning parity)
             g = _lib.Gaussians(self.P, self.means3D.data_ptr(), self.shs.data_ptr(), 16, None,
                                self.opacity.data_ptr(), self.scales.data_ptr(), self.rotations.data_ptr(), None)
             fo = _lib.FrameOutputs(out["color"].data_ptr(), out["radii"].data_ptr(), out["depth"].data_ptr(),
@@ -211,11 +214,12 @@ class ComposedScene:
                 R, overflow = int(ws.status_host[0]) & 0xFFFFFFFF, int(ws.status_host[1])
                 out["num_rendered"] = R
                 out["num_visible"] = int(ws.status_host[2])
+                out["num_stored"] = int(ws.status_host[3]) & 0xFFFFFFFF
                 if not overflow:
                     break
-                if R >= (1 << 30):
-                    raise RuntimeError(f"{R} (tile, Gaussian) pairs exceed the supported maximum of 2^30")
-                cap = int(min(max(R + R // 8, 2 * cap), 1 << 30))
+                if cap >= (1 << 30):
+                    raise RuntimeError("the (tile, Gaussian) pairs exceed the supported maximum of 2^30")
+                cap = int(min(max(2 * cap, 1 << 20), max(R + R // 8, 1 << 20), 1 << 30)) if R > cap else int(min(2 * cap, 1 << 30))
                 _PAIR_CAPACITY_HINT[(W, H)] = cap
             out["pair_capacity"] = cap
         return out
@@ -240,11 +244,12 @@ class ComposedScene:
                                     C.c_void_p(stream.cuda_stream)), "pg_read_status")
         stream.synchronize()
         return dict(num_rendered=int(ws.status_host[0]) & 0xFFFFFFFF, overflow=int(ws.status_host[1]),
-                    num_visible=int(ws.status_host[2]))
+                    num_visible=int(ws.status_host[2]), num_stored=int(ws.status_host[3]) & 0xFFFFFFFF)
 
 
 def export_binning(device, P: int, W: int, H: int, pair_capacity: int, num_rendered: int):
-    """Tests/debug: the reference's sorted 64-bit keys, point list and tile ranges of the last forward."""
+    """Tests/debug: sorted 64-bit keys, point list and tile ranges of the last forward; `num_rendered`
+    is that forward's num_stored (== the reference's R when it ran with reference_lists=True)."""
     L = _lib.load()
     device = torch.device(device)
     ws = workspace_for(device)

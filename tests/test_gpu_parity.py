@@ -24,7 +24,7 @@ def dev():
     return torch.device("cuda", 0)
 
 
-def gpu_forward(inp, ocam, bg, sh_degree=3, **kw):
+def gpu_forward(inp, ocam, bg, sh_degree=3, reference_lists=False, **kw):
     from diff_gaussian_rasterization import GaussianRasterizationSettings, GaussianRasterizer
     d = dev()
     t = lambda a: None if a is None else torch.from_numpy(np.ascontiguousarray(a)).to(d)
@@ -35,6 +35,7 @@ def gpu_forward(inp, ocam, bg, sh_degree=3, **kw):
         projmatrix=t(ocam["full_proj_transform"]), sh_degree=sh_degree, campos=t(ocam["camera_center"]),
         prefiltered=False, debug=kw.get("debug", False))
     rast = GaussianRasterizer(raster_settings=settings)
+    rast.reference_lists = reference_lists
     means3D = t(inp["means3D"])
     color, radii, depth = rast(
         means3D=means3D, means2D=torch.zeros_like(means3D), shs=t(kw.get("shs", inp.get("shs"))),
@@ -44,29 +45,57 @@ def gpu_forward(inp, ocam, bg, sh_degree=3, **kw):
     return color, radii, depth, rast.aux
 
 
+def assert_sublists(ranges_sub, plist_sub, ranges_ref, plist_ref):
+    """Per tile, the stored list must be a subsequence (same order) of the reference's list."""
+    for t in range(ranges_ref.shape[0]):
+        a = plist_sub[ranges_sub[t, 0]:ranges_sub[t, 1]]
+        b = plist_ref[ranges_ref[t, 0]:ranges_ref[t, 1]]
+        if a.size == 0:
+            continue
+        assert a.size <= b.size
+        # greedy subsequence match: Gaussian ids are unique inside a tile list
+        pos = {int(v): i for i, v in enumerate(b)}
+        idx = np.fromiter((pos.get(int(v), -1) for v in a), dtype=np.int64, count=a.size)
+        assert (idx >= 0).all() and (np.diff(idx) > 0).all(), f"tile {t}: stored list is not a subsequence"
+
+
 def check_against_oracle(inp, ocam, bg, sh_degree=3, expect_bitexact_images=True, **kw):
+    """Two GPU runs against one oracle run: (1) reference_lists=True — the binning state (64-bit keys,
+    point list, ranges, n_contrib) must equal the reference's bit for bit; (2) the default path, which
+    stores only pairs that can contribute — identical radii / R / images / final_T, and per tile a
+    subsequence of the reference's list."""
     from pegasus_b200.scene import export_binning
     ref = util.oracle_forward(inp, ocam, bg, sh_degree, **kw)
-    color, radii, depth, aux = gpu_forward(inp, ocam, bg, sh_degree, **kw)
     W, H = ocam["image_width"], ocam["image_height"]
     P = inp["means3D"].shape[0]
-    np.testing.assert_array_equal(radii.cpu().numpy(), ref["radii"])
-    assert aux["num_rendered"] == ref["num_rendered"]
-    assert aux["num_visible"] == int((ref["radii"] > 0).sum())
-    keys, plist, ranges = export_binning(dev(), P, W, H, aux["pair_capacity"], aux["num_rendered"])
-    np.testing.assert_array_equal(ranges, ref["ranges"])
-    np.testing.assert_array_equal(keys, ref["keys"])
-    np.testing.assert_array_equal(plist, ref["point_list"])
-    c, d = color.cpu().numpy(), depth.cpu().numpy()
-    assert np.abs(c - ref["color"]).max() <= RGB_TOL
     denom = np.maximum(np.abs(ref["depth"]), 1e-6)
-    assert (np.abs(d - ref["depth"]) / denom).max() <= DEPTH_RTOL
-    np.testing.assert_array_equal(aux["final_T"].cpu().numpy(), ref["final_T"])
-    np.testing.assert_array_equal(aux["n_contrib"].cpu().numpy().view(np.uint32), ref["n_contrib"])
-    if expect_bitexact_images:
-        np.testing.assert_array_equal(c, ref["color"])
-        np.testing.assert_array_equal(d, ref["depth"])
-    return ref, (color, radii, depth, aux)
+    full = None
+    for reference_lists in (True, False):
+        color, radii, depth, aux = gpu_forward(inp, ocam, bg, sh_degree, reference_lists=reference_lists, **kw)
+        np.testing.assert_array_equal(radii.cpu().numpy(), ref["radii"])
+        assert aux["num_rendered"] == ref["num_rendered"]
+        assert aux["num_visible"] == int((ref["radii"] > 0).sum())
+        keys, plist, ranges = export_binning(dev(), P, W, H, aux["pair_capacity"], aux["num_stored"])
+        if reference_lists:
+            assert aux["num_stored"] == ref["num_rendered"]
+            np.testing.assert_array_equal(ranges, ref["ranges"])
+            np.testing.assert_array_equal(keys, ref["keys"])
+            np.testing.assert_array_equal(plist, ref["point_list"])
+            np.testing.assert_array_equal(aux["n_contrib"].cpu().numpy().view(np.uint32), ref["n_contrib"])
+            full = (color, radii, depth, aux)
+        else:
+            assert aux["num_stored"] <= ref["num_rendered"] and "n_contrib" not in aux
+            assert bool((keys[1:] >= keys[:-1]).all())
+            if ref["num_rendered"] <= 3_000_000:
+                assert_sublists(ranges, plist, ref["ranges"], ref["point_list"])
+        c, d = color.cpu().numpy(), depth.cpu().numpy()
+        assert np.abs(c - ref["color"]).max() <= RGB_TOL
+        assert (np.abs(d - ref["depth"]) / denom).max() <= DEPTH_RTOL
+        np.testing.assert_array_equal(aux["final_T"].cpu().numpy(), ref["final_T"])
+        if expect_bitexact_images:
+            np.testing.assert_array_equal(c, ref["color"])
+            np.testing.assert_array_equal(d, ref["depth"])
+    return ref, full
 
 
 def test_forward_bitexact_small_640x480():
@@ -387,9 +416,9 @@ def test_full_size_properties_1080p_3M():
     c = synth.orbit_cameras(4, 1920, 1080, seed=3000)[1]
     cam = Camera(c["R"], c["T"], c["FoVx"], c["FoVy"], c["W"], c["H"])
     bg = torch.zeros(3, device="cuda")
-    out = sc.render(cam, bg)
+    out = sc.render(cam, bg, reference_lists=True)
     R = out["num_rendered"]
-    assert R > 1_000_000
+    assert R > 1_000_000 and out["num_stored"] == R
     keys, plist, ranges = export_binning("cuda:0", sc.P, 1920, 1080, out["pair_capacity"], R)
     k = torch.from_numpy(keys.view(np.int64)).cuda()
     assert bool((k[1:] >= k[:-1]).all()), "sorted keys must be non-decreasing"
@@ -412,7 +441,9 @@ def test_full_size_properties_1080p_3M():
     assert float(T.min()) >= 0.0 and float(T.max()) <= 1.0
     assert bool(torch.isfinite(out["color"]).all()) and float(out["color"].min()) >= 0.0
     first = {kk: out[kk].clone() for kk in ("color", "depth", "visible", "silhouette", "sem_seg")}
+    # the default path (only pairs that can contribute are stored) gives bit-identical products
     out2 = sc.render(cam, bg)
+    assert out2["num_rendered"] == R and 0 < out2["num_stored"] < 0.8 * R
     for kk, v in first.items():
         assert torch.equal(v, out2[kk]), kk
     # masks=False path gives the same RGB/depth
