@@ -51,9 +51,20 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// Blocking wait: try_wait with a suspend-time hint parks the warp in hardware (no issue slots burnt
+// while other warps of the SM have work) and is re-armed until the phase completes.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    if (mbar_try_wait(bar, parity)) return;
-    while (!mbar_try_wait(bar, parity)) __nanosleep(32);  // do not burn issue slots other warps need
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity), "r"(1000000u)
+        : "memory");
 }
 // 1-D TMA bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
@@ -110,11 +121,12 @@ __device__ __forceinline__ void flush_stats(unsigned long long* stats, uint32_t 
 // block, walk the hits, arrive on `empty`.  No CTA-wide barrier in the steady state; a consumer whose
 // 32 pixels are finished keeps releasing stages, the producer stops when all 8 have finished.
 constexpr int COMP_STAGES = 4;
-constexpr int COMP_BATCH = 256;
+constexpr int COMP_BATCH = 128;
 constexpr int COMP_THREADS = 288;
 
-constexpr int COMP_IDCHUNK = 512;
-constexpr int COMP_PEND = 1024;
+constexpr int COMP_IDCHUNK = 256;
+constexpr int COMP_PEND = 512;
+static_assert(COMP_BATCH - 1 + COMP_IDCHUNK <= COMP_PEND, "pending ring too small");
 
 struct CompSmem {
     GeomRec rec[COMP_STAGES][COMP_BATCH];
@@ -157,7 +169,7 @@ __device__ __forceinline__ float expf_exact_nz(float x) {
 // rasterizer produces for object k's flat SH), then Tk[K][256] — the standalone transmittance of
 // object k at each of the tile's 256 pixels (silhouette chains), slot = warp * 32 + lane.
 template <bool MASKS, bool STATS>
-__global__ void __launch_bounds__(COMP_THREADS) composite_kernel(const CompArgs a) {
+__global__ void __launch_bounds__(COMP_THREADS, 4) composite_kernel(const CompArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     CompSmem& sm = *reinterpret_cast<CompSmem*>(smem_raw);
     float4* sm_eff = reinterpret_cast<float4*>(smem_raw + sizeof(CompSmem));
@@ -306,8 +318,10 @@ __global__ void __launch_bounds__(COMP_THREADS) composite_kernel(const CompArgs 
                 // chain is alive, else those whose silhouette chain is alive somewhere.  Entries of other
                 // objects can no longer change any output of this block and are not walked.
                 uint32_t need = 0;
-                if (MASKS) need = __any_sync(0xffffffffu, !done_o) ? all_k : (__reduce_or_sync(0xffffffffu, ~done_k) & all_k);
-                if (MASKS && !wm && need == 0) break;
+                if (MASKS && !wm) {  // while a main chain is alive every entry is wanted anyway
+                    need = __any_sync(0xffffffffu, !done_o) ? all_k : (__reduce_or_sync(0xffffffffu, ~done_k) & all_k);
+                    if (need == 0) break;
+                }
                 bool hit = false;
                 if (e < cnt) {
                     const float4 A = sr[e].a;
