@@ -49,6 +49,7 @@ extern "C" {
 #define PG_MAX_COLORS 64
 
 typedef void* pg_stream_t; /* cudaStream_t */
+typedef void* pg_event_t;  /* cudaEvent_t */
 
 /* Mirrors GaussianRasterizationSettings (GSP/gaussian_renderer/__init__.py:38-51).
  * bg/viewmatrix/projmatrix/campos are DEVICE pointers, exactly as the reference passes CUDA tensors;
@@ -164,6 +165,12 @@ int pg_rasterize_forward(const pg_raster_settings* settings, const pg_gaussians*
 int pg_render_composed(const pg_raster_settings* settings, const pg_gaussians* g,
                        const pg_object_table* objects, const pg_frame_outputs* out, void* workspace,
                        size_t workspace_bytes, uint64_t pair_capacity, pg_stream_t stream);
+
+/* Pipelining frames on several streams: the NEXT forward / composed render issued by the calling thread
+ * records `event` on its stream right after its per-Gaussian stage — the last stage that reads the
+ * scene arrays (means3D, shs, opacities, scales, rotations).  A pg_pose_apply for the following frame
+ * on another stream only has to wait for this event, not for the whole frame.  One-shot; NULL clears. */
+int pg_set_scene_read_event(pg_event_t event);
 
 /* Asynchronously copies the workspace's status block to host_status (pinned host memory). */
 int pg_read_status(const void* workspace, pg_status* host_status, pg_stream_t stream);

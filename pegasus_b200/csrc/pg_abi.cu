@@ -71,6 +71,7 @@ static std::vector<cudaEvent_t> g_events;  // [max_frames][kStageEvents]
 static int g_prof_max = 0;
 static std::atomic<int> g_prof_frames{0};
 static thread_local int t_prof_frame = -1;  // slot of the forward in flight on this thread
+static thread_local cudaEvent_t t_scene_read_event = nullptr;  // pg_set_scene_read_event (one-shot)
 
 static void prof_begin_frame() {
     t_prof_frame = -1;
@@ -127,6 +128,11 @@ static int run_binning(const pg_raster_settings* s, const pg_gaussians* g, const
     int rc = launch_preprocess(s, g, objs, radii, at<GeomRec>(ws, L.recs), at<ushort4>(ws, L.rect),
                                at<uint32_t>(ws, L.dkey_a), counters, stream);
     if (rc) return rc;
+    if (t_scene_read_event) {  // nothing after this point reads the caller's scene arrays
+        cudaEvent_t ev = t_scene_read_event;
+        t_scene_read_event = nullptr;
+        PG_CUDA_CHECK(cudaEventRecord(ev, stream));
+    }
     prof_mark(2, stream);
     if (s->debug & 1) PG_CUDA_CHECK(cudaStreamSynchronize(stream));
     // depth sort: a -> b -> a -> b -> a
@@ -253,6 +259,11 @@ int pg_render_composed(const pg_raster_settings* s, const pg_gaussians* g, const
                                    (s->debug & 2) ? at<Counters>(ws, L.counters)->stats : nullptr, stream);
     prof_mark(7, stream);
     return rc;
+}
+
+int pg_set_scene_read_event(pg_event_t event) {
+    t_scene_read_event = (cudaEvent_t)event;
+    return PG_OK;
 }
 
 int pg_read_status(const void* ws, pg_status* host_status, pg_stream_t stream) {

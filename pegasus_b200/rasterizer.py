@@ -59,8 +59,10 @@ _WORKSPACES = {}
 _PAIR_CAPACITY_HINT = {}
 
 
-def workspace_for(device) -> _Workspace:
-    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+def workspace_for(device, slot: int = 0) -> _Workspace:
+    """Grow-only scratch of (device, slot).  Frames that are in flight at the same time (different CUDA
+    streams) must use different slots; everything on one stream shares slot 0."""
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device(), int(slot))
     ws = _WORKSPACES.get(key)
     if ws is None:
         ws = _WORKSPACES[key] = _Workspace()

@@ -172,9 +172,15 @@ class ComposedScene:
 
     def render(self, cam, bg: torch.Tensor, masks: bool = True, out: Optional[Dict] = None, sh_degree: int = 3,
                sync_check: bool = True, pair_capacity: Optional[int] = None, debug: int = 0,
-               reference_lists: bool = False) -> Dict[str, torch.Tensor]:
+               reference_lists: bool = False, slot: int = 0,
+               scene_read_event: Optional[torch.cuda.Event] = None) -> Dict[str, torch.Tensor]:
         """One frame: RGB + depth (+ seg render, sem-seg, visible and silhouette masks when
-        masks=True) — everything the reference's K+3 passes produce (src/gs/render.py:14-129)."""
+        masks=True) — everything the reference's K+3 passes produce (src/gs/render.py:14-129).
+
+        The frame is enqueued on the current CUDA stream.  `slot` selects the workspace: frames in
+        flight concurrently on different streams need distinct slots (and distinct `out` buffers).
+        `scene_read_event` is recorded right after the per-Gaussian stage, the last reader of the scene
+        arrays: the next frame's apply_pose_packets (on another stream) only has to wait for it."""
         L = _lib.load()
         H, W = int(cam.image_height), int(cam.image_width)
         if out is None:
@@ -192,7 +198,7 @@ class ComposedScene:
                                    out["sem_seg"].data_ptr() if masks else None,
                                    out["visible"].data_ptr() if masks else None,
                                    out["silhouette"].data_ptr() if masks else None)
-            ws = workspace_for(self.device)
+            ws = workspace_for(self.device, slot)
             stream = torch.cuda.current_stream(self.device)
             cap = pair_capacity or default_pair_capacity(self.P, W, H)
             table = self.table
@@ -202,6 +208,9 @@ class ComposedScene:
                 table.num_colors = 0
             while True:
                 buf = ws.ensure(self.device, self.P, W, H, cap)
+                if scene_read_event is not None:
+                    scene_read_event.record(stream)  # creates the lazily-initialised handle; re-recorded by the library
+                    _lib.check(L.pg_set_scene_read_event(C.c_void_p(scene_read_event.cuda_event)), "pg_set_scene_read_event")
                 rc = L.pg_render_composed(C.byref(s), C.byref(g), C.byref(table), C.byref(fo),
                                           C.c_void_p(buf.data_ptr()), buf.numel(), cap,
                                           C.c_void_p(stream.cuda_stream))
@@ -224,10 +233,10 @@ class ComposedScene:
             out["pair_capacity"] = cap
         return out
 
-    def read_stats(self) -> Dict[str, int]:
+    def read_stats(self, slot: int = 0) -> Dict[str, int]:
         """Compositing statistics of the last render(debug=2); synchronises."""
         L = _lib.load()
-        ws = workspace_for(self.device)
+        ws = workspace_for(self.device, slot)
         host = torch.zeros(4, dtype=torch.int64).pin_memory()
         stream = torch.cuda.current_stream(self.device)
         _lib.check(L.pg_read_stats(C.c_void_p(ws.buf.data_ptr()), C.c_void_p(host.data_ptr()),
@@ -235,10 +244,10 @@ class ComposedScene:
         stream.synchronize()
         return dict(pairs_evaluated=int(host[0]), pairs_exp=int(host[1]), pairs_blended=int(host[2]))
 
-    def read_status(self) -> Dict[str, int]:
+    def read_status(self, slot: int = 0) -> Dict[str, int]:
         """Status of the last (possibly still running) render on this device; synchronises."""
         L = _lib.load()
-        ws = workspace_for(self.device)
+        ws = workspace_for(self.device, slot)
         stream = torch.cuda.current_stream(self.device)
         _lib.check(L.pg_read_status(C.c_void_p(ws.buf.data_ptr()), C.c_void_p(ws.status_host.data_ptr()),
                                     C.c_void_p(stream.cuda_stream)), "pg_read_status")
