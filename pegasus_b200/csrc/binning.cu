@@ -2,8 +2,8 @@
 //   emit_kernel      : fused inclusive scan of tiles_touched (decoupled look-back over 1024-Gaussian
 //                      chunks, in DEPTH order) + key duplication: writes (tile id, Gaussian index)
 //                      pairs and counts pairs per tile.  12 B read per Gaussian, 8 B written per pair.
-//   tile_scan_kernel : exclusive digit bases of both tile-sort passes from the histograms emit
-//                      accumulated (shared memory per CTA, one flush).
+//   tile_hist_kernel : digit histograms of both tile-sort passes from the emitted tile ids (warp votes).
+//   tile_scan_kernel : exclusive digit bases of both tile-sort passes.
 //   ranges_kernel    : identifyTileRanges on the sorted tile ids.
 //   export_keys_kernel (tests only): rebuilds the reference's 64-bit tile|depth keys.
 #include "pg_common.cuh"
@@ -22,7 +22,6 @@ struct EmitSmem {
     uint32_t g[EMIT_CHUNK];
     uint32_t cnt[EMIT_CHUNK];
     uint32_t off[EMIT_CHUNK];
-    uint32_t hist[2][RADIX];
     uint32_t rowpre[8][32];
     short2 rowrun[8][32];
     uint32_t scan[8];
@@ -32,35 +31,13 @@ struct EmitSmem {
 constexpr int EMIT_SMALL = 16;  // entries with at most this many pairs are written by their own thread
 
 // One stored pair.  flag: the tile cannot receive a contribution (KEEP_ALL lists only).
-// The digit histograms of the two tile-sort passes are accumulated in shared memory (s_hist[0]: low
-// digit, s_hist[1]: high digit) and flushed once per CTA; per-tile ranges come from the sorted keys.
-// COOP: called by a converged warp whose lanes hold consecutive pairs of ONE Gaussian — the high digit
-// is then almost always warp-uniform and is added once per warp instead of 32 same-address atomics.
-template <bool COOP>
 __device__ __forceinline__ void emit_pair(bool valid, uint32_t dst, uint32_t tile, uint32_t g, bool flag,
-                                          uint32_t n_env, int bits_lo, uint32_t* __restrict__ tkeys,
-                                          uint32_t* __restrict__ tvals, uint32_t* __restrict__ tile_obj_count,
-                                          uint32_t (*s_hist)[RADIX]) {
-    const uint32_t dlo = tile & ((1u << bits_lo) - 1u), dhi = tile >> bits_lo;
+                                          uint32_t n_env, uint32_t* __restrict__ tkeys,
+                                          uint32_t* __restrict__ tvals, uint32_t* __restrict__ tile_obj_count) {
     if (valid) {
         tkeys[dst] = tile;
         tvals[dst] = flag ? (g | PG_CULL_FLAG) : g;
-        atomicAdd(&s_hist[0][dlo], 1u);
         if (g >= n_env && !flag) atomicAdd(&tile_obj_count[tile], 1u);
-    }
-    if (COOP) {
-        const uint32_t vm = __ballot_sync(0xffffffffu, valid);
-        if (vm) {
-            const int leader = __ffs(vm) - 1;
-            const uint32_t d0 = __shfl_sync(0xffffffffu, dhi, leader);
-            if (__all_sync(0xffffffffu, !valid || dhi == d0)) {
-                if ((int)(threadIdx.x & 31) == leader) atomicAdd(&s_hist[1][d0], (uint32_t)__popc(vm));
-            } else if (valid) {
-                atomicAdd(&s_hist[1][dhi], 1u);
-            }
-        }
-    } else if (valid) {
-        atomicAdd(&s_hist[1][dhi], 1u);
     }
 }
 
@@ -78,11 +55,9 @@ emit_kernel(const uint32_t* __restrict__ sorted_dkey, const uint32_t* __restrict
             const ushort4* __restrict__ rects, const GeomRec* __restrict__ recs, uint32_t P, uint32_t gx,
             int W, int H, uint32_t* __restrict__ tkeys,
             uint32_t* __restrict__ tvals, uint32_t R_cap, uint32_t* __restrict__ status,
-            uint32_t* __restrict__ hist_tile /*[2][256]*/, int bits_lo, uint32_t n_env,
-            uint32_t* __restrict__ tile_obj_count, Counters* __restrict__ counters) {
+            uint32_t n_env, uint32_t* __restrict__ tile_obj_count, Counters* __restrict__ counters) {
     extern __shared__ __align__(16) unsigned char emit_smem_raw[];
     EmitSmem& sm = *reinterpret_cast<EmitSmem*>(emit_smem_raw);
-    uint32_t (*s_hist)[RADIX] = sm.hist;
     uint32_t* s_g = sm.g;
     ushort4* s_rect = sm.rect;
     uint32_t* s_cnt = sm.cnt;
@@ -101,7 +76,6 @@ emit_kernel(const uint32_t* __restrict__ sorted_dkey, const uint32_t* __restrict
     const uint32_t chunk = s_chunk;
     const uint32_t num_chunks = (P + EMIT_CHUNK - 1) / EMIT_CHUNK;
     if (chunk >= num_chunks) return;
-    for (int i = tid; i < 2 * RADIX; i += 256) (&s_hist[0][0])[i] = 0;
 
     // ---- (0) gather: thread owns 4 consecutive sorted positions (blocked, the scan order)
     const uint32_t s0 = chunk * EMIT_CHUNK + tid * 4;
@@ -120,6 +94,7 @@ emit_kernel(const uint32_t* __restrict__ sorted_dkey, const uint32_t* __restrict
         s_g[tid * 4 + j] = g;
         s_rect[tid * 4 + j] = r;
     }
+    __syncthreads();
     // ---- (A) count
     uint32_t local = 0;
     unsigned long long local_full = 0;
@@ -228,8 +203,8 @@ emit_kernel(const uint32_t* __restrict__ sorted_dkey, const uint32_t* __restrict
             cull_row_run(cg, ty, r.x, r.z, W, H, &ta, &tb);
             const int xa = KEEP_ALL ? (int)r.x : ta, xb = KEEP_ALL ? (int)r.z : tb;
             for (int tx = xa; tx < xb; ++tx, ++dst)
-                emit_pair<false>(dst < R_cap, dst, (uint32_t)ty * gx + (uint32_t)tx, g, KEEP_ALL && !(tx >= ta && tx < tb),
-                                 n_env, bits_lo, tkeys, tvals, tile_obj_count, s_hist);
+                emit_pair(dst < R_cap, dst, (uint32_t)ty * gx + (uint32_t)tx, g, KEEP_ALL && !(tx >= ta && tx < tb),
+                          n_env, tkeys, tvals, tile_obj_count);
         }
     }
     __syncthreads();  // s_off of every entry is visible to its warp mates
@@ -278,20 +253,69 @@ emit_kernel(const uint32_t* __restrict__ sorted_dkey, const uint32_t* __restrict
                     const int col = (int)(p - s_rowpre[warp][i]);
                     const int tx = (KEEP_ALL ? (int)r.x : (int)run.x) + col;
                     const int ty = r.y + row0 + i;
-                    emit_pair<true>(valid, off + p, (uint32_t)ty * gx + (uint32_t)tx, g,
-                                    KEEP_ALL && !(tx >= run.x && tx < run.y), n_env, bits_lo, tkeys, tvals,
-                                    tile_obj_count, s_hist);
+                    emit_pair(valid, off + p, (uint32_t)ty * gx + (uint32_t)tx, g,
+                              KEEP_ALL && !(tx >= run.x && tx < run.y), n_env, tkeys, tvals, tile_obj_count);
                 }
                 off += tot;
                 __syncwarp();
             }
         }
     }
-    // ---- flush the CTA's digit histograms
+}
+
+// Digit histograms of both tile-sort passes from the emitted tile ids.  Shared-memory atomics cost
+// ~64 cycles per warp instruction on this part, so counting is done with warp votes instead: one
+// ballot per digit bit gives every lane the set of lanes with the same digit, the lowest of them adds
+// the group size to a warp-private counter (plain load/store).  ~30 vote-pipe cycles per 32 keys.
+constexpr int THIST_IPT = 16;
+__global__ void __launch_bounds__(256)
+tile_hist_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ n_ptr, int bits_lo, int bits_hi,
+                 uint32_t* __restrict__ hist /*[2][256]*/) {
+    __shared__ uint32_t s_h[8][2][RADIX];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < 8 * 2 * RADIX; i += 256) (&s_h[0][0][0])[i] = 0;
+    __syncthreads();
+    const uint32_t n = *n_ptr;
+    const uint32_t mask_lo = (1u << bits_lo) - 1u;
+    const uint32_t lt = (1u << lane) - 1u;
+    const uint32_t tile_items = 256 * THIST_IPT;
+    for (uint32_t base = blockIdx.x * tile_items; base < n; base += gridDim.x * tile_items) {
+        const uint32_t wbase = base + warp * (32 * THIST_IPT) + lane;
+        uint32_t k[THIST_IPT];
+#pragma unroll
+        for (int i = 0; i < THIST_IPT; ++i) k[i] = (wbase + i * 32 < n) ? keys[wbase + i * 32] : 0xFFFFFFFFu;
+#pragma unroll
+        for (int i = 0; i < THIST_IPT; ++i) {
+            const bool valid = wbase + i * 32 < n;
+            const uint32_t vm = __ballot_sync(0xffffffffu, valid);
+            const uint32_t dlo = k[i] & mask_lo, dhi = (k[i] >> bits_lo) & 255u;
+            uint32_t plo = vm, phi = vm;
+#pragma unroll
+            for (int b = 0; b < 8; ++b) {
+                if (b < bits_lo) {
+                    uint32_t bal, bit = (dlo >> b) & 1u;
+                    asm volatile("{\n.reg .pred p;\nsetp.ne.u32 p, %1, 0;\nvote.sync.ballot.b32 %0, p, 0xffffffff;\n}\n"
+                                 : "=r"(bal) : "r"(bit));
+                    plo &= bal ^ (bit - 1u);
+                }
+                if (b < bits_hi) {
+                    uint32_t bal, bit = (dhi >> b) & 1u;
+                    asm volatile("{\n.reg .pred p;\nsetp.ne.u32 p, %1, 0;\nvote.sync.ballot.b32 %0, p, 0xffffffff;\n}\n"
+                                 : "=r"(bal) : "r"(bit));
+                    phi &= bal ^ (bit - 1u);
+                }
+            }
+            if (valid && (plo & lt) == 0) s_h[warp][0][dlo] += __popc(plo);
+            if (valid && (phi & lt) == 0) s_h[warp][1][dhi] += __popc(phi);
+            __syncwarp();
+        }
+    }
     __syncthreads();
     for (int i = tid; i < 2 * RADIX; i += 256) {
-        const uint32_t c = (&s_hist[0][0])[i];
-        if (c) atomicAdd(&hist_tile[i], c);
+        uint32_t c = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) c += (&s_h[w][0][0])[i];
+        if (c) atomicAdd(&hist[i], c);
     }
 }
 
@@ -351,8 +375,7 @@ __global__ void export_keys_kernel(const uint2* __restrict__ ranges, uint32_t ti
 
 int launch_emit(bool keep_all, const uint32_t* sorted_dkey, const uint32_t* perm, const ushort4* rects, const GeomRec* recs,
                 uint32_t P, uint32_t gx, int W, int H, uint32_t* tkeys, uint32_t* tvals, uint32_t R_cap, uint32_t* status,
-                uint32_t* hist_tile, int bits_lo, uint32_t n_env, uint32_t* tile_obj_count, Counters* counters,
-                cudaStream_t stream) {
+                uint32_t n_env, uint32_t* tile_obj_count, Counters* counters, cudaStream_t stream) {
     uint32_t chunks = (P + EMIT_CHUNK - 1) / EMIT_CHUNK;
     if (chunks == 0) return PG_OK;
     static bool attr_set = false;
@@ -363,10 +386,21 @@ int launch_emit(bool keep_all, const uint32_t* sorted_dkey, const uint32_t* perm
     }
     if (keep_all)
         emit_kernel<true><<<chunks, 256, sizeof(EmitSmem), stream>>>(sorted_dkey, perm, rects, recs, P, gx, W, H, tkeys, tvals, R_cap, status,
-                                                      hist_tile, bits_lo, n_env, tile_obj_count, counters);
+                                                      n_env, tile_obj_count, counters);
     else
         emit_kernel<false><<<chunks, 256, sizeof(EmitSmem), stream>>>(sorted_dkey, perm, rects, recs, P, gx, W, H, tkeys, tvals, R_cap, status,
-                                                       hist_tile, bits_lo, n_env, tile_obj_count, counters);
+                                                       n_env, tile_obj_count, counters);
+    count_launch(1);
+    PG_CUDA_CHECK(cudaGetLastError());
+    return PG_OK;
+}
+
+int launch_tile_hist(const uint32_t* keys, const uint32_t* n_ptr, uint32_t max_n, int bits_lo, int bits_hi, uint32_t* hist,
+                     cudaStream_t stream) {
+    if (max_n == 0) return PG_OK;
+    const uint32_t tiles = (max_n + 256 * THIST_IPT - 1) / (256 * THIST_IPT);
+    const uint32_t blocks = min(tiles, (uint32_t)(PG_SM_COUNT * 8));
+    tile_hist_kernel<<<blocks, 256, 0, stream>>>(keys, n_ptr, bits_lo, bits_hi, hist);
     count_launch(1);
     PG_CUDA_CHECK(cudaGetLastError());
     return PG_OK;

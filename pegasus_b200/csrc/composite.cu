@@ -293,9 +293,10 @@ __global__ void __launch_bounds__(COMP_THREADS, 4) composite_kernel(const CompAr
     if (MASKS)
         for (int k = 0; k < K; ++k) my_tk[k * 256] = 1.0f;
 
-    float T = 1.0f, C0 = 0.0f, C1 = 0.0f, C2 = 0.0f, D = 0.0f;
-    float To = 1.0f, S0 = 0.0f, S1 = 0.0f, S2 = 0.0f;
-    bool done_main = !inside, done_o = !inside || !MASKS;
+    // A finished chain keeps its transmittance with the sign flipped (T > 0 always while alive, since a
+    // chain stops before T would drop below 1e-4): one compare serves "already done" and "done now".
+    float T = inside ? 1.0f : -1.0f, C0 = 0.0f, C1 = 0.0f, C2 = 0.0f, D = 0.0f;
+    float To = (inside && MASKS) ? 1.0f : -1.0f, S0 = 0.0f, S1 = 0.0f, S2 = 0.0f;
     uint32_t done_k = (inside && MASKS) ? 0u : 0xFFFFFFFFu;
     uint32_t last = 0;
     uint32_t n_eval = 0, n_exp = 0, n_blend = 0;
@@ -319,7 +320,7 @@ __global__ void __launch_bounds__(COMP_THREADS, 4) composite_kernel(const CompAr
                 // objects can no longer change any output of this block and are not walked.
                 uint32_t need = 0;
                 if (MASKS && !wm) {  // while a main chain is alive every entry is wanted anyway
-                    need = __any_sync(0xffffffffu, !done_o) ? all_k : (__reduce_or_sync(0xffffffffu, ~done_k) & all_k);
+                    need = __any_sync(0xffffffffu, To > 0.0f) ? all_k : (__reduce_or_sync(0xffffffffu, ~done_k) & all_k);
                     if (need == 0) break;
                 }
                 bool hit = false;
@@ -345,7 +346,7 @@ __global__ void __launch_bounds__(COMP_THREADS, 4) composite_kernel(const CompAr
                     const int obj = MASKS ? (__float_as_int(B.w) & 63) : 0;  // warp-uniform
                     bool live = true;  // STATS only: does any chain of this pixel still want this Gaussian?
                     if (STATS) {
-                        live = !done_main || (MASKS && obj > 0 && (!done_o || !((done_k >> (obj - 1)) & 1u)));
+                        live = T > 0.0f || (MASKS && obj > 0 && (To > 0.0f || !((done_k >> (obj - 1)) & 1u)));
                         if (live) { ++n_eval; if (!(power > 0.0f) && !(power < B.w)) ++n_exp; }
                     }
                     // A.7: power > 0 skips; below the per-Gaussian cut alpha < 1/255 is certain (also a skip)
@@ -354,9 +355,9 @@ __global__ void __launch_bounds__(COMP_THREADS, 4) composite_kernel(const CompAr
                         if (!(alpha < 1.0f / 255.0f)) {
                             if (STATS && live) ++n_blend;
                             const float om = sub(1.0f, alpha);
-                            if (!done_main) {
-                                const float test_T = mul(T, om);
-                                if (test_T < 0.0001f) done_main = true;
+                            {
+                                const float test_T = mul(T, om);  // negative when the chain is already done
+                                if (test_T < 0.0001f) T = -fabsf(T);
                                 else {
                                     const float4 Cc = r->c;
                                     C0 = fma(mul(Cc.x, alpha), T, C0);
@@ -368,9 +369,9 @@ __global__ void __launch_bounds__(COMP_THREADS, 4) composite_kernel(const CompAr
                                 }
                             }
                             if (MASKS && obj > 0) {
-                                if (!done_o) {
+                                {
                                     const float test_T = mul(To, om);
-                                    if (test_T < 0.0001f) done_o = true;
+                                    if (test_T < 0.0001f) To = -fabsf(To);
                                     else {
                                         const float4 ec = sm_eff[obj - 1];
                                         S0 = fma(mul(ec.x, alpha), To, S0);
@@ -390,7 +391,7 @@ __global__ void __launch_bounds__(COMP_THREADS, 4) composite_kernel(const CompAr
                     }
                 }
                 // warp-level progress: environment entries are no longer hits once every main chain is done
-                if (wm && __all_sync(0xffffffffu, done_main)) {
+                if (wm && __all_sync(0xffffffffu, T < 0.0f)) {
                     wm = false;
                     if (!MASKS) break;
                 }
@@ -400,7 +401,7 @@ __global__ void __launch_bounds__(COMP_THREADS, 4) composite_kernel(const CompAr
                 w_main_done = true;
                 if (lane == 0) atomicAdd(&sm.warps_main_done, 1);
             }
-            const bool pix_done = done_main && (!MASKS || (done_o && (done_k & all_k) == all_k));
+            const bool pix_done = T < 0.0f && (!MASKS || (To < 0.0f && (done_k & all_k) == all_k));
             if (__all_sync(0xffffffffu, pix_done)) {
                 w_done = true;
                 if (lane == 0) atomicAdd(&sm.warps_done, 1);
@@ -411,6 +412,8 @@ __global__ void __launch_bounds__(COMP_THREADS, 4) composite_kernel(const CompAr
     }
 
     if (inside) {
+        T = fabsf(T);
+        To = fabsf(To);
         const size_t HW = (size_t)a.W * a.H, pix = (size_t)py * a.W + px;
         const float bg0 = a.bg[0], bg1 = a.bg[1], bg2 = a.bg[2];
         a.out_color[pix] = fma(T, bg0, C0);
