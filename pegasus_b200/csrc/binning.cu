@@ -1,7 +1,7 @@
 // binning.cu — tile binning after the depth sort (re-designed):
-//   emit_kernel      : fused inclusive scan of tiles_touched (decoupled look-back over 1024-Gaussian
-//                      chunks, in DEPTH order) + key duplication: writes (tile id, Gaussian index)
-//                      pairs and counts pairs per tile.  12 B read per Gaussian, 8 B written per pair.
+//   emit_kernel      : fused scan of the stored pairs per Gaussian (decoupled look-back over chunks of
+//                      512 Gaussians, in DEPTH order) + key duplication, one thread per rectangle ROW:
+//                      writes (tile id, Gaussian index) pairs.  12 B read per Gaussian, 8 B written per pair.
 //   tile_hist_kernel : digit histograms of both tile-sort passes from the emitted tile ids (warp votes).
 //   tile_scan_kernel : exclusive digit bases of both tile-sort passes.
 //   ranges_kernel    : identifyTileRanges on the sorted tile ids.
@@ -15,20 +15,27 @@ constexpr uint32_t E_FLAG_AGG = 1u << 30;
 constexpr uint32_t E_FLAG_INCL = 2u << 30;
 constexpr uint32_t E_VAL_MASK = (1u << 30) - 1;
 
+constexpr int EMIT_THREADS = 256;
+constexpr int EMIT_EPT = EMIT_CHUNK / EMIT_THREADS;  // entries per thread (blocked = depth order)
+constexpr int EMIT_RPT = 14;                         // rows per thread in the row scan
+constexpr int EMIT_ROWCAP = EMIT_THREADS * EMIT_RPT; // tile rows of one window (3584)
+constexpr int EMIT_SMALL = 4;                        // runs of at most this many tiles are written by their own thread
+constexpr uint32_t EMIT_OK = 0x80000000u;            // s_g bit 31: the row test may cull (CullGauss::ok)
+
 struct EmitSmem {
-    float4 ga[EMIT_CHUNK];  // x, y, conic.x, conic.y
+    // per entry of the chunk (depth order)
+    float4 cga[EMIT_CHUNK];            // CullGauss: gx, gy, qb, thr2qa
+    float4 cgb[EMIT_CHUNK];            //            det_lo, inv_qa, umax, k
     ushort4 rect[EMIT_CHUNK];
-    float2 gb[EMIT_CHUNK];  // conic.z, cut
-    uint32_t g[EMIT_CHUNK];
-    uint32_t cnt[EMIT_CHUNK];
-    uint32_t off[EMIT_CHUNK];
-    uint32_t rowpre[8][32];
-    short2 rowrun[8][32];
+    uint32_t g[EMIT_CHUNK];            // Gaussian index | EMIT_OK
+    uint32_t rowbase[EMIT_CHUNK + 1];  // exclusive scan of the rectangles' row counts
+    // per tile row of the current window
+    uint32_t rowinfo[EMIT_ROWCAP];     // ta | tb << 11 | entry << 22   (run [ta, tb) of this row; gx <= 2047)
+    uint32_t rowoff[EMIT_ROWCAP + 1];  // exclusive scan of the rows' stored pairs (window-relative)
     uint32_t scan[8];
     uint32_t chunk, base;
 };
-
-constexpr int EMIT_SMALL = 16;  // entries with at most this many pairs are written by their own thread
+static_assert(EMIT_CHUNK <= 1024 && EMIT_CHUNK % EMIT_THREADS == 0, "entry id is packed into 10 bits");
 
 // One stored pair.  flag: the tile cannot receive a contribution (KEEP_ALL lists only).
 __device__ __forceinline__ void emit_pair(bool valid, uint32_t dst, uint32_t tile, uint32_t g, bool flag,
@@ -41,16 +48,46 @@ __device__ __forceinline__ void emit_pair(bool valid, uint32_t dst, uint32_t til
     }
 }
 
+// CTA-wide exclusive scan of one value per thread (256 threads); returns the exclusive prefix, *total = sum.
+__device__ __forceinline__ uint32_t cta_excl_scan(uint32_t v, uint32_t* s_scan, uint32_t* total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    __syncthreads();  // previous users of s_scan are done
+    if (lane == 31) s_scan[warp] = x;
+    __syncthreads();
+    uint32_t wb = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+        const uint32_t c = s_scan[w];
+        if (w < warp) wb += c;
+        tot += c;
+    }
+    *total = tot;
+    return wb + x - v;
+}
+
 // KEEP_ALL = false (default): only (tile, Gaussian) pairs that can contribute are stored — per tile a
 //            subsequence, in the same order, of the reference's list.
 // KEEP_ALL = true : every tile of every rectangle is stored exactly as the reference's duplicateWithKeys
 //            does (pairs that cannot contribute carry PG_CULL_FLAG): pg_export_binning / n_contrib parity.
-// Phases: (0) gather the chunk's 1024 depth-ordered entries into shared memory; (A) one thread per
-// entry counts its pairs with the closed-form tile-row test of tile_cull.h; (B) CTA scan + decoupled
-// look-back -> output offsets; (C1) entries with <= EMIT_SMALL pairs are written by their own thread,
-// (C2) larger ones by their whole warp, lanes over pairs (coalesced), rows found by binary search.
+//
+// The unit of work is the TILE ROW of a rectangle, not the Gaussian: rectangles span 1..gy rows, and a
+// thread that walks a tall one alone stalls its warp.  Per chunk of EMIT_CHUNK depth-ordered entries:
+//   (0) gather rect + record, derive the row test's constants (tile_cull.h) once per entry;
+//   (1) scan the row counts -> every (entry, row) gets a slot in a flat row list (windows of
+//       EMIT_ROWCAP rows; one window is the common case and its runs stay cached in shared memory);
+//   (2) one thread per row: closed-form run [ta, tb) of tiles that can contribute; scan of run lengths;
+//   (3) decoupled look-back over chunks -> output offset of the chunk;
+//   (4) one thread per row writes its run (adjacent lanes -> adjacent addresses); runs longer than
+//       EMIT_SMALL are written by the whole warp, lanes over tiles.
+// Output order = entry order (depth), rows top to bottom, tiles left to right = the reference's order.
 template <bool KEEP_ALL>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(EMIT_THREADS)
 emit_kernel(const uint32_t* __restrict__ sorted_dkey, const uint32_t* __restrict__ perm,
             const ushort4* __restrict__ rects, const GeomRec* __restrict__ recs, uint32_t P, uint32_t gx,
             int W, int H, uint32_t* __restrict__ tkeys,
@@ -58,91 +95,123 @@ emit_kernel(const uint32_t* __restrict__ sorted_dkey, const uint32_t* __restrict
             uint32_t n_env, uint32_t* __restrict__ tile_obj_count, Counters* __restrict__ counters) {
     extern __shared__ __align__(16) unsigned char emit_smem_raw[];
     EmitSmem& sm = *reinterpret_cast<EmitSmem*>(emit_smem_raw);
-    uint32_t* s_g = sm.g;
-    ushort4* s_rect = sm.rect;
-    uint32_t* s_cnt = sm.cnt;
-    uint32_t* s_off = sm.off;
-    float4* s_ga = sm.ga;
-    float2* s_gb = sm.gb;
-    uint32_t (*s_rowpre)[32] = sm.rowpre;
-    short2 (*s_rowrun)[32] = sm.rowrun;
-    uint32_t* s_scan = sm.scan;
-    uint32_t& s_chunk = sm.chunk;
-    uint32_t& s_base = sm.base;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_chunk = atomicAdd(&counters->tile_counter[4], 1u);
+    if (tid == 0) sm.chunk = atomicAdd(&counters->tile_counter[4], 1u);
     __syncthreads();
-    const uint32_t chunk = s_chunk;
+    const uint32_t chunk = sm.chunk;
     const uint32_t num_chunks = (P + EMIT_CHUNK - 1) / EMIT_CHUNK;
     if (chunk >= num_chunks) return;
 
-    // ---- (0) gather: thread owns 4 consecutive sorted positions (blocked, the scan order)
-    const uint32_t s0 = chunk * EMIT_CHUNK + tid * 4;
+    // ---- (0) gather: thread owns EMIT_EPT consecutive sorted positions (blocked, the scan order)
+    uint32_t my_rows = 0;
+    unsigned long long local_full = 0;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        uint32_t s = s0 + j;
+    for (int j = 0; j < EMIT_EPT; ++j) {
+        const int q = tid * EMIT_EPT + j;
+        const uint32_t spos = chunk * EMIT_CHUNK + q;
         uint32_t g = 0;
         ushort4 r = make_ushort4(0, 0, 0, 0);
-        if (s < P && sorted_dkey[s] != 0xFFFFFFFFu) {
-            g = perm[s];
+        if (spos < P && sorted_dkey[spos] != 0xFFFFFFFFu) {
+            g = perm[spos];
             r = rects[g];
             const float4 ra = recs[g].a, rb = recs[g].b;
-            s_ga[tid * 4 + j] = ra;
-            s_gb[tid * 4 + j] = make_float2(rb.x, rb.w);
+            const CullGauss cg = cull_setup(ra.x, ra.y, ra.z, ra.w, rb.x, rb.w);
+            sm.cga[q] = make_float4(cg.gx, cg.gy, cg.qb, cg.thr2qa);
+            sm.cgb[q] = make_float4(cg.det_lo, cg.inv_qa, cg.umax, cg.k);
+            if (cg.ok) g |= EMIT_OK;
         }
-        s_g[tid * 4 + j] = g;
-        s_rect[tid * 4 + j] = r;
-    }
-    __syncthreads();
-    // ---- (A) count
-    uint32_t local = 0;
-    unsigned long long local_full = 0;
-#pragma unroll 1
-    for (int j = 0; j < 4; ++j) {
-        const int q = tid * 4 + j;
-        const ushort4 r = s_rect[q];
-        const uint32_t n = (uint32_t)(r.z - r.x) * (uint32_t)(r.w - r.y);
-        uint32_t cnt = n;
-        if (!KEEP_ALL && n > 0) {
-            const float4 ga = s_ga[q];
-            const float2 gb = s_gb[q];
-            const CullGauss cg = cull_setup(ga.x, ga.y, ga.z, ga.w, gb.x, gb.y);
-            cnt = 0;
-            for (int ty = r.y; ty < r.w; ++ty) {
-                int ta, tb;
-                cnt += (uint32_t)cull_row_run(cg, ty, r.x, r.z, W, H, &ta, &tb);
-            }
-        }
-        s_cnt[q] = cnt;
-        local += cnt;
-        local_full += n;
+        sm.g[q] = g;
+        sm.rect[q] = r;
+        const uint32_t nr = (r.z > r.x) ? (uint32_t)(r.w - r.y) : 0u;
+        my_rows += nr;
+        local_full += (unsigned long long)nr * (uint32_t)(r.z - r.x);
     }
     // the reference's R = sum of all rectangle areas (what pg_status.num_rendered reports)
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) local_full += __shfl_xor_sync(0xffffffffu, local_full, o);
     if (lane == 0 && local_full) atomicAdd(&counters->rendered_full, local_full);
-    // ---- (B) block exclusive scan of `local`
-    uint32_t x = local;
+
+    // ---- (1) row slots
+    uint32_t total_rows;
+    {
+        uint32_t rb = cta_excl_scan(my_rows, sm.scan, &total_rows);
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
-        if (lane >= o) x += y;
+        for (int j = 0; j < EMIT_EPT; ++j) {
+            const int q = tid * EMIT_EPT + j;
+            const ushort4 r = sm.rect[q];
+            sm.rowbase[q] = rb;
+            rb += (r.z > r.x) ? (uint32_t)(r.w - r.y) : 0u;
+        }
+        if (tid == EMIT_THREADS - 1) sm.rowbase[EMIT_CHUNK] = rb;
     }
-    if (lane == 31) s_scan[warp] = x;
     __syncthreads();
-    uint32_t wb = 0, total = 0;
+    const uint32_t nwin = (total_rows + EMIT_ROWCAP - 1) / EMIT_ROWCAP;
+
+    // rows [w0, w0 + tw) -> sm.rowinfo / sm.rowoff; returns the window's stored pairs
+    auto compute_window = [&](uint32_t w0, uint32_t tw) -> uint32_t {
+        // (a) expansion: every entry writes its id into the slots of its rows that fall into the window
 #pragma unroll
-    for (int w = 0; w < 8; ++w) {
-        if (w < warp) wb += s_scan[w];
-        total += s_scan[w];
+        for (int j = 0; j < EMIT_EPT; ++j) {
+            const int q = tid * EMIT_EPT + j;
+            const uint32_t b = sm.rowbase[q], e = sm.rowbase[q + 1];
+            const uint32_t lo = max(b, w0), hi = min(e, w0 + tw);
+            for (uint32_t t = lo; t < hi; ++t) sm.rowinfo[t - w0] = (uint32_t)q;
+        }
+        __syncthreads();
+        // (b) one thread per row (adjacent lanes = adjacent rows)
+        for (uint32_t t = tid; t < tw; t += EMIT_THREADS) {
+            const uint32_t q = sm.rowinfo[t];
+            const ushort4 r = sm.rect[q];
+            const int ty = (int)r.y + (int)(w0 + t - sm.rowbase[q]);
+            const float4 ca = sm.cga[q], cb = sm.cgb[q];
+            CullGauss cg;
+            cg.gx = ca.x; cg.gy = ca.y; cg.qb = ca.z; cg.thr2qa = ca.w;
+            cg.det_lo = cb.x; cg.inv_qa = cb.y; cg.umax = cb.z; cg.k = cb.w;
+            cg.qa = 0.0f; cg.qc = 0.0f;  // not used by the row test
+            cg.ok = (sm.g[q] & EMIT_OK) != 0;
+            int ta, tb;
+            const int c = cull_row_run(cg, ty, r.x, r.z, W, H, &ta, &tb);
+            sm.rowinfo[t] = (uint32_t)ta | ((uint32_t)tb << 11) | (q << 22);
+            sm.rowoff[t] = KEEP_ALL ? (uint32_t)(r.z - r.x) : (uint32_t)c;
+        }
+        __syncthreads();
+        // (c) exclusive scan of the run lengths, EMIT_RPT consecutive rows per thread
+        uint32_t len[EMIT_RPT], sum = 0;
+#pragma unroll
+        for (int i = 0; i < EMIT_RPT; ++i) {
+            const uint32_t t = tid * EMIT_RPT + i;
+            len[i] = t < tw ? sm.rowoff[t] : 0u;
+            sum += len[i];
+        }
+        uint32_t win_total;
+        uint32_t o = cta_excl_scan(sum, sm.scan, &win_total);
+#pragma unroll
+        for (int i = 0; i < EMIT_RPT; ++i) {
+            const uint32_t t = tid * EMIT_RPT + i;
+            if (t < tw) sm.rowoff[t] = o;
+            o += len[i];
+        }
+        if (tid == 0) sm.rowoff[tw] = win_total;
+        __syncthreads();
+        return win_total;
+    };
+
+    // ---- (2) sweep 1: count
+    uint32_t total = 0;
+    {
+        uint64_t t64 = 0;
+        for (uint32_t w = 0; w < nwin; ++w) {
+            const uint32_t w0 = w * EMIT_ROWCAP;
+            t64 += compute_window(w0, min((uint32_t)EMIT_ROWCAP, total_rows - w0));
+        }
+        total = (uint32_t)min(t64, (uint64_t)E_VAL_MASK);
     }
-    uint32_t excl = wb + x - local;
-    // chunk-level decoupled look-back (single value): warp 0 inspects 32 predecessors per step
+    // ---- (3) chunk-level decoupled look-back (single value): warp 0 inspects 32 predecessors per step
     if (warp == 0) {
         volatile uint32_t* st = status + chunk;
         uint32_t prev = 0;
-        const uint32_t tot_c = min(total, E_VAL_MASK);
+        const uint32_t tot_c = total;
         if (chunk == 0) {
             if (lane == 0) *st = tot_c | E_FLAG_INCL;
         } else {
@@ -161,14 +230,14 @@ emit_kernel(const uint32_t* __restrict__ sorted_dkey, const uint32_t* __restrict
                 uint32_t v = lane < take ? (sv & E_VAL_MASK) : 0u;
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                prev += v;
+                prev = min(prev + v, E_VAL_MASK);
                 if (first_in < first_nr) break;
                 t -= take;
             }
             if (lane == 0) *st = min(prev + tot_c, E_VAL_MASK) | E_FLAG_INCL;
         }
         if (lane == 0) {
-            s_base = prev;
+            sm.base = prev;
             if (chunk == num_chunks - 1) {
                 uint64_t R = (uint64_t)prev + total;
                 counters->sort_n = (uint32_t)min(R, (uint64_t)R_cap);
@@ -177,89 +246,57 @@ emit_kernel(const uint32_t* __restrict__ sorted_dkey, const uint32_t* __restrict
         }
     }
     __syncthreads();
-    const uint32_t base = s_base;
-    {
-        uint32_t o = base + excl;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            s_off[tid * 4 + j] = o;
-            o += s_cnt[tid * 4 + j];
-        }
-    }
-    // ---- (C1) small entries: own thread, tile rows in order (y outer, x inner = the reference's order)
-#pragma unroll 1
-    for (int j = 0; j < 4; ++j) {
-        const int q = tid * 4 + j;
-        const uint32_t cnt = s_cnt[q];
-        if (cnt == 0 || cnt > (uint32_t)EMIT_SMALL) continue;
-        const ushort4 r = s_rect[q];
-        const uint32_t g = s_g[q];
-        const float4 ga = s_ga[q];
-        const float2 gb = s_gb[q];
-        const CullGauss cg = cull_setup(ga.x, ga.y, ga.z, ga.w, gb.x, gb.y);
-        uint32_t dst = s_off[q];
-        for (int ty = r.y; ty < r.w; ++ty) {
-            int ta, tb;
-            cull_row_run(cg, ty, r.x, r.z, W, H, &ta, &tb);
-            const int xa = KEEP_ALL ? (int)r.x : ta, xb = KEEP_ALL ? (int)r.z : tb;
-            for (int tx = xa; tx < xb; ++tx, ++dst)
-                emit_pair(dst < R_cap, dst, (uint32_t)ty * gx + (uint32_t)tx, g, KEEP_ALL && !(tx >= ta && tx < tb),
-                          n_env, tkeys, tvals, tile_obj_count);
-        }
-    }
-    __syncthreads();  // s_off of every entry is visible to its warp mates
-    // ---- (C2) large entries: the whole warp, lanes over pairs
-#pragma unroll 1
-    for (int j = 0; j < 4; ++j) {
-        uint32_t big = __ballot_sync(0xffffffffu, s_cnt[tid * 4 + j] > (uint32_t)EMIT_SMALL);
-        while (big) {
-            const int src = __ffs(big) - 1;
-            big &= big - 1;
-            const int q = (warp * 32 + src) * 4 + j;
-            const ushort4 r = s_rect[q];
-            const uint32_t g = s_g[q];
-            const float4 ga = s_ga[q];
-            const float2 gb = s_gb[q];
-            const CullGauss cg = cull_setup(ga.x, ga.y, ga.z, ga.w, gb.x, gb.y);
-            uint32_t off = s_off[q];
-            const int rows = r.w - r.y;
-            for (int row0 = 0; row0 < rows; row0 += 32) {
-                const int row = row0 + lane;
-                int ta = r.x, tb = r.x;
-                uint32_t len = 0;
-                if (row < rows) {
-                    const int c = cull_row_run(cg, r.y + row, r.x, r.z, W, H, &ta, &tb);
-                    len = KEEP_ALL ? (uint32_t)(r.z - r.x) : (uint32_t)c;
-                }
-                uint32_t incl = len;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
-                    if (lane >= o) incl += y;
-                }
-                const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
-                s_rowpre[warp][lane] = incl - len;
-                s_rowrun[warp][lane] = make_short2((short)ta, (short)tb);
-                __syncwarp();
-                for (uint32_t p0 = 0; p0 < tot; p0 += 32) {
-                    const uint32_t p = p0 + lane;
-                    const bool valid = p < tot && off + p < R_cap;
-                    // largest i with rowpre[i] <= p (its row is non-empty)
-                    int i = 0;
-#pragma unroll
-                    for (int step = 16; step > 0; step >>= 1)
-                        if (s_rowpre[warp][i + step] <= p) i += step;
-                    const short2 run = s_rowrun[warp][i];
-                    const int col = (int)(p - s_rowpre[warp][i]);
-                    const int tx = (KEEP_ALL ? (int)r.x : (int)run.x) + col;
-                    const int ty = r.y + row0 + i;
-                    emit_pair(valid, off + p, (uint32_t)ty * gx + (uint32_t)tx, g,
-                              KEEP_ALL && !(tx >= run.x && tx < run.y), n_env, tkeys, tvals, tile_obj_count);
-                }
-                off += tot;
-                __syncwarp();
+    // ---- (4) sweep 2: write
+    uint32_t off = sm.base;
+    for (uint32_t w = 0; w < nwin; ++w) {
+        const uint32_t w0 = w * EMIT_ROWCAP;
+        const uint32_t tw = min((uint32_t)EMIT_ROWCAP, total_rows - w0);
+        uint32_t win_total;
+        if (nwin > 1) win_total = compute_window(w0, tw);  // a single window is still cached
+        else win_total = sm.rowoff[tw];
+        for (uint32_t t0 = 0; t0 < tw; t0 += EMIT_THREADS) {
+            const uint32_t t = t0 + tid;
+            uint32_t info = 0, o0 = 0, len = 0, g = 0;
+            int ty = 0, x0 = 0;
+            if (t < tw) {
+                info = sm.rowinfo[t];
+                o0 = sm.rowoff[t];
+                len = sm.rowoff[t + 1] - o0;
+                const uint32_t q = info >> 22;
+                const ushort4 r = sm.rect[q];
+                g = sm.g[q] & ~EMIT_OK;
+                ty = (int)r.y + (int)(w0 + t - sm.rowbase[q]);
+                x0 = KEEP_ALL ? (int)r.x : (int)(info & 2047u);
+            }
+            const int ta = (int)(info & 2047u), tb = (int)((info >> 11) & 2047u);
+            const uint32_t dst0 = off + o0;                    // may wrap only beyond R_cap (checked below)
+            const uint32_t room = dst0 < R_cap ? R_cap - dst0 : 0u;
+            const uint32_t tile0 = (uint32_t)ty * gx + (uint32_t)x0;
+            if (len <= (uint32_t)EMIT_SMALL) {
+                for (uint32_t i = 0; i < len; ++i)
+                    emit_pair(i < room, dst0 + i, tile0 + i, g,
+                              KEEP_ALL && !(x0 + (int)i >= ta && x0 + (int)i < tb), n_env, tkeys, tvals, tile_obj_count);
+            }
+            // long runs: the whole warp, lanes over tiles
+            uint32_t big = __ballot_sync(0xffffffffu, len > (uint32_t)EMIT_SMALL);
+            while (big) {
+                const int src = __ffs(big) - 1;
+                big &= big - 1;
+                const uint32_t b_len = __shfl_sync(0xffffffffu, len, src);
+                const uint32_t b_dst = __shfl_sync(0xffffffffu, dst0, src);
+                const uint32_t b_room = __shfl_sync(0xffffffffu, room, src);
+                const uint32_t b_tile = __shfl_sync(0xffffffffu, tile0, src);
+                const uint32_t b_g = __shfl_sync(0xffffffffu, g, src);
+                const int b_x0 = __shfl_sync(0xffffffffu, x0, src);
+                const int b_ta = __shfl_sync(0xffffffffu, ta, src), b_tb = __shfl_sync(0xffffffffu, tb, src);
+                for (uint32_t i = lane; i < b_len; i += 32)
+                    emit_pair(i < b_room, b_dst + i, b_tile + i, b_g,
+                              KEEP_ALL && !(b_x0 + (int)i >= b_ta && b_x0 + (int)i < b_tb), n_env, tkeys, tvals,
+                              tile_obj_count);
             }
         }
+        off = (uint32_t)min((uint64_t)off + win_total, (uint64_t)0xFFFFFFFFu);
+        if (nwin > 1) __syncthreads();  // the next window overwrites rowinfo / rowoff
     }
 }
 
@@ -357,6 +394,57 @@ ranges_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ n_
     }
 }
 
+// Compositing launch order: tile ids by descending list length (longest-processing-time-first keeps
+// the SMs evenly loaded to the end of the kernel; natural order leaves a ~14 % idle tail).  One CTA:
+// counting sort on length / 16 (4096 buckets, longer lists clipped into the first bucket); the order
+// inside a bucket is irrelevant.
+constexpr int ORDER_BUCKETS = 4096;
+__global__ void __launch_bounds__(1024)
+tile_order_kernel(const uint2* __restrict__ ranges, uint32_t tiles, uint32_t* __restrict__ order) {
+    __shared__ uint32_t s_cnt[ORDER_BUCKETS];
+    __shared__ uint32_t s_warp[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < ORDER_BUCKETS; i += 1024) s_cnt[i] = 0;
+    __syncthreads();
+    for (uint32_t t = tid; t < tiles; t += 1024) {
+        const uint2 r = ranges[t];
+        const uint32_t b = (ORDER_BUCKETS - 1) - min((r.y - r.x) >> 4, (uint32_t)(ORDER_BUCKETS - 1));
+        atomicAdd(&s_cnt[b], 1u);
+    }
+    __syncthreads();
+    // exclusive scan of the 4096 bucket counts: 4 consecutive buckets per thread
+    uint32_t c[4], sum = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { c[j] = s_cnt[tid * 4 + j]; sum += c[j]; }
+    uint32_t x = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    if (lane == 31) s_warp[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = s_warp[lane], wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t y = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += y;
+        }
+        s_warp[lane] = wi - w;
+    }
+    __syncthreads();
+    uint32_t base = s_warp[warp] + x - sum;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { s_cnt[tid * 4 + j] = base; base += c[j]; }
+    __syncthreads();
+    for (uint32_t t = tid; t < tiles; t += 1024) {
+        const uint2 r = ranges[t];
+        const uint32_t b = (ORDER_BUCKETS - 1) - min((r.y - r.x) >> 4, (uint32_t)(ORDER_BUCKETS - 1));
+        order[atomicAdd(&s_cnt[b], 1u)] = t;
+    }
+}
+
 // tests only: keys[i] = (tile << 32) | depth_bits[point_list[i]], tile from ranges
 __global__ void export_keys_kernel(const uint2* __restrict__ ranges, uint32_t tiles,
                                    const uint32_t* __restrict__ point_list,
@@ -385,10 +473,10 @@ int launch_emit(bool keep_all, const uint32_t* sorted_dkey, const uint32_t* perm
         attr_set = true;
     }
     if (keep_all)
-        emit_kernel<true><<<chunks, 256, sizeof(EmitSmem), stream>>>(sorted_dkey, perm, rects, recs, P, gx, W, H, tkeys, tvals, R_cap, status,
+        emit_kernel<true><<<chunks, EMIT_THREADS, sizeof(EmitSmem), stream>>>(sorted_dkey, perm, rects, recs, P, gx, W, H, tkeys, tvals, R_cap, status,
                                                       n_env, tile_obj_count, counters);
     else
-        emit_kernel<false><<<chunks, 256, sizeof(EmitSmem), stream>>>(sorted_dkey, perm, rects, recs, P, gx, W, H, tkeys, tvals, R_cap, status,
+        emit_kernel<false><<<chunks, EMIT_THREADS, sizeof(EmitSmem), stream>>>(sorted_dkey, perm, rects, recs, P, gx, W, H, tkeys, tvals, R_cap, status,
                                                        n_env, tile_obj_count, counters);
     count_launch(1);
     PG_CUDA_CHECK(cudaGetLastError());
@@ -417,6 +505,13 @@ int launch_ranges(const uint32_t* sorted_tile_keys, const uint32_t* n_ptr, uint3
     if (max_n == 0) return PG_OK;
     const uint32_t blocks = min((max_n + 255u) / 256u, (uint32_t)(PG_SM_COUNT * 16));
     ranges_kernel<<<blocks, 256, 0, stream>>>(sorted_tile_keys, n_ptr, ranges);
+    count_launch(1);
+    PG_CUDA_CHECK(cudaGetLastError());
+    return PG_OK;
+}
+
+int launch_tile_order(const uint2* ranges, uint32_t tiles, uint32_t* order, cudaStream_t stream) {
+    tile_order_kernel<<<1, 1024, 0, stream>>>(ranges, tiles, order);
     count_launch(1);
     PG_CUDA_CHECK(cudaGetLastError());
     return PG_OK;

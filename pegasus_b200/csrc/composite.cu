@@ -22,6 +22,7 @@
 //
 // Issue-bound on the FP32/ALU pipes (exp is a 12-op FMA polynomial so that results are
 // bit-reproducible on the CPU oracle).
+#include <cstdlib>
 #include <cstring>
 
 #include "pg_common.cuh"
@@ -77,6 +78,7 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 
 struct CompArgs {
     const uint2* ranges;
+    const uint32_t* tile_order;  // launch order: CTA b composites tile tile_order[b]
     const uint32_t* point_list;  // bit 31 = PG_CULL_FLAG
     const GeomRec* recs;
     int W, H, gx;
@@ -120,7 +122,6 @@ __device__ __forceinline__ void flush_stats(unsigned long long* stats, uint32_t 
 // CONSUMERS, each owning an 8x4 pixel block: wait `full`, cull the batch lane-parallel against the
 // block, walk the hits, arrive on `empty`.  No CTA-wide barrier in the steady state; a consumer whose
 // 32 pixels are finished keeps releasing stages, the producer stops when all 8 have finished.
-constexpr int COMP_STAGES = 4;
 constexpr int COMP_BATCH = 128;
 constexpr int COMP_THREADS = 288;
 
@@ -128,7 +129,8 @@ constexpr int COMP_IDCHUNK = 256;
 constexpr int COMP_PEND = 512;
 static_assert(COMP_BATCH - 1 + COMP_IDCHUNK <= COMP_PEND, "pending ring too small");
 
-struct CompSmem {
+template <int COMP_STAGES>
+struct CompSmemT {
     GeomRec rec[COMP_STAGES][COMP_BATCH];
     uint32_t pos[COMP_STAGES][COMP_BATCH];  // 1-based list position of each staged entry (n_contrib)
     uint32_t ids[2][COMP_IDCHUNK];          // producer: raw id chunks, TMA double buffer
@@ -168,15 +170,20 @@ __device__ __forceinline__ float expf_exact_nz(float x) {
 // Dynamic shared memory after CompSmem (MASKS only): eff[PG_MAX_OBJECTS] float4 (colour the
 // rasterizer produces for object k's flat SH), then Tk[K][256] — the standalone transmittance of
 // object k at each of the tile's 256 pixels (silhouette chains), slot = warp * 32 + lane.
-template <bool MASKS, bool STATS>
-__global__ void __launch_bounds__(COMP_THREADS, 4) composite_kernel(const CompArgs a) {
+// COMP_STAGES: depth of the record ring (how far fast warps may run ahead of the slowest one);
+// ILP: hits evaluated together (2: geometry + exp of two hits interleave, blending stays in list order);
+// MINB: CTAs per SM the register allocation is bounded for.
+template <bool MASKS, bool STATS, int COMP_STAGES, int ILP, int MINB>
+__global__ void __launch_bounds__(COMP_THREADS, MINB) composite_kernel(const CompArgs a) {
+    using CompSmem = CompSmemT<COMP_STAGES>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     CompSmem& sm = *reinterpret_cast<CompSmem*>(smem_raw);
     float4* sm_eff = reinterpret_cast<float4*>(smem_raw + sizeof(CompSmem));
     float* sm_tk = reinterpret_cast<float*>(smem_raw + sizeof(CompSmem) + PG_MAX_OBJECTS * sizeof(float4));
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int tile = blockIdx.y * a.gx + blockIdx.x;
+    const int tile = (int)a.tile_order[blockIdx.x];
+    const int tile_x = tile % a.gx, tile_y = tile / a.gx;
     const uint2 range = a.ranges[tile];
     const int n = (int)(range.y - range.x);
     const uint32_t lt = (1u << lane) - 1u;
@@ -279,7 +286,7 @@ __global__ void __launch_bounds__(COMP_THREADS, 4) composite_kernel(const CompAr
     }
 
     // =========================== CONSUMERS ===========================
-    const int wx0 = blockIdx.x * PG_TILE + (warp & 1) * 8, wy0 = blockIdx.y * PG_TILE + (warp >> 1) * 4;
+    const int wx0 = tile_x * PG_TILE + (warp & 1) * 8, wy0 = tile_y * PG_TILE + (warp >> 1) * 4;
     const int px = wx0 + (lane & 7), py = wy0 + (lane >> 3);
     const bool inside = px < a.W && py < a.H;
     float pfx = (float)px, pfy = (float)py;
@@ -332,60 +339,88 @@ __global__ void __launch_bounds__(COMP_THREADS, 4) composite_kernel(const CompAr
                     hit = wanted && !block_culled(A.x, A.y, A.z, A.w, B.x, B.w, bx0, bx1, by0, by1);
                 }
                 uint32_t mm = __ballot_sync(0xffffffffu, hit);
-#pragma unroll 1
-                while (mm) {
-                    const GeomRec* r = sr + (c0 + __ffs(mm) - 1);
-                    mm &= mm - 1;
-                    const float4 A = r->a;
-                    const float4 B = r->b;
+                // blend one hit into every chain of this pixel that still wants it (A.7 order of operations)
+                auto blend = [&](const GeomRec* r, const float4& B, float alpha, int obj) {
+                    const float om = sub(1.0f, alpha);
+                    {
+                        const float test_T = mul(T, om);  // negative when the chain is already done
+                        if (test_T < 0.0001f) T = -fabsf(T);
+                        else {
+                            const float4 Cc = r->c;
+                            C0 = fma(mul(Cc.x, alpha), T, C0);
+                            C1 = fma(mul(Cc.y, alpha), T, C1);
+                            C2 = fma(mul(Cc.z, alpha), T, C2);
+                            D = fma(mul(B.z, alpha), T, D);
+                            T = test_T;
+                            if (!MASKS) last = sm.pos[s][r - sr];
+                        }
+                    }
+                    if (MASKS && obj > 0) {
+                        {
+                            const float test_T = mul(To, om);
+                            if (test_T < 0.0001f) To = -fabsf(To);
+                            else {
+                                const float4 ec = sm_eff[obj - 1];
+                                S0 = fma(mul(ec.x, alpha), To, S0);
+                                S1 = fma(mul(ec.y, alpha), To, S1);
+                                S2 = fma(mul(ec.z, alpha), To, S2);
+                                To = test_T;
+                            }
+                        }
+                        const uint32_t kb = (uint32_t)(obj - 1) & 31u;
+                        if (!((done_k >> kb) & 1u)) {
+                            const float test_T = mul(my_tk[(obj - 1) * 256], om);
+                            if (test_T < 0.0001f) done_k |= 1u << kb;
+                            else my_tk[(obj - 1) * 256] = test_T;
+                        }
+                    }
+                };
+                auto power_of = [&](const float4& A, const float4& B) {
                     const float dx = sub(A.x, pfx), dy = sub(A.y, pfy);
                     const float w = mul(dy, mul(B.x, dy));
                     const float sq = fma(dx, mul(A.z, dx), w);
                     const float bxy = mul(mul(A.w, dx), dy);
-                    const float power = fma(sq, -0.5f, -bxy);
-                    const int obj = MASKS ? (__float_as_int(B.w) & 63) : 0;  // warp-uniform
-                    bool live = true;  // STATS only: does any chain of this pixel still want this Gaussian?
-                    if (STATS) {
-                        live = T > 0.0f || (MASKS && obj > 0 && (To > 0.0f || !((done_k >> (obj - 1)) & 1u)));
-                        if (live) { ++n_eval; if (!(power > 0.0f) && !(power < B.w)) ++n_exp; }
+                    return fma(sq, -0.5f, -bxy);
+                };
+                if (ILP == 2 && !STATS) {
+#pragma unroll 1
+                    while (mm) {
+                        const GeomRec* r1 = sr + (c0 + __ffs(mm) - 1);
+                        mm &= mm - 1;
+                        const bool two = mm != 0;  // warp-uniform
+                        const GeomRec* r2 = two ? sr + (c0 + __ffs(mm) - 1) : r1;
+                        mm &= mm - 1;
+                        const float4 A1 = r1->a, B1 = r1->b, A2 = r2->a, B2 = r2->b;
+                        const float p1 = power_of(A1, B1), p2 = power_of(A2, B2);
+                        // both exponentials are evaluated unconditionally (independent chains interleave); a hit
+                        // outside [cut, 0] is discarded by its predicate, exactly like the branch of the ILP == 1 path
+                        const float a1 = fminf(0.99f, mul(B1.y, expf_exact_nz(p1)));
+                        const float a2 = fminf(0.99f, mul(B2.y, expf_exact_nz(p2)));
+                        const bool v1 = !(p1 > 0.0f) && !(p1 < B1.w) && !(a1 < 1.0f / 255.0f);
+                        const bool v2 = two && !(p2 > 0.0f) && !(p2 < B2.w) && !(a2 < 1.0f / 255.0f);
+                        if (v1) blend(r1, B1, a1, MASKS ? (__float_as_int(B1.w) & 63) : 0);
+                        if (v2) blend(r2, B2, a2, MASKS ? (__float_as_int(B2.w) & 63) : 0);
                     }
-                    // A.7: power > 0 skips; below the per-Gaussian cut alpha < 1/255 is certain (also a skip)
-                    if (!(power > 0.0f) && !(power < B.w)) {
-                        const float alpha = fminf(0.99f, mul(B.y, expf_exact_nz(power)));
-                        if (!(alpha < 1.0f / 255.0f)) {
-                            if (STATS && live) ++n_blend;
-                            const float om = sub(1.0f, alpha);
-                            {
-                                const float test_T = mul(T, om);  // negative when the chain is already done
-                                if (test_T < 0.0001f) T = -fabsf(T);
-                                else {
-                                    const float4 Cc = r->c;
-                                    C0 = fma(mul(Cc.x, alpha), T, C0);
-                                    C1 = fma(mul(Cc.y, alpha), T, C1);
-                                    C2 = fma(mul(Cc.z, alpha), T, C2);
-                                    D = fma(mul(B.z, alpha), T, D);
-                                    T = test_T;
-                                    if (!MASKS) last = sm.pos[s][r - sr];
-                                }
-                            }
-                            if (MASKS && obj > 0) {
-                                {
-                                    const float test_T = mul(To, om);
-                                    if (test_T < 0.0001f) To = -fabsf(To);
-                                    else {
-                                        const float4 ec = sm_eff[obj - 1];
-                                        S0 = fma(mul(ec.x, alpha), To, S0);
-                                        S1 = fma(mul(ec.y, alpha), To, S1);
-                                        S2 = fma(mul(ec.z, alpha), To, S2);
-                                        To = test_T;
-                                    }
-                                }
-                                const uint32_t kb = (uint32_t)(obj - 1) & 31u;
-                                if (!((done_k >> kb) & 1u)) {
-                                    const float test_T = mul(my_tk[(obj - 1) * 256], om);
-                                    if (test_T < 0.0001f) done_k |= 1u << kb;
-                                    else my_tk[(obj - 1) * 256] = test_T;
-                                }
+                } else {
+#pragma unroll 1
+                    while (mm) {
+                        const GeomRec* r = sr + (c0 + __ffs(mm) - 1);
+                        mm &= mm - 1;
+                        const float4 A = r->a;
+                        const float4 B = r->b;
+                        const float power = power_of(A, B);
+                        const int obj = MASKS ? (__float_as_int(B.w) & 63) : 0;  // warp-uniform
+                        bool live = true;  // STATS only: does any chain of this pixel still want this Gaussian?
+                        if (STATS) {
+                            live = T > 0.0f || (MASKS && obj > 0 && (To > 0.0f || !((done_k >> (obj - 1)) & 1u)));
+                            if (live) { ++n_eval; if (!(power > 0.0f) && !(power < B.w)) ++n_exp; }
+                        }
+                        // A.7: power > 0 skips; below the per-Gaussian cut alpha < 1/255 is certain (also a skip)
+                        if (!(power > 0.0f) && !(power < B.w)) {
+                            const float alpha = fminf(0.99f, mul(B.y, expf_exact_nz(power)));
+                            if (!(alpha < 1.0f / 255.0f)) {
+                                if (STATS && live) ++n_blend;
+                                blend(r, B, alpha, obj);
                             }
                         }
                     }
@@ -458,25 +493,49 @@ __global__ void __launch_bounds__(COMP_THREADS, 4) composite_kernel(const CompAr
     if (STATS) flush_stats(a.stats, n_eval, n_exp, n_blend);
 }
 
-template <bool MASKS, bool STATS>
+template <bool MASKS, bool STATS, int STAGES, int ILP, int MINB>
 static int launch_one(const CompArgs& a, dim3 grid, cudaStream_t stream) {
     static int attr_smem = 0;
-    const int smem = (int)sizeof(CompSmem) +
+    const int smem = (int)sizeof(CompSmemT<STAGES>) +
                      (MASKS ? (int)(PG_MAX_OBJECTS * sizeof(float4)) + a.num_objects * 256 * (int)sizeof(float) : 0);
     if (smem > attr_smem) {
-        PG_CUDA_CHECK(cudaFuncSetAttribute(composite_kernel<MASKS, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        PG_CUDA_CHECK(cudaFuncSetAttribute(composite_kernel<MASKS, STATS, STAGES, ILP, MINB>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_smem = smem;
     }
-    composite_kernel<MASKS, STATS><<<grid, COMP_THREADS, smem, stream>>>(a);
+    composite_kernel<MASKS, STATS, STAGES, ILP, MINB><<<grid, COMP_THREADS, smem, stream>>>(a);
     return PG_OK;
 }
 
+// PG_COMP_VARIANT (tuning only, read once).  Measured on B200, C2 workload (profiles/README.md, r1t):
+// 0: 4 stages, ILP 1 -> 1.235 ms; 1: 6 stages 1.222; 2: 8 stages (3 CTAs/SM) 1.355; 3: ILP 2 1.139;
+// 4 (default): ILP 2, registers bounded for 3 CTAs/SM 1.119; 5: 6 stages + ILP 2 1.120.
+static int comp_variant() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("PG_COMP_VARIANT");
+        v = e ? atoi(e) : 4;
+    }
+    return v;
+}
+
 int launch_composite(const CompArgs& a, int gy, bool masks, cudaStream_t stream) {
-    dim3 grid(a.gx, gy);
+    dim3 grid(a.gx * gy);
     const bool st = a.stats != nullptr;
     int rc;
-    if (!masks) rc = st ? launch_one<false, true>(a, grid, stream) : launch_one<false, false>(a, grid, stream);
-    else rc = st ? launch_one<true, true>(a, grid, stream) : launch_one<true, false>(a, grid, stream);
+    if (!masks) rc = st ? launch_one<false, true, 4, 1, 4>(a, grid, stream) : launch_one<false, false, 4, 1, 4>(a, grid, stream);
+    else if (st) rc = launch_one<true, true, 4, 1, 4>(a, grid, stream);
+    else {
+        switch (comp_variant()) {
+            case 1: rc = launch_one<true, false, 6, 1, 4>(a, grid, stream); break;
+            case 2: rc = launch_one<true, false, 8, 1, 4>(a, grid, stream); break;
+            case 3: rc = launch_one<true, false, 4, 2, 4>(a, grid, stream); break;
+            case 5: rc = launch_one<true, false, 6, 2, 3>(a, grid, stream); break;
+            case 6: rc = launch_one<true, false, 4, 1, 3>(a, grid, stream); break;
+            case 0: rc = launch_one<true, false, 4, 1, 4>(a, grid, stream); break;
+            default: rc = launch_one<true, false, 4, 2, 3>(a, grid, stream); break;
+        }
+    }
     if (rc) return rc;
     PG_CUDA_CHECK(cudaGetLastError());
     count_launch(1);
@@ -484,14 +543,14 @@ int launch_composite(const CompArgs& a, int gy, bool masks, cudaStream_t stream)
 }
 
 // Fills CompArgs from the ABI structs and launches the right kernel.
-int launch_composite_from_abi(const uint2* ranges, const uint32_t* point_list, const GeomRec* recs, int W,
+int launch_composite_from_abi(const uint2* ranges, const uint32_t* tile_order, const uint32_t* point_list, const GeomRec* recs, int W,
                               int H, const float* bg, const pg_raster_outputs* ro, const pg_frame_outputs* fo,
                               const pg_object_table* objs, uint32_t n_env, const uint32_t* tile_obj_count,
                               unsigned long long* stats, cudaStream_t stream) {
     CompArgs a;
     memset(&a, 0, sizeof(a));
     a.stats = stats;
-    a.ranges = ranges; a.point_list = point_list; a.recs = recs;
+    a.ranges = ranges; a.tile_order = tile_order; a.point_list = point_list; a.recs = recs;
     a.W = W; a.H = H; a.gx = (W + PG_TILE - 1) / PG_TILE;
     const int gy = (H + PG_TILE - 1) / PG_TILE;
     a.bg = bg;

@@ -52,13 +52,14 @@ int launch_tile_hist(const uint32_t* keys, const uint32_t* n_ptr, uint32_t max_n
                      cudaStream_t stream);
 int launch_tile_scan(const uint32_t* hist_tile, uint32_t* bins, Counters* counters, cudaStream_t stream);
 int launch_ranges(const uint32_t* sorted_tile_keys, const uint32_t* n_ptr, uint32_t max_n, uint2* ranges, cudaStream_t stream);
+int launch_tile_order(const uint2* ranges, uint32_t tiles, uint32_t* order, cudaStream_t stream);
 int launch_export_keys(const uint2* ranges, uint32_t tiles, const uint32_t* point_list, const GeomRec* recs,
                        uint64_t* keys, uint32_t* point_list_out, uint32_t* ranges_out, cudaStream_t stream);
 int launch_pose(int K, const int32_t* first, const PoseDev* poses_dev, const pg_canonical* canon,
                 int scene_offset, const pg_scene* scene, cudaStream_t stream);
 int launch_pack(int W, int H, const float* color, const float* depth, uint8_t* rgb_u8, uint16_t* depth_u16,
                 cudaStream_t stream);
-int launch_composite_from_abi(const uint2* ranges, const uint32_t* point_list, const GeomRec* recs, int W,
+int launch_composite_from_abi(const uint2* ranges, const uint32_t* tile_order, const uint32_t* point_list, const GeomRec* recs, int W,
                               int H, const float* bg, const pg_raster_outputs* ro, const pg_frame_outputs* fo,
                               const pg_object_table* objs, uint32_t n_env, const uint32_t* tile_obj_count,
                               unsigned long long* stats, cudaStream_t stream);
@@ -108,8 +109,8 @@ static int check_common(const pg_raster_settings* s, const pg_gaussians* g, uint
     }
     if (pair_capacity == 0 || pair_capacity > (1ull << 30)) { set_error("pair_capacity must be in [1, 2^30]"); return PG_ERR_INVALID; }
     uint32_t gx = (s->image_width + PG_TILE - 1) / PG_TILE, gy = (s->image_height + PG_TILE - 1) / PG_TILE;
-    if (gx > 65535 || gy > 65535 || (uint64_t)gx * gy > (1u << 16)) {
-        set_error("image too large: at most 65536 tiles of 16x16 are supported");
+    if (gx > 2047 || gy > 65535 || (uint64_t)gx * gy > (1u << 16)) {
+        set_error("image too large: at most 65536 tiles of 16x16 and 2047 tile columns are supported");
         return PG_ERR_INVALID;
     }
     return PG_OK;
@@ -188,6 +189,8 @@ static int run_binning(const pg_raster_settings* s, const pg_gaussians* g, const
     rc = launch_ranges(at<uint32_t>(ws, two ? L.tkey_a : L.tkey_b), &counters->sort_n, (uint32_t)R_cap,
                        at<uint2>(ws, L.ranges), stream);
     if (rc) return rc;
+    rc = launch_tile_order(at<uint2>(ws, L.ranges), L.tiles, at<uint32_t>(ws, L.tile_order), stream);
+    if (rc) return rc;
     prof_mark(6, stream);
     if (s->debug & 1) PG_CUDA_CHECK(cudaStreamSynchronize(stream));
     return PG_OK;
@@ -226,7 +229,7 @@ int pg_rasterize_forward(const pg_raster_settings* s, const pg_gaussians* g, con
     const bool keep_all = (s->debug & 4) != 0 || out->n_contrib != nullptr;
     rc = run_binning(s, g, nullptr, out->radii, ws, L, pair_capacity, keep_all, stream);
     if (rc) return rc;
-    rc = launch_composite_from_abi(at<uint2>(ws, L.ranges), sorted_point_list(ws, L), at<GeomRec>(ws, L.recs),
+    rc = launch_composite_from_abi(at<uint2>(ws, L.ranges), at<uint32_t>(ws, L.tile_order), sorted_point_list(ws, L), at<GeomRec>(ws, L.recs),
                                    s->image_width, s->image_height, s->bg, out, nullptr, nullptr,
                                    (uint32_t)g->P, at<uint32_t>(ws, L.tile_obj_count),
                                    (s->debug & 2) ? at<Counters>(ws, L.counters)->stats : nullptr, stream);
@@ -257,7 +260,7 @@ int pg_render_composed(const pg_raster_settings* s, const pg_gaussians* g, const
     const uint32_t n_env = objs->num_objects > 0 ? (uint32_t)objs->first[0] : (uint32_t)g->P;
     if (out->silhouette && objs->num_colors > 0)
         PG_CUDA_CHECK(cudaMemsetAsync(out->silhouette, 0, (size_t)objs->num_colors * s->image_width * s->image_height, stream));
-    rc = launch_composite_from_abi(at<uint2>(ws, L.ranges), sorted_point_list(ws, L), at<GeomRec>(ws, L.recs),
+    rc = launch_composite_from_abi(at<uint2>(ws, L.ranges), at<uint32_t>(ws, L.tile_order), sorted_point_list(ws, L), at<GeomRec>(ws, L.recs),
                                    s->image_width, s->image_height, s->bg, nullptr, out, objs, n_env,
                                    at<uint32_t>(ws, L.tile_obj_count),
                                    (s->debug & 2) ? at<Counters>(ws, L.counters)->stats : nullptr, stream);

@@ -92,7 +92,7 @@ constexpr int SORT_THREADS = 256;
 constexpr int SORT_IPT = 16;
 constexpr int SORT_TILE = SORT_THREADS * SORT_IPT;  // 4096 items per CTA-tile
 constexpr int RADIX = 256;
-constexpr int EMIT_CHUNK = 1024;
+constexpr int EMIT_CHUNK = 512;
 
 struct Layout {
     // all offsets in bytes from the workspace base; every region 256-B aligned
@@ -107,6 +107,7 @@ struct Layout {
     size_t status_tile;  // u32[2][tilesR][256]
     size_t zero_end;
     size_t bins_tile;    // u32[2][256] exclusive bases of the two tile-sort passes
+    size_t tile_order;   // u32[tiles] tile ids by descending list length (compositing launch order)
     size_t recs;         // GeomRec[P]
     size_t rect;         // ushort4[P]
     size_t dkey_a, dkey_b, dval_a, dval_b;  // u32[P] depth-sort ping-pong
@@ -139,6 +140,7 @@ inline Layout make_layout(int P, int W, int H, uint64_t R_cap) {
     L.status_tile = o; o = align_up(o + (size_t)2 * L.tilesR * RADIX * 4);
     L.zero_end = o;
     L.bins_tile = o; o = align_up(o + 2 * RADIX * 4);
+    L.tile_order = o; o = align_up(o + (size_t)L.tiles * 4);
     L.recs = o; o = align_up(o + (size_t)P * sizeof(GeomRec));
     L.rect = o; o = align_up(o + (size_t)P * 8);
     L.dkey_a = o; o = align_up(o + (size_t)P * 4);

@@ -177,6 +177,20 @@ def test_edge_cases_empty_culled_single_and_huge():
     assert ref["num_rendered"] == 10 * 6
 
 
+def test_binning_tall_rectangles_span_several_row_windows():
+    """The binning kernel flattens rectangles into tile rows and processes them in windows of 3584 rows
+    per 512-Gaussian chunk: big splats (tens of rows each) force several windows per chunk, in both the
+    reference-list and the culled mode."""
+    env, _ = util.small_scene(n_env=3000, n_obj=(), seed=31)
+    env["scaling"] = env["scaling"] + 2.5   # ~12x larger: most rectangles cover a large part of the 30 tile rows
+    inp = util.activated(env)
+    from pegasus_b200 import synth
+    c = synth.orbit_cameras(1, 640, 480, seed=16)[0]
+    ref, _ = check_against_oracle(inp, util.oracle_cam(c), np.zeros(3, np.float32))
+    vis = ref["radii"] > 0
+    assert ref["num_rendered"] / max(int(vis.sum()), 1) > 150   # > 150 tiles per visible Gaussian on average
+
+
 def test_workspace_overflow_is_detected_and_retried():
     from pegasus_b200 import rasterizer
     env, objs = util.small_scene(n_env=8000, n_obj=(), seed=21)
