@@ -67,6 +67,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "r"(parity), "r"(1000000u)
         : "memory");
 }
+// WAITNS > 0: back off with nanosleep between polls instead of re-arming the suspended try_wait
+// (a waiting warp then issues ~1 instruction per WAITNS ns instead of 3 per hardware time-out).
+template <int WAITNS>
+__device__ __forceinline__ void mbar_wait_t(uint64_t* bar, uint32_t parity) {
+    if (WAITNS == 0) mbar_wait(bar, parity);
+    else
+        while (!mbar_try_wait(bar, parity)) __nanosleep(WAITNS);
+}
 // 1-D TMA bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
     asm volatile(
@@ -167,13 +175,25 @@ __device__ __forceinline__ float expf_exact_nz(float x) {
     return __int_as_float(__float_as_int(p) + (__float_as_int(z) << 23));  // MAGIC's low 9 bits are 0
 }
 
+// TUNING ONLY (PG_COMP_VARIANT 9): exp through MUFU ex2.approx — not reproducible on the CPU oracle, used
+// to measure what the bit-exact polynomial costs; never the default.
+template <bool FASTEXP>
+__device__ __forceinline__ float exp_sel(float x) {
+    if (FASTEXP) {
+        float y;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(mul(x, 1.44269502162933349609375f)));
+        return y;
+    }
+    return expf_exact_nz(x);
+}
+
 // Dynamic shared memory after CompSmem (MASKS only): eff[PG_MAX_OBJECTS] float4 (colour the
 // rasterizer produces for object k's flat SH), then Tk[K][256] — the standalone transmittance of
 // object k at each of the tile's 256 pixels (silhouette chains), slot = warp * 32 + lane.
 // COMP_STAGES: depth of the record ring (how far fast warps may run ahead of the slowest one);
 // ILP: hits evaluated together (2: geometry + exp of two hits interleave, blending stays in list order);
 // MINB: CTAs per SM the register allocation is bounded for.
-template <bool MASKS, bool STATS, int COMP_STAGES, int ILP, int MINB>
+template <bool MASKS, bool STATS, int COMP_STAGES, int ILP, int MINB, int WAITNS, bool FASTEXP>
 __global__ void __launch_bounds__(COMP_THREADS, MINB) composite_kernel(const CompArgs a) {
     using CompSmem = CompSmemT<COMP_STAGES>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -225,7 +245,7 @@ __global__ void __launch_bounds__(COMP_THREADS, MINB) composite_kernel(const Com
         for (int it = 0;; ++it) {
             const int s = it % COMP_STAGES;
             if (it >= COMP_STAGES)
-                mbar_wait(reinterpret_cast<uint64_t*>(&sm.empty[s]), (uint32_t)(((it / COMP_STAGES) - 1) & 1));
+                mbar_wait_t<(WAITNS < 0 ? -WAITNS : WAITNS)>(reinterpret_cast<uint64_t*>(&sm.empty[s]), (uint32_t)(((it / COMP_STAGES) - 1) & 1));
             const bool all_done = *(volatile int*)&sm.warps_done == 8;
             const bool mode_all = !MASKS || *(volatile int*)&sm.warps_main_done < 8;
             while (!all_done && fill < COMP_BATCH && ci < nchunks && (mode_all || obj_left > 0)) {
@@ -311,7 +331,9 @@ __global__ void __launch_bounds__(COMP_THREADS, MINB) composite_kernel(const Com
 
     for (int it = 0;; ++it) {
         const int s = it % COMP_STAGES;
-        mbar_wait(reinterpret_cast<uint64_t*>(&sm.full[s]), (uint32_t)((it / COMP_STAGES) & 1));
+        // WAITNS < 0: only parties with nothing to do back off (the producer, finished consumers)
+        if (WAITNS < 0 && w_done) mbar_wait_t<-WAITNS>(reinterpret_cast<uint64_t*>(&sm.full[s]), (uint32_t)((it / COMP_STAGES) & 1));
+        else mbar_wait_t<(WAITNS < 0 ? 0 : WAITNS)>(reinterpret_cast<uint64_t*>(&sm.full[s]), (uint32_t)((it / COMP_STAGES) & 1));
         const int cnt = *(volatile int*)&sm.cnt[s];
         if (cnt == 0) break;
         if (!w_done) {
@@ -394,8 +416,8 @@ __global__ void __launch_bounds__(COMP_THREADS, MINB) composite_kernel(const Com
                         const float p1 = power_of(A1, B1), p2 = power_of(A2, B2);
                         // both exponentials are evaluated unconditionally (independent chains interleave); a hit
                         // outside [cut, 0] is discarded by its predicate, exactly like the branch of the ILP == 1 path
-                        const float a1 = fminf(0.99f, mul(B1.y, expf_exact_nz(p1)));
-                        const float a2 = fminf(0.99f, mul(B2.y, expf_exact_nz(p2)));
+                        const float a1 = fminf(0.99f, mul(B1.y, exp_sel<FASTEXP>(p1)));
+                        const float a2 = fminf(0.99f, mul(B2.y, exp_sel<FASTEXP>(p2)));
                         const bool v1 = !(p1 > 0.0f) && !(p1 < B1.w) && !(a1 < 1.0f / 255.0f);
                         const bool v2 = two && !(p2 > 0.0f) && !(p2 < B2.w) && !(a2 < 1.0f / 255.0f);
                         if (v1) blend(r1, B1, a1, MASKS ? (__float_as_int(B1.w) & 63) : 0);
@@ -417,7 +439,7 @@ __global__ void __launch_bounds__(COMP_THREADS, MINB) composite_kernel(const Com
                         }
                         // A.7: power > 0 skips; below the per-Gaussian cut alpha < 1/255 is certain (also a skip)
                         if (!(power > 0.0f) && !(power < B.w)) {
-                            const float alpha = fminf(0.99f, mul(B.y, expf_exact_nz(power)));
+                            const float alpha = fminf(0.99f, mul(B.y, exp_sel<FASTEXP>(power)));
                             if (!(alpha < 1.0f / 255.0f)) {
                                 if (STATS && live) ++n_blend;
                                 blend(r, B, alpha, obj);
@@ -493,17 +515,17 @@ __global__ void __launch_bounds__(COMP_THREADS, MINB) composite_kernel(const Com
     if (STATS) flush_stats(a.stats, n_eval, n_exp, n_blend);
 }
 
-template <bool MASKS, bool STATS, int STAGES, int ILP, int MINB>
+template <bool MASKS, bool STATS, int STAGES, int ILP, int MINB, int WAITNS = 0, bool FASTEXP = false>
 static int launch_one(const CompArgs& a, dim3 grid, cudaStream_t stream) {
     static int attr_smem = 0;
     const int smem = (int)sizeof(CompSmemT<STAGES>) +
                      (MASKS ? (int)(PG_MAX_OBJECTS * sizeof(float4)) + a.num_objects * 256 * (int)sizeof(float) : 0);
     if (smem > attr_smem) {
-        PG_CUDA_CHECK(cudaFuncSetAttribute(composite_kernel<MASKS, STATS, STAGES, ILP, MINB>,
+        PG_CUDA_CHECK(cudaFuncSetAttribute(composite_kernel<MASKS, STATS, STAGES, ILP, MINB, WAITNS, FASTEXP>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_smem = smem;
     }
-    composite_kernel<MASKS, STATS, STAGES, ILP, MINB><<<grid, COMP_THREADS, smem, stream>>>(a);
+    composite_kernel<MASKS, STATS, STAGES, ILP, MINB, WAITNS, FASTEXP><<<grid, COMP_THREADS, smem, stream>>>(a);
     return PG_OK;
 }
 
@@ -533,6 +555,12 @@ int launch_composite(const CompArgs& a, int gy, bool masks, cudaStream_t stream)
             case 5: rc = launch_one<true, false, 6, 2, 3>(a, grid, stream); break;
             case 6: rc = launch_one<true, false, 4, 1, 3>(a, grid, stream); break;
             case 0: rc = launch_one<true, false, 4, 1, 4>(a, grid, stream); break;
+            case 7: rc = launch_one<true, false, 4, 2, 3, 20>(a, grid, stream); break;
+            case 8: rc = launch_one<true, false, 4, 2, 3, 100>(a, grid, stream); break;
+            case 9: rc = launch_one<true, false, 4, 2, 3, 0, true>(a, grid, stream); break;
+            case 10: rc = launch_one<true, false, 4, 2, 3, 400>(a, grid, stream); break;
+            case 11: rc = launch_one<true, false, 4, 2, 3, -100>(a, grid, stream); break;
+            case 12: rc = launch_one<true, false, 4, 2, 3, -400>(a, grid, stream); break;
             default: rc = launch_one<true, false, 4, 2, 3>(a, grid, stream); break;
         }
     }

@@ -108,10 +108,10 @@ def save_ply(path: str, cloud: Dict[str, np.ndarray]) -> None:
     """Write a cloud dict in the reference's layout (binary little endian, normals zero)."""
     xyz = np.asarray(cloud["xyz"], dtype=np.float32)
     n = xyz.shape[0]
-    dc = np.asarray(cloud["features_dc"], dtype=np.float32).reshape(n, -1, 3).transpose(0, 2, 1).reshape(n, -1)
-    rest = np.asarray(cloud["features_rest"], dtype=np.float32).reshape(n, -1, 3)
-    n_coef = rest.shape[1]
-    rest = rest.transpose(0, 2, 1).reshape(n, -1)
+    dc = np.asarray(cloud["features_dc"], dtype=np.float32).reshape(n, 1, 3).transpose(0, 2, 1).reshape(n, 3)
+    rest = np.asarray(cloud["features_rest"], dtype=np.float32)
+    n_coef = rest.shape[1] if rest.ndim == 3 else rest.size // max(3 * n, 1)  # (n, coef, 3)
+    rest = rest.reshape(n, n_coef, 3).transpose(0, 2, 1).reshape(n, 3 * n_coef)
     cols = np.concatenate([xyz, np.zeros_like(xyz), dc, rest,
                            np.asarray(cloud["opacity"], dtype=np.float32).reshape(n, 1),
                            np.asarray(cloud["scaling"], dtype=np.float32).reshape(n, 3),
