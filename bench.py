@@ -51,6 +51,8 @@ def parse_args():
     ap.add_argument("--obj-n", type=int, default=None)
     ap.add_argument("--views", type=int, default=100)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-baseline", action="store_true")
+    ap.add_argument("--gpu-baseline-frames", type=int, default=10)
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--ref-seconds", type=float, default=240.0, help="cap of the --impl reference run")
     return ap.parse_args()
@@ -527,6 +529,40 @@ def run_ours(args):
         cpu_baseline = {"value": fps, "unit": UNIT, "cores": oracle.num_threads(), "kind": "port",
                         "sample": desc, "seconds": secs}
 
+    # ---- the upstream-style CUDA rasterizer (baseline/upstream_style.cu: CUB scan + 64-bit-key radix sort,
+    # blocking pair-count read, 16x16-thread render) running the reference's K+3 passes per frame on the
+    # same scene and views; rasterizer passes only (no merges, activations or CPU mask tests)
+    gpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_gpu_baseline:
+        import baseline
+        brast = baseline.UpstreamStyleRasterizer()
+        first = [scene.n_env + int(v) for v in scene.first_rel]
+        sizes = [scene.P] + [first[k + 1] - first[k] for k in range(Kobj)] + [scene.P - scene.n_env] * 2
+        bouts = [dict(color=torch.empty((3, Hd, Wd), dtype=torch.float32, device=dev),
+                      depth=torch.empty((1, Hd, Wd), dtype=torch.float32, device=dev),
+                      radii=torch.empty((max(n, 1),), dtype=torch.int32, device=dev)) for n in sizes]
+        if Kobj:
+            scene.apply_pose_packets(packets[0])
+        for i in range(2):  # warm-up: buffer growth
+            baseline.reference_frame(brast, scene, cams[i % len(cams)], bg, outs=bouts)
+        nb = max(1, args.gpu_baseline_frames)
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        b0.record(main)
+        pairs = 0
+        for i in range(nb):
+            res = baseline.reference_frame(brast, scene, cams[(W_steps + i) % len(cams)], bg, outs=bouts)
+            pairs += res[0]["num_rendered"]
+        b1.record(main)
+        torch.cuda.synchronize()
+        bms = b0.elapsed_time(b1) / nb
+        gpu_baseline = {"value": 1e3 / bms, "unit": UNIT, "ms_per_step": bms, "frames": nb, "kind": "restatement",
+                        "passes_per_frame": Kobj + 3, "pairs_full_scene_pass": pairs / nb,
+                        "what": "baseline/upstream_style.cu: restatement of the public CUDA forward rasterizer the "
+                                "reference pins as a submodule (source absent from the reference tree), sm_100a build, "
+                                "CUB scan/sort; K+3 rasterizer passes per frame as src/gs/render.py issues them, "
+                                "scene merges / activations / CPU mask tests NOT included"}
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K_steps, "warmup": W_steps,
@@ -547,6 +583,7 @@ def run_ours(args):
             "sequential_ms_per_step": seq_ms_per_step,
             "compositing_stats": {"pairs_evaluated": ev_, "pairs_reaching_exp": ex_, "pairs_blended": bl_},
             "cpu_baseline": cpu_baseline,
+            "gpu_baseline": gpu_baseline,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

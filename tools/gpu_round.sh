@@ -14,9 +14,9 @@ fi
 timeout 600 python bench.py --steps 100 --warmup 5 > $OUT/bench.json 2> $OUT/bench.err
 echo "bench exit $?"; tail -c 600 $OUT/bench.json
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
-  --log-file $OUT/launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $OUT/launches_run.log 2>&1
+  --log-file $OUT/launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-gpu-baseline > $OUT/launches_run.log 2>&1
 # frames before the timed ones: 3 calibration + 3 stats + 1 warm-up = 7 frames x 12 pegasus kernels
 timeout 900 ncu --set full --clock-control none --import-source on \
   -k regex:'composite|emit|onesweep|preprocess|hist_kernel|tile_scan' -s 84 -c 12 -o $OUT/prof \
-  python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $OUT/prof_run.log 2>&1
+  python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-gpu-baseline > $OUT/prof_run.log 2>&1
 ls -la $OUT

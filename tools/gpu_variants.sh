@@ -15,7 +15,7 @@ if [ "$KEXPR" != "skip" ]; then
   tail -15 $OUT/test.log
 fi
 for v in $VALS; do
-  env $VAR=$v timeout 600 python bench.py --steps 60 --warmup 5 --no-cpu-baseline > $OUT/bench_$v.json 2> $OUT/bench_$v.err
+  env $VAR=$v timeout 600 python bench.py --steps 60 --warmup 5 --no-cpu-baseline --no-gpu-baseline > $OUT/bench_$v.json 2> $OUT/bench_$v.err
   python - <<PY
 import json
 try:
