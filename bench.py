@@ -386,88 +386,49 @@ def run_ours(args):
     ms_max = pgd.max_over_ranks(ms, device=dev)
     value = world * K_steps / (ms_max / 1e3)
 
-    # ---- end-to-end timing: host camera/pose in, packed frame products out; same NSLOT-deep pipeline:
-    # per slot one stream carries H2D (camera + pose packet) -> pose kernel -> frame -> packing -> D2H,
-    # so frame i+1's kernels overlap frame i's copies and compositing.
+    # ---- end-to-end timing through the public API (pegasus_b200.DatasetGenerator, the generate_dataset loop
+    # of pegasus.py:247-390): per frame the camera + pose packets are copied from pinned host memory, the pose
+    # kernel and the fused frame run, the products are packed (u8 RGB, u16 depth mm, u8 masks) and copied back to
+    # pinned host memory; NSLOT frames in flight, one stream per slot.  No PNG encoding (host-side, not this path).
+    from pegasus_b200 import DatasetGenerator
+    gen = DatasetGenerator(scene, Wd, Hd, bg=bg, frames_in_flight=NSLOT)
+    gen.pair_capacity = cap  # calibrated above; the slots' workspaces are already sized
     nc = colors.shape[0]
-    HW = Wd * Hd
-    dev_pack = [dict(rgb=torch.empty((Hd, Wd, 3), dtype=torch.uint8, device=dev),
-                     depth=torch.empty((Hd, Wd), dtype=torch.int16, device=dev)) for _ in range(NSLOT)]
-    host = [dict(rgb=torch.empty((Hd, Wd, 3), dtype=torch.uint8).pin_memory(),
-                 depth=torch.empty((Hd, Wd), dtype=torch.int16).pin_memory(),
-                 sem=torch.empty((Hd, Wd, 3), dtype=torch.uint8).pin_memory(),
-                 vis=torch.empty((nc, Hd, Wd), dtype=torch.uint8).pin_memory(),
-                 sil=torch.empty((nc, Hd, Wd), dtype=torch.uint8).pin_memory()) for _ in range(NSLOT)]
-    cam_host = torch.zeros((len(cams), 35), dtype=torch.float32)
-    for j, cm in enumerate(cams):
-        cam_host[j, 0:16] = cm.world_view_transform.cpu().reshape(-1)
-        cam_host[j, 16:32] = cm.full_proj_transform.cpu().reshape(-1)
-        cam_host[j, 32:35] = cm.camera_center.cpu()
-    cam_host = cam_host.pin_memory()
-    cam_dev = [torch.zeros(35, dtype=torch.float32, device=dev) for _ in range(NSLOT)]
-    pose_dev = [torch.zeros((max(Kobj, 1), 103), dtype=torch.float32, device=dev) for _ in range(NSLOT)]
 
-    class CamView:  # a Camera whose tensors are views into the per-slot device staging buffer
-        def __init__(self, base, slot):
-            self.image_width, self.image_height, self.FoVx, self.FoVy = base.image_width, base.image_height, base.FoVx, base.FoVy
-            self.world_view_transform = cam_dev[slot][0:16].view(4, 4)
-            self.full_proj_transform = cam_dev[slot][16:32].view(4, 4)
-            self.camera_center = cam_dev[slot][32:35]
+    def e2e_inputs(first_local, count):
+        """Global frame list [first_local*world, (first_local+count)*world): cameras + per-frame host pose packets."""
+        gl = range(first_local * world, (first_local + count) * world)
+        cam_list = [cams[g % len(cams)] for g in gl]
+        pk = torch.stack([packets_host[g % n_pose_frames] for g in gl]) if Kobj else None
+        return cam_list, pk
 
     h2d = 35 * 4 + (Kobj * 103 * 4 if Kobj else 0)
-    d2h = HW * 3 + HW * 2 + HW * 3 + 2 * nc * HW
-    e2e_issued = [0]
+    d2h = gen.d2h_bytes_per_frame
+    checksum = [0]
 
-    def e2e_frame(i):
-        sl = i % NSLOT
-        g = (i * world + rank)
-        st_ = streams[sl]
-        with torch.cuda.stream(st_):
-            # stream order already guarantees that this slot's previous D2H copies have finished
-            cam_dev[sl].copy_(cam_host[g % len(cams)], non_blocking=True)
-            if Kobj:
-                pose_dev[sl].copy_(packets_host[g % n_pose_frames], non_blocking=True)
-                if e2e_issued[0] > 0:
-                    st_.wait_event(read_ev[(i - 1) % NSLOT])
-                scene.apply_pose_packets(pose_dev[sl])
-            o = slot_out[sl]
-            scene.render(CamView(cams[g % len(cams)], sl), bg, masks=True, out=o, sync_check=False, pair_capacity=cap,
-                         slot=sl, scene_read_event=read_ev[sl] if Kobj else None)
-            _lib.check(L.pg_pack_frame(Wd, Hd, C.c_void_p(o["color"].data_ptr()), C.c_void_p(o["depth"].data_ptr()),
-                                       C.c_void_p(dev_pack[sl]["rgb"].data_ptr()),
-                                       C.c_void_p(dev_pack[sl]["depth"].data_ptr()), C.c_void_p(st_.cuda_stream)),
-                       "pg_pack_frame")
-            host[sl]["rgb"].copy_(dev_pack[sl]["rgb"], non_blocking=True)
-            host[sl]["depth"].copy_(dev_pack[sl]["depth"], non_blocking=True)
-            host[sl]["sem"].copy_(o["sem_seg"], non_blocking=True)
-            host[sl]["vis"].copy_(o["visible"], non_blocking=True)
-            host[sl]["sil"].copy_(o["silhouette"], non_blocking=True)
-            e2e_issued[0] += 1
+    def on_frame(f, prods):
+        if f == 0:
+            checksum[0] = int(prods["rgb"].astype(np.int64).sum()) + int(prods["visible"].astype(np.int64).sum())
 
-    torch.cuda.synchronize()
-    for i in range(W_steps):
-        e2e_frame(i)
+    if W_steps:
+        cl, pk = e2e_inputs(0, W_steps)
+        gen.generate(cl, pose_packets=pk, rank=rank, world=world)
+    cl, pk = e2e_inputs(W_steps, K_steps)
     torch.cuda.synchronize()
     pgd.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(main)
-    for st_ in streams:
-        st_.wait_event(e0)
-    for i in range(W_steps, W_steps + K_steps):
-        e2e_frame(i)
-    for st_ in streams:
-        e_ = torch.cuda.Event()
-        e_.record(st_)
-        main.wait_event(e_)
+    t_wall = time.perf_counter()
+    st = gen.generate(cl, pose_packets=pk, rank=rank, world=world)  # returns when every frame's products are on the host
+    t_wall = time.perf_counter() - t_wall
     e1.record(main)
     torch.cuda.synchronize()
     pgd.barrier()
-    e2e_ms = pgd.max_over_ranks(e0.elapsed_time(e1), device=dev)
+    assert st["frames"] == K_steps
+    e2e_ms = pgd.max_over_ranks(max(e0.elapsed_time(e1), t_wall * 1e3), device=dev)
     e2e_value = world * K_steps / (e2e_ms / 1e3)
-    for sl in range(NSLOT):
-        if scene.read_status(slot=sl)["overflow"]:
-            raise RuntimeError("pair capacity overflowed inside the e2e region")
-    checksum = int(host[0]["rgb"].to(torch.int64).sum()) + int(host[NSLOT - 1]["vis"].to(torch.int64).sum())
+    gen.generate(cl[:world], pose_packets=None if pk is None else pk[:world], rank=rank, world=world, on_frame=on_frame)
+    checksum = checksum[0]
 
     # ---- roofline per stage (rank 0's numbers)
     hbm_peak, sm_max_mhz, peak_src = measured_peaks()

@@ -6,6 +6,8 @@ Public surface:
     Camera                                               view / projection tensors (reference Camera semantics)
     render_rgb_and_depth, render_silhouette_mask, render_visib_mask, render_semanticsegmentation_mask
                                                          mirrors of src/gs/render.py on a ComposedScene
+    DatasetGenerator, BOPDatasetWriter, ObjectMeta       the generate_dataset loop (pegasus.py:247-390) with frames
+                                                         in flight, GPU-side packing and the BOP writer
 Everything computes in libpegasus_b200.so (C ABI, include/pegasus_b200.h); there is no CPU path.
 """
 from .rasterizer import GaussianRasterizationSettings, GaussianRasterizer  # noqa: F401
@@ -14,7 +16,10 @@ from .scene import ComposedScene  # noqa: F401
 from .render import (render_rgb_and_depth, render_silhouette_mask, render_visib_mask,  # noqa: F401
                      render_semanticsegmentation_mask, render_frame)
 from .sh_rotation import generate_pose_packets  # noqa: F401
+from .generate import DatasetGenerator  # noqa: F401
+from .bop_writer import BOPDatasetWriter, ObjectMeta  # noqa: F401
 
 __all__ = ["GaussianRasterizationSettings", "GaussianRasterizer", "ComposedScene", "Camera", "focal2fov",
            "fov2focal", "render_rgb_and_depth", "render_silhouette_mask", "render_visib_mask",
-           "render_semanticsegmentation_mask", "render_frame", "generate_pose_packets"]
+           "render_semanticsegmentation_mask", "render_frame", "generate_pose_packets", "DatasetGenerator",
+           "BOPDatasetWriter", "ObjectMeta"]

@@ -211,3 +211,22 @@ def test_object_meta_from_points_is_a_tight_box():
     coords = (pts - o) @ np.linalg.pinv(e)
     assert coords.min() > -1e-9 and coords.max() < 1 + 1e-9
     np.testing.assert_allclose(m.box_center, m.box_points.mean(0), atol=1e-12)
+
+
+# ---- multi-GPU: per-rank JSON fragments merged by rank 0 (pegasus_b200/generate.py) --------------
+def test_rank_fragments_merge_in_frame_order(G, tmp_path):
+    from pegasus_b200.generate import merge_rank_fragments, write_rank_fragment
+    full = None
+    for rank in range(3):
+        w = _writer(G, tmp_path)
+        for f in range(rank, 8, 3):
+            w.add_scene_camera_json(frame_id=f)
+            w.scene_gt_json[str(f)] = [{"obj_id": f}]
+        write_rank_fragment(w, rank)
+        full = w
+    merge_rank_fragments(full.scene_path, world=3)
+    cam = json.load(open(full.scene_path / "scene_camera.json"))
+    gt = json.load(open(full.scene_path / "scene_gt.json"))
+    assert list(cam.keys()) == list(gt.keys()) == [str(f) for f in range(8)]
+    assert [gt[k][0]["obj_id"] for k in gt] == list(range(8))
+    assert not list(full.scene_path.glob("*.rank*.json"))

@@ -11,7 +11,7 @@ else
 fi
 echo "pytest exit $?" >> $OUT/test.log
 tail -15 $OUT/test.log
-timeout 600 python bench.py --steps 100 --warmup 5 --no-cpu-baseline > $OUT/bench.json 2> $OUT/bench.err
+timeout 600 python bench.py --steps 100 --warmup 5 --no-cpu-baseline --no-gpu-baseline > $OUT/bench.json 2> $OUT/bench.err
 echo "bench exit $?"; tail -5 $OUT/bench.err
 python - <<PY
 import json
