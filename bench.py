@@ -203,6 +203,35 @@ def cpu_reference_frames_per_s(spec, env, objs, cams, poses0, budget_s, bands_pe
     return fps, desc, frames, spent
 
 
+def use_host_cores(oracle):
+    """torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm runs on rank 0 alone and is meant to
+    use every host core this process may run on."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    oracle.set_num_threads(n)
+    try:
+        import torch
+        torch.set_num_threads(n)
+    except Exception:
+        pass
+
+
+def emit_line(line):
+    """The ONE JSON line goes to the real stdout; everything else this process (or NCCL) prints to fd 1 was
+    redirected to stderr by main()."""
+    data = (json.dumps(line) + "\n").encode()
+    fd = _REAL_STDOUT[0]
+    if fd is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(fd, data)
+
+
+_REAL_STDOUT = [None]
+
+
 def run_reference(args):
     """--impl reference: the reference's algorithm for the path on the host cores (oracle port: the
     reference's own rasterizer is CUDA-only and absent from the tree, so there is no oracle/_ref)."""
@@ -210,6 +239,7 @@ def run_reference(args):
     if rank != 0:
         return
     import oracle
+    use_host_cores(oracle)
     spec = workload_spec(args)
     env, objs, cams = build_clouds(spec)
     poses0 = object_poses(spec, 1)[0]
@@ -231,7 +261,7 @@ def run_reference(args):
         "note": "each step is one frame estimated from a bounded sample (see cpu_baseline.sample); "
                 "%.1f s of CPU time were spent on %d steps" % (secs, steps),
     }
-    print(json.dumps(line), flush=True)
+    emit_line(line)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -484,6 +514,7 @@ def run_ours(args):
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         import oracle
+        use_host_cores(oracle)
         poses0 = object_poses(spec, 1)[0]
         fps, desc, steps, secs = cpu_reference_frames_per_s(spec, env, objs, cams_h, poses0, args.cpu_seconds,
                                                             bands_per_frame=3, max_frames=2)
@@ -546,7 +577,7 @@ def run_ours(args):
             "cpu_baseline": cpu_baseline,
             "gpu_baseline": gpu_baseline,
         }
-        print(json.dumps(line), flush=True)
+        emit_line(line)
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
@@ -554,6 +585,10 @@ def run_ours(args):
 
 def main():
     args = parse_args()
+    # keep stdout to the single JSON line: libraries (NCCL's version banner, torchrun notices) write to fd 1
+    sys.stdout.flush()
+    _REAL_STDOUT[0] = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:
