@@ -344,8 +344,13 @@ def run_ours(args):
     # slot), the way a dataset generator renders a sequence: frame i+1's per-Gaussian / binning stages
     # overlap frame i's compositing.  Every frame's complete work lies inside the timed region.
     NSLOT = max(1, int(os.environ.get("PG_SLOTS", "3")))
+    # PG_SPLIT=1 (default): every slot has a high-priority stream for the per-Gaussian / sort stages and a
+    # normal-priority one for compositing (pg_set_composite_stream), so the latency-bound stages of frame
+    # i+1 co-run with the issue-bound compositing of frame i on every SM.
+    SPLIT = NSLOT > 1 and os.environ.get("PG_SPLIT", "1") != "0"
     main = torch.cuda.current_stream(dev)
-    streams = [torch.cuda.Stream(device=dev) for _ in range(NSLOT)]
+    streams = [torch.cuda.Stream(device=dev, priority=-1 if SPLIT else 0) for _ in range(NSLOT)]
+    comp_streams = [torch.cuda.Stream(device=dev, priority=0) if SPLIT else None for _ in range(NSLOT)]
     slot_out = [out] + [scene.alloc_outputs(Wd, Hd, masks=True) for _ in range(NSLOT - 1)]
     read_ev = [torch.cuda.Event() for _ in range(NSLOT)]  # "frame's per-Gaussian stage has read the scene"
     frames_issued = [0]
@@ -360,7 +365,8 @@ def run_ours(args):
                     streams[sl].wait_event(read_ev[(i - 1) % NSLOT])
                 scene.apply_pose_packets(pose_of(i))
             scene.render(view_of(i), bg, masks=True, out=slot_out[sl], sync_check=False, pair_capacity=cap, slot=sl,
-                         scene_read_event=read_ev[sl] if (spec["dynamic"] and Kobj) else None)
+                         scene_read_event=read_ev[sl] if (spec["dynamic"] and Kobj) else None,
+                         composite_stream=comp_streams[sl])
             frames_issued[0] += 1
 
     for sl in range(NSLOT):  # size every slot's workspace before timing
@@ -421,7 +427,7 @@ def run_ours(args):
     # kernel and the fused frame run, the products are packed (u8 RGB, u16 depth mm, u8 masks) and copied back to
     # pinned host memory; NSLOT frames in flight, one stream per slot.  No PNG encoding (host-side, not this path).
     from pegasus_b200 import DatasetGenerator
-    gen = DatasetGenerator(scene, Wd, Hd, bg=bg, frames_in_flight=NSLOT)
+    gen = DatasetGenerator(scene, Wd, Hd, bg=bg, frames_in_flight=NSLOT, overlap_compositing=SPLIT)
     gen.pair_capacity = cap  # calibrated above; the slots' workspaces are already sized
     nc = colors.shape[0]
 
@@ -562,8 +568,10 @@ def run_ours(args):
             "dtype": "f32", "data": "synthetic",
             "config": dict({k: spec[k] for k in ("workload", "env_n", "objects", "obj_n", "views", "width", "height")},
                            parallelism=f"view-parallel x{world} (scene replicated, frames round-robin, pose packets NCCL-broadcast); "
-                                       f"{NSLOT} frames in flight per GPU (one stream + workspace per slot)",
-                           frames_in_flight=NSLOT,
+                                       f"{NSLOT} frames in flight per GPU (one workspace + "
+                                       + ("a high-priority binning stream and a normal-priority compositing stream"
+                                          if SPLIT else "one stream") + " per slot)",
+                           frames_in_flight=NSLOT, split_compositing_stream=bool(SPLIT),
                            cache="inputs larger than L2 (scene parameters 0.7 GB per frame vs 126 MB L2)",
                            pair_capacity=cap, pairs_per_frame=mR, stored_pairs_per_frame=mS, visible_per_frame=mV),
             "clocks": clocks,

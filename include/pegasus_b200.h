@@ -172,6 +172,16 @@ int pg_render_composed(const pg_raster_settings* settings, const pg_gaussians* g
  * on another stream only has to wait for this event, not for the whole frame.  One-shot; NULL clears. */
 int pg_set_scene_read_event(pg_event_t event);
 
+/* Overlapping frames: the NEXT forward / composed render issued by the calling thread launches its
+ * compositing kernel on `composite_stream` instead of `stream`: `fork_event` is recorded on `stream`
+ * after the binning stages and waited for by `composite_stream`; `join_event` is recorded on
+ * `composite_stream` after compositing and waited for by `stream`, so for the caller the whole frame
+ * is still ordered on `stream`.  With `stream` created at a HIGHER priority than `composite_stream`
+ * the latency-bound per-Gaussian / sort stages of the following frame (another stream pair) take the
+ * SM slots that the issue-bound compositing CTAs of this frame free, and the two co-run on every SM.
+ * One-shot; a NULL composite_stream clears. */
+int pg_set_composite_stream(pg_stream_t composite_stream, pg_event_t fork_event, pg_event_t join_event);
+
 /* Asynchronously copies the workspace's status block to host_status (pinned host memory). */
 int pg_read_status(const void* workspace, pg_status* host_status, pg_stream_t stream);
 

@@ -69,7 +69,8 @@ class Status(C.Structure):
 EXPORTS = ["pg_version", "pg_last_error", "pg_workspace_bytes", "pg_rasterize_forward",
            "pg_render_composed", "pg_read_status", "pg_mark_visible", "pg_pose_apply",
            "pg_export_binning", "pg_pack_frame", "pg_profile_enable", "pg_profile_frames",
-           "pg_profile_read", "pg_launch_count", "pg_read_stats", "pg_set_scene_read_event"]
+           "pg_profile_read", "pg_launch_count", "pg_read_stats", "pg_set_scene_read_event",
+           "pg_set_composite_stream"]
 
 NUM_STAGES = 7
 STAGE_NAMES = ["clear", "preprocess", "depth_sort", "emit", "tile_scan", "tile_sort", "composite"]
@@ -113,6 +114,8 @@ def load():
     L.pg_read_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.pg_set_scene_read_event.argtypes = [C.c_void_p]
     L.pg_set_scene_read_event.restype = C.c_int
+    L.pg_set_composite_stream.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.pg_set_composite_stream.restype = C.c_int
     for name in ("pg_profile_enable", "pg_profile_read", "pg_read_stats"):
         getattr(L, name).restype = C.c_int
     for name in ("pg_rasterize_forward", "pg_render_composed", "pg_read_status", "pg_mark_visible",

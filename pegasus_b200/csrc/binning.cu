@@ -100,7 +100,10 @@ emit_kernel(const uint32_t* __restrict__ sorted_dkey, const uint32_t* __restrict
     if (tid == 0) sm.chunk = atomicAdd(&counters->tile_counter[4], 1u);
     __syncthreads();
     const uint32_t chunk = sm.chunk;
-    const uint32_t num_chunks = (P + EMIT_CHUNK - 1) / EMIT_CHUNK;
+    // Culled Gaussians carry the largest depth key and sort behind every visible one: only the first
+    // ceil(num_visible / EMIT_CHUNK) chunks hold rectangles (num_visible is final: preprocess has finished).
+    const uint32_t n_vis = min(counters->num_visible, P);
+    const uint32_t num_chunks = max((n_vis + EMIT_CHUNK - 1) / EMIT_CHUNK, 1u);
     if (chunk >= num_chunks) return;
 
     // ---- (0) gather: thread owns EMIT_EPT consecutive sorted positions (blocked, the scan order)

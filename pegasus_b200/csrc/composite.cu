@@ -187,6 +187,93 @@ __device__ __forceinline__ float exp_sel(float x) {
     return expf_exact_nz(x);
 }
 
+// The producer warp of a compositing CTA (shared by the 1-pixel and the 2-pixel-per-thread kernels):
+// TMA-prefetches the tile's ids in 1 KB chunks, drops culled / no-longer-needed entries by ballot
+// compaction, gathers each surviving 48-byte record into the COMP_STAGES-deep shared-memory ring with
+// cp.async whose completion arrives on the stage's `full` mbarrier.  NCW = number of consumer warps.
+template <bool MASKS, int COMP_STAGES, int NCW, int WAITNS>
+__device__ __forceinline__ void composite_producer(const CompArgs& a, CompSmemT<COMP_STAGES>& sm, const int tile,
+                                                   const uint2 range, const int n, const int lane, const uint32_t lt) {
+    // =========================== PRODUCER ===========================
+    int obj_left = MASKS ? (int)a.tile_obj_count[tile] : 0;  // un-culled object entries not yet compacted
+    // id chunks are fetched by TMA from a 16-byte aligned base; entries outside [range.x, range.y) are ignored
+    const uint32_t a0 = range.x & ~3u;
+    const int span = (int)(range.y - a0);
+    const int nchunks = n > 0 ? (span + COMP_IDCHUNK - 1) / COMP_IDCHUNK : 0;
+    auto fetch_ids = [&](int ci) {
+        if (lane == 0) {
+            const int left = span - ci * COMP_IDCHUNK;
+            const uint32_t bytes = (uint32_t)((min(left, COMP_IDCHUNK) + 3) & ~3) * 4u;
+            uint64_t* bar = reinterpret_cast<uint64_t*>(&sm.idbar[ci & 1]);
+            mbar_expect_tx(bar, bytes);
+            bulk_g2s(sm.ids[ci & 1], a.point_list + a0 + (size_t)ci * COMP_IDCHUNK, bytes, bar);
+        }
+    };
+    if (nchunks > 0) fetch_ids(0);
+    if (nchunks > 1) fetch_ids(1);
+    int ci = 0, head = 0, fill = 0;
+    for (int it = 0;; ++it) {
+        const int s = it % COMP_STAGES;
+        if (it >= COMP_STAGES)
+            mbar_wait_t<(WAITNS < 0 ? -WAITNS : WAITNS)>(reinterpret_cast<uint64_t*>(&sm.empty[s]), (uint32_t)(((it / COMP_STAGES) - 1) & 1));
+        const bool all_done = *(volatile int*)&sm.warps_done == NCW;
+        const bool mode_all = !MASKS || *(volatile int*)&sm.warps_main_done < NCW;
+        while (!all_done && fill < COMP_BATCH && ci < nchunks && (mode_all || obj_left > 0)) {
+            mbar_wait(reinterpret_cast<uint64_t*>(&sm.idbar[ci & 1]), (uint32_t)((ci >> 1) & 1));
+            const uint32_t* src = sm.ids[ci & 1];
+            const uint32_t g0 = a0 + (uint32_t)ci * COMP_IDCHUNK;
+#pragma unroll 4
+            for (int u = 0; u < COMP_IDCHUNK / 32; ++u) {
+                const uint32_t gi = g0 + u * 32 + lane;
+                const uint32_t v = src[u * 32 + lane];
+                const bool live = gi >= range.x && gi < range.y && !(v & PG_CULL_FLAG);
+                const bool is_obj = MASKS && live && v >= a.n_env;
+                const bool keep = live && (mode_all || is_obj);
+                const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+                if (keep) {
+                    const int slot = (head + fill + __popc(bal & lt)) & (COMP_PEND - 1);
+                    sm.pend[slot] = v;
+                    sm.pendpos[slot] = gi - range.x + 1u;
+                }
+                fill += __popc(bal);
+                if (MASKS) obj_left -= __popc(__ballot_sync(0xffffffffu, is_obj));
+            }
+            __syncwarp();
+            if (ci + 2 < nchunks) fetch_ids(ci + 2);
+            ++ci;
+        }
+        __syncwarp();
+        const int cnt = all_done ? 0 : min(fill, COMP_BATCH);
+        if (lane == 0) sm.cnt[s] = cnt;
+        if (!MASKS)
+            for (int e = lane; e < cnt; e += 32) sm.pos[s][e] = sm.pendpos[(head + e) & (COMP_PEND - 1)];
+        __syncwarp();
+        // full[s] expects 33 arrivals: lane 0's release-arrive (publishes cnt / pos) + one per lane that
+        // fires when that lane's cp.async gathers have landed
+        if (lane == 0) mbar_arrive(&sm.full[s]);
+        if (cnt == 0) {
+            mbar_arrive(&sm.full[s]);  // end marker: plain arrivals
+            break;
+        }
+        // gather: 3 x 16-byte cp.async per record (per-lane addresses issue as ordinary SIMT instructions;
+        // a per-record TMA bulk copy needs uniform operands and serialises over the 32 lanes)
+        for (int e = lane; e < cnt; e += 32) {
+            const char* src = reinterpret_cast<const char*>(a.recs + sm.pend[(head + e) & (COMP_PEND - 1)]);
+            const uint32_t dst = smem_u32(&sm.rec[s][e]);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16), "l"(src + 16) : "memory");
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 32), "l"(src + 32) : "memory");
+        }
+        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&sm.full[s])) : "memory");
+        head = (head + cnt) & (COMP_PEND - 1);
+        fill -= cnt;
+        __syncwarp();
+    }
+    // drain id chunks that were fetched but never consumed (never exit with a copy in flight)
+    for (int c2 = ci; c2 < min(nchunks, ci + 2); ++c2)
+        mbar_wait(reinterpret_cast<uint64_t*>(&sm.idbar[c2 & 1]), (uint32_t)((c2 >> 1) & 1));
+}
+
 // Dynamic shared memory after CompSmem (MASKS only): eff[PG_MAX_OBJECTS] float4 (colour the
 // rasterizer produces for object k's flat SH), then Tk[K][256] — the standalone transmittance of
 // object k at each of the tile's 256 pixels (silhouette chains), slot = warp * 32 + lane.
@@ -224,84 +311,7 @@ __global__ void __launch_bounds__(COMP_THREADS, MINB) composite_kernel(const Com
     __syncthreads();
 
     if (warp == 8) {
-        // =========================== PRODUCER ===========================
-        int obj_left = MASKS ? (int)a.tile_obj_count[tile] : 0;  // un-culled object entries not yet compacted
-        // id chunks are fetched by TMA from a 16-byte aligned base; entries outside [range.x, range.y) are ignored
-        const uint32_t a0 = range.x & ~3u;
-        const int span = (int)(range.y - a0);
-        const int nchunks = n > 0 ? (span + COMP_IDCHUNK - 1) / COMP_IDCHUNK : 0;
-        auto fetch_ids = [&](int ci) {
-            if (lane == 0) {
-                const int left = span - ci * COMP_IDCHUNK;
-                const uint32_t bytes = (uint32_t)((min(left, COMP_IDCHUNK) + 3) & ~3) * 4u;
-                uint64_t* bar = reinterpret_cast<uint64_t*>(&sm.idbar[ci & 1]);
-                mbar_expect_tx(bar, bytes);
-                bulk_g2s(sm.ids[ci & 1], a.point_list + a0 + (size_t)ci * COMP_IDCHUNK, bytes, bar);
-            }
-        };
-        if (nchunks > 0) fetch_ids(0);
-        if (nchunks > 1) fetch_ids(1);
-        int ci = 0, head = 0, fill = 0;
-        for (int it = 0;; ++it) {
-            const int s = it % COMP_STAGES;
-            if (it >= COMP_STAGES)
-                mbar_wait_t<(WAITNS < 0 ? -WAITNS : WAITNS)>(reinterpret_cast<uint64_t*>(&sm.empty[s]), (uint32_t)(((it / COMP_STAGES) - 1) & 1));
-            const bool all_done = *(volatile int*)&sm.warps_done == 8;
-            const bool mode_all = !MASKS || *(volatile int*)&sm.warps_main_done < 8;
-            while (!all_done && fill < COMP_BATCH && ci < nchunks && (mode_all || obj_left > 0)) {
-                mbar_wait(reinterpret_cast<uint64_t*>(&sm.idbar[ci & 1]), (uint32_t)((ci >> 1) & 1));
-                const uint32_t* src = sm.ids[ci & 1];
-                const uint32_t g0 = a0 + (uint32_t)ci * COMP_IDCHUNK;
-#pragma unroll 4
-                for (int u = 0; u < COMP_IDCHUNK / 32; ++u) {
-                    const uint32_t gi = g0 + u * 32 + lane;
-                    const uint32_t v = src[u * 32 + lane];
-                    const bool live = gi >= range.x && gi < range.y && !(v & PG_CULL_FLAG);
-                    const bool is_obj = MASKS && live && v >= a.n_env;
-                    const bool keep = live && (mode_all || is_obj);
-                    const uint32_t bal = __ballot_sync(0xffffffffu, keep);
-                    if (keep) {
-                        const int slot = (head + fill + __popc(bal & lt)) & (COMP_PEND - 1);
-                        sm.pend[slot] = v;
-                        sm.pendpos[slot] = gi - range.x + 1u;
-                    }
-                    fill += __popc(bal);
-                    if (MASKS) obj_left -= __popc(__ballot_sync(0xffffffffu, is_obj));
-                }
-                __syncwarp();
-                if (ci + 2 < nchunks) fetch_ids(ci + 2);
-                ++ci;
-            }
-            __syncwarp();
-            const int cnt = all_done ? 0 : min(fill, COMP_BATCH);
-            if (lane == 0) sm.cnt[s] = cnt;
-            if (!MASKS)
-                for (int e = lane; e < cnt; e += 32) sm.pos[s][e] = sm.pendpos[(head + e) & (COMP_PEND - 1)];
-            __syncwarp();
-            // full[s] expects 33 arrivals: lane 0's release-arrive (publishes cnt / pos) + one per lane that
-            // fires when that lane's cp.async gathers have landed
-            if (lane == 0) mbar_arrive(&sm.full[s]);
-            if (cnt == 0) {
-                mbar_arrive(&sm.full[s]);  // end marker: plain arrivals
-                break;
-            }
-            // gather: 3 x 16-byte cp.async per record (per-lane addresses issue as ordinary SIMT instructions;
-            // a per-record TMA bulk copy needs uniform operands and serialises over the 32 lanes)
-            for (int e = lane; e < cnt; e += 32) {
-                const char* src = reinterpret_cast<const char*>(a.recs + sm.pend[(head + e) & (COMP_PEND - 1)]);
-                const uint32_t dst = smem_u32(&sm.rec[s][e]);
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16), "l"(src + 16) : "memory");
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 32), "l"(src + 32) : "memory");
-            }
-            asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&sm.full[s])) : "memory");
-            head = (head + cnt) & (COMP_PEND - 1);
-            fill -= cnt;
-            __syncwarp();
-        }
-        // drain id chunks that were fetched but never consumed (never exit with a copy in flight)
-        for (int c2 = ci; c2 < min(nchunks, ci + 2); ++c2)
-            mbar_wait(reinterpret_cast<uint64_t*>(&sm.idbar[c2 & 1]), (uint32_t)((c2 >> 1) & 1));
+        composite_producer<MASKS, COMP_STAGES, 8, WAITNS>(a, sm, tile, range, n, lane, lt);
         return;
     }
 
@@ -515,6 +525,390 @@ __global__ void __launch_bounds__(COMP_THREADS, MINB) composite_kernel(const Com
     if (STATS) flush_stats(a.stats, n_eval, n_exp, n_blend);
 }
 
+// =================================================================================================
+// 2 pixels per thread: packed FP32 (sm_100 FFMA2 / FMUL2 / FADD2 — PTX fma/mul/add.rn.f32x2).
+//
+// The 1-pixel kernel above is issue-bound (83 % issue-active, FMA pipe 41 %, ALU pipe 39 %): every
+// instruction of the hit loop serves 32 pixels.  Here a warp owns an 8x8 pixel block, a lane owns the two
+// vertically adjacent pixels (x, y0) and (x, y0 + 1), and the per-pixel arithmetic of both runs in ONE packed
+// instruction per operation: each half is an individually rounded IEEE binary32 op in the same order as the
+// scalar kernel (the per-Gaussian operands ride along as broadcast scalars, SASS `R.F32`), so results stay
+// bit-identical to the oracle.  Record loads, hit-list scanning, address arithmetic and the lane-parallel
+// cull (4 consumer warps per tile instead of 8) are shared by the two pixels.
+//
+// Blending is branch-free: a half that does not blend (outside [cut, 0], alpha < 1/255, chain finished)
+// gets alpha = 0, which makes every update an exact no-op (1 - 0 = 1, T * 1 = T, C + 0 * T = C); a finished
+// chain keeps -|T| as in the scalar kernel.  The silhouette chains keep the same sign convention in
+// shared memory (float2 per lane and object).
+//
+// ptxas contracts mul.rn.f32x2 feeding add.rn.f32x2 into FFMA2 (observed with 12.9, unlike the scalar
+// .rn forms), so no packed add here consumes a packed mul: 1 - alpha is fma(alpha, -1, 1), the polynomial
+// and the accumulations are fma by definition, negations ride on scalar operands.
+// =================================================================================================
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpk2(f32x2 v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 bc2(float s) { return pk2(s, s); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+
+// expf_exact_nz on both halves (same operation sequence per half)
+__device__ __forceinline__ void exp2_exact_nz(f32x2 x, float& e0, float& e1) {
+    const f32x2 z = fma2(x, bc2(1.44269502162933349609375f), bc2(12582912.0f));
+    const f32x2 n = add2(z, bc2(-12582912.0f));
+    f32x2 r = fma2(n, bc2(-0.693145751953125f), x);
+    r = fma2(n, bc2(-1.428606765330187045e-06f), r);
+    f32x2 p = bc2(0x1.6b5016p-10f);
+    p = fma2(p, r, bc2(0x1.126caep-7f));
+    p = fma2(p, r, bc2(0x1.55578ep-5f));
+    p = fma2(p, r, bc2(0x1.55540cp-3f));
+    p = fma2(p, r, bc2(0x1.fffffcp-2f));
+    p = fma2(p, r, bc2(1.0f));
+    p = fma2(p, r, bc2(1.0f));
+    float p0, p1, z0, z1;
+    unpk2(p, p0, p1);
+    unpk2(z, z0, z1);
+    e0 = __int_as_float(__float_as_int(p0) + (__float_as_int(z0) << 23));
+    e1 = __int_as_float(__float_as_int(p1) + (__float_as_int(z1) << 23));
+}
+
+// A.7's three skips as ONE predicate chain: !(power > 0) && !(power < cut) && !(alpha < 1/255) (NaNs pass,
+// as in the scalar kernel).  Written in PTX so that it stays 3 FSETP instead of a chain of selects.
+__device__ __forceinline__ bool blends(float power, float cut, float alpha) {
+    uint32_t r;
+    asm("{\n.reg .pred q;\n"
+        "setp.leu.f32 q, %1, 0f00000000;\n"
+        "setp.geu.and.f32 q, %1, %2, q;\n"
+        "setp.geu.and.f32 q, %3, 0f3B808081, q;\n"
+        "selp.u32 %0, 1, 0, q;\n}\n"
+        : "=r"(r) : "f"(power), "f"(cut), "f"(alpha));
+    return r != 0;
+}
+
+constexpr int COMP2_CW = 4;                       // consumer warps: 8x8 pixel blocks of the 16x16 tile
+constexpr int COMP2_THREADS = (COMP2_CW + 1) * 32;
+
+// Dynamic shared memory after CompSmem (MASKS only): eff[PG_MAX_OBJECTS] float4, then Tk2[K][128] float2 —
+// the standalone transmittance of object k at the two pixels of each lane (slot = warp * 32 + lane).
+template <bool MASKS, bool STATS, int COMP_STAGES, int ILP, int MINB>
+__global__ void __launch_bounds__(COMP2_THREADS, MINB) composite2_kernel(const CompArgs a) {
+    using CompSmem = CompSmemT<COMP_STAGES>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    CompSmem& sm = *reinterpret_cast<CompSmem*>(smem_raw);
+    float4* sm_eff = reinterpret_cast<float4*>(smem_raw + sizeof(CompSmem));
+    float2* sm_tk = reinterpret_cast<float2*>(smem_raw + sizeof(CompSmem) + PG_MAX_OBJECTS * sizeof(float4));
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tile = (int)a.tile_order[blockIdx.x];
+    const int tile_x = tile % a.gx, tile_y = tile / a.gx;
+    const uint2 range = a.ranges[tile];
+    const int n = (int)(range.y - range.x);
+    const uint32_t lt = (1u << lane) - 1u;
+
+    if (tid == 0) {
+        for (int s = 0; s < COMP_STAGES; ++s) {
+            mbar_init(reinterpret_cast<uint64_t*>(&sm.full[s]), 33);
+            mbar_init(reinterpret_cast<uint64_t*>(&sm.empty[s]), COMP2_CW);
+        }
+        mbar_init(reinterpret_cast<uint64_t*>(&sm.idbar[0]), 1);
+        mbar_init(reinterpret_cast<uint64_t*>(&sm.idbar[1]), 1);
+        sm.warps_done = 0;
+        sm.warps_main_done = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (MASKS && tid < a.num_objects)
+        sm_eff[tid] = make_float4(a.eff_color[tid][0], a.eff_color[tid][1], a.eff_color[tid][2], 0.0f);
+    __syncthreads();
+
+    if (warp == COMP2_CW) {
+        composite_producer<MASKS, COMP_STAGES, COMP2_CW, 0>(a, sm, tile, range, n, lane, lt);
+        return;
+    }
+
+    // =========================== CONSUMERS ===========================
+    const int wx0 = tile_x * PG_TILE + (warp & 1) * 8, wy0 = tile_y * PG_TILE + (warp >> 1) * 8;
+    const int px = wx0 + (lane & 7), py0 = wy0 + (lane >> 3) * 2, py1 = py0 + 1;
+    const bool in0 = px < a.W && py0 < a.H, in1 = px < a.W && py1 < a.H;
+    float pfx = (float)px;
+    asm volatile("" : "+f"(pfx));
+    const f32x2 npfy = pk2(-(float)py0, -(float)py1);
+    const float bx0 = (float)wx0, bx1 = (float)min(wx0 + 7, a.W - 1);
+    const float by0 = (float)wy0, by1 = (float)min(wy0 + 7, a.H - 1);
+    const int K = MASKS ? a.num_objects : 0;
+    const uint32_t all_k = K >= 32 ? 0xFFFFFFFFu : ((1u << K) - 1u);
+    float2* my_tk = sm_tk + (warp * 32 + lane);  // object k's chains at my_tk[k * 128]
+    if (MASKS)
+        for (int k = 0; k < K; ++k) my_tk[k * 128] = make_float2(in0 ? 1.0f : -1.0f, in1 ? 1.0f : -1.0f);
+
+    // finished chains keep -|T| (see the scalar kernel)
+    f32x2 T = pk2(in0 ? 1.0f : -1.0f, in1 ? 1.0f : -1.0f);
+    f32x2 To = pk2((in0 && MASKS) ? 1.0f : -1.0f, (in1 && MASKS) ? 1.0f : -1.0f);
+    f32x2 C0 = bc2(0.0f), C1 = C0, C2 = C0, D = C0, S0 = C0, S1 = C0, S2 = C0;
+    uint32_t dk0 = (in0 && MASKS) ? 0u : 0xFFFFFFFFu, dk1 = (in1 && MASKS) ? 0u : 0xFFFFFFFFu;
+    uint32_t last0 = 0, last1 = 0;
+    uint32_t n_eval = 0, n_exp = 0, n_blend = 0;
+    bool w_main_done = false, w_done = false;
+    const f32x2 ONE = bc2(1.0f), MONE = bc2(-1.0f);
+
+    for (int it = 0;; ++it) {
+        const int s = it % COMP_STAGES;
+        mbar_wait(reinterpret_cast<uint64_t*>(&sm.full[s]), (uint32_t)((it / COMP_STAGES) & 1));
+        const int cnt = *(volatile int*)&sm.cnt[s];
+        if (cnt == 0) break;
+        if (!w_done) {
+            const GeomRec* sr = sm.rec[s];
+            bool wm = !w_main_done;
+#pragma unroll 1
+            for (int c0 = 0; c0 < cnt; c0 += 32) {
+                const int e = c0 + lane;
+                uint32_t need = 0;
+                if (MASKS && !wm) {
+                    float to0, to1;
+                    unpk2(To, to0, to1);
+                    need = __any_sync(0xffffffffu, to0 > 0.0f || to1 > 0.0f)
+                               ? all_k : (__reduce_or_sync(0xffffffffu, ~(dk0 & dk1)) & all_k);
+                    if (need == 0) break;
+                }
+                bool hit = false;
+                if (e < cnt) {
+                    const float4 A = sr[e].a;
+                    const float4 B = sr[e].b;
+                    const int eo = MASKS ? (__float_as_int(B.w) & 63) : 0;
+                    const bool wanted = wm || (MASKS && eo > 0 && ((need >> ((uint32_t)(eo - 1) & 31u)) & 1u));
+                    hit = wanted && !block_culled(A.x, A.y, A.z, A.w, B.x, B.w, bx0, bx1, by0, by1);
+                }
+                uint32_t mm = __ballot_sync(0xffffffffu, hit);
+
+                // power of one Gaussian at the lane's two pixels (A.7 operation order per half)
+                auto power_of = [&](const float4& A, const float4& B) -> f32x2 {
+                    const float dx = sub(A.x, pfx);
+                    const float t1 = mul(A.z, dx);     // conic.x * dx
+                    const float nt2 = mul(-A.w, dx);   // -(conic.y * dx)
+                    const f32x2 dy = add2(bc2(A.y), npfy);
+                    const f32x2 w = mul2(dy, mul2(bc2(B.x), dy));
+                    const f32x2 sq = fma2(bc2(dx), bc2(t1), w);
+                    const f32x2 nbxy = mul2(bc2(nt2), dy);
+                    return fma2(sq, bc2(-0.5f), nbxy);
+                };
+                // alpha of both halves; v = the half blends at all (A.7's three skips)
+                auto alpha_of = [&](f32x2 pw, const float4& B, float& a0, float& a1, bool& v0, bool& v1) {
+                    float e0, e1, p0, p1;
+                    exp2_exact_nz(pw, e0, e1);
+                    unpk2(pw, p0, p1);
+                    a0 = fminf(0.99f, mul(B.y, e0));
+                    a1 = fminf(0.99f, mul(B.y, e1));
+                    v0 = blends(p0, B.w, a0);
+                    v1 = blends(p1, B.w, a1);
+                    if (STATS) {
+                        float t0, t1, o0, o1;
+                        unpk2(T, t0, t1);
+                        unpk2(To, o0, o1);
+                        const int obj = MASKS ? (__float_as_int(B.w) & 63) : 0;
+                        const bool l0 = t0 > 0.0f || (MASKS && obj > 0 && (o0 > 0.0f || !((dk0 >> (obj - 1)) & 1u)));
+                        const bool l1 = t1 > 0.0f || (MASKS && obj > 0 && (o1 > 0.0f || !((dk1 >> (obj - 1)) & 1u)));
+                        n_eval += (l0 ? 1 : 0) + (l1 ? 1 : 0);
+                        n_exp += ((l0 && !(p0 > 0.0f) && !(p0 < B.w)) ? 1 : 0) + ((l1 && !(p1 > 0.0f) && !(p1 < B.w)) ? 1 : 0);
+                        n_blend += ((l0 && v0) ? 1 : 0) + ((l1 && v1) ? 1 : 0);
+                    }
+                };
+                // one transmittance chain, both halves: returns the chain's alpha (0 where it does not blend)
+                auto chain = [&](f32x2& Tc, f32x2 om, float av0, float av1, float& am0, float& am1) {
+                    const f32x2 tT = mul2(Tc, om);
+                    float n0, n1, o0, o1;
+                    unpk2(tT, n0, n1);
+                    unpk2(Tc, o0, o1);
+                    const bool d0 = n0 < 0.0001f, d1 = n1 < 0.0001f;
+                    am0 = d0 ? 0.0f : av0;
+                    am1 = d1 ? 0.0f : av1;
+                    Tc = pk2(d0 ? -fabsf(o0) : n0, d1 ? -fabsf(o1) : n1);
+                };
+                auto blend = [&](const GeomRec* r, const float4& B, float a0, float a1, bool v0, bool v1) {
+                    const float av0 = v0 ? a0 : 0.0f, av1 = v1 ? a1 : 0.0f;
+                    const f32x2 om = fma2(pk2(av0, av1), MONE, ONE);  // 1 - alpha
+                    {
+                        const f32x2 Told = T;
+                        float am0, am1;
+                        chain(T, om, av0, av1, am0, am1);
+                        const f32x2 am = pk2(am0, am1);
+                        const float4 Cc = r->c;
+                        C0 = fma2(mul2(bc2(Cc.x), am), Told, C0);
+                        C1 = fma2(mul2(bc2(Cc.y), am), Told, C1);
+                        C2 = fma2(mul2(bc2(Cc.z), am), Told, C2);
+                        D = fma2(mul2(bc2(B.z), am), Told, D);
+                        if (!MASKS) {
+                            const uint32_t pos = sm.pos[s][r - sr];
+                            if (am0 > 0.0f) last0 = pos;
+                            if (am1 > 0.0f) last1 = pos;
+                        }
+                    }
+                    const int obj = MASKS ? (__float_as_int(B.w) & 63) : 0;  // warp-uniform
+                    if (MASKS && obj > 0) {
+                        {
+                            const f32x2 Told = To;
+                            float am0, am1;
+                            chain(To, om, av0, av1, am0, am1);
+                            const f32x2 am = pk2(am0, am1);
+                            const float4 ec = sm_eff[obj - 1];
+                            S0 = fma2(mul2(bc2(ec.x), am), Told, S0);
+                            S1 = fma2(mul2(bc2(ec.y), am), Told, S1);
+                            S2 = fma2(mul2(bc2(ec.z), am), Told, S2);
+                        }
+                        const uint32_t kbit = 1u << ((uint32_t)(obj - 1) & 31u);
+                        const float2 tk = my_tk[(obj - 1) * 128];
+                        const f32x2 tT = mul2(pk2(tk.x, tk.y), om);
+                        float n0, n1;
+                        unpk2(tT, n0, n1);
+                        const bool d0 = n0 < 0.0001f, d1 = n1 < 0.0001f;  // also true for a finished (negative) chain
+                        if (d0) dk0 |= kbit;
+                        if (d1) dk1 |= kbit;
+                        my_tk[(obj - 1) * 128] = make_float2(d0 ? -fabsf(tk.x) : n0, d1 ? -fabsf(tk.y) : n1);
+                    }
+                };
+#pragma unroll 1
+                while (mm) {
+                    const GeomRec* r1 = sr + (c0 + __ffs(mm) - 1);
+                    mm &= mm - 1;
+                    if (ILP == 2) {
+                        const bool two = mm != 0;  // warp-uniform
+                        const GeomRec* r2 = two ? sr + (c0 + __ffs(mm) - 1) : r1;
+                        mm &= mm - 1;
+                        const float4 A1 = r1->a, B1 = r1->b, A2 = r2->a, B2 = r2->b;
+                        const f32x2 p1 = power_of(A1, B1), p2 = power_of(A2, B2);
+                        float a10, a11, a20, a21;
+                        bool v10, v11, v20, v21;
+                        alpha_of(p1, B1, a10, a11, v10, v11);
+                        alpha_of(p2, B2, a20, a21, v20, v21);
+                        // without a second hit r2 == r1 blends with alpha 0: an exact no-op, cheaper than a branch
+                        // whose two sides keep the accumulators in different registers
+                        blend(r1, B1, a10, a11, v10, v11);
+                        blend(r2, B2, a20, a21, v20 && two, v21 && two);
+                    } else {
+                        const float4 A1 = r1->a, B1 = r1->b;
+                        const f32x2 p1 = power_of(A1, B1);
+                        float a10, a11;
+                        bool v10, v11;
+                        alpha_of(p1, B1, a10, a11, v10, v11);
+                        blend(r1, B1, a10, a11, v10, v11);
+                    }
+                }
+                if (wm) {
+                    float t0, t1;
+                    unpk2(T, t0, t1);
+                    if (__all_sync(0xffffffffu, t0 < 0.0f && t1 < 0.0f)) {
+                        wm = false;
+                        if (!MASKS) break;
+                    }
+                }
+            }
+            if (!w_main_done && !wm) {
+                w_main_done = true;
+                if (lane == 0) atomicAdd(&sm.warps_main_done, 1);
+            }
+            float t0, t1, o0, o1;
+            unpk2(T, t0, t1);
+            unpk2(To, o0, o1);
+            const bool pix_done = t0 < 0.0f && t1 < 0.0f &&
+                                  (!MASKS || (o0 < 0.0f && o1 < 0.0f && (dk0 & dk1 & all_k) == all_k));
+            if (__all_sync(0xffffffffu, pix_done)) {
+                w_done = true;
+                if (lane == 0) atomicAdd(&sm.warps_done, 1);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.empty[s]);
+    }
+
+    const size_t HW = (size_t)a.W * a.H;
+    const float bg0 = a.bg[0], bg1 = a.bg[1], bg2 = a.bg[2];
+    float Th[2], Toh[2], Ch[3][2], Dh[2], Sh[3][2];
+    unpk2(T, Th[0], Th[1]); unpk2(To, Toh[0], Toh[1]);
+    unpk2(C0, Ch[0][0], Ch[0][1]); unpk2(C1, Ch[1][0], Ch[1][1]); unpk2(C2, Ch[2][0], Ch[2][1]);
+    unpk2(D, Dh[0], Dh[1]);
+    unpk2(S0, Sh[0][0], Sh[0][1]); unpk2(S1, Sh[1][0], Sh[1][1]); unpk2(S2, Sh[2][0], Sh[2][1]);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        if (!(h == 0 ? in0 : in1)) continue;
+        const float Tf = fabsf(Th[h]), Tof = fabsf(Toh[h]);
+        const size_t pix = (size_t)(h == 0 ? py0 : py1) * a.W + px;
+        a.out_color[pix] = fma(Tf, bg0, Ch[0][h]);
+        a.out_color[HW + pix] = fma(Tf, bg1, Ch[1][h]);
+        a.out_color[2 * HW + pix] = fma(Tf, bg2, Ch[2][h]);
+        a.out_depth[pix] = Dh[h];
+        if (a.out_final_T) a.out_final_T[pix] = Tf;
+        if (!MASKS && a.out_n_contrib) a.out_n_contrib[pix] = h == 0 ? last0 : last1;
+        if (MASKS) {
+            const float s0 = fma(Tof, bg0, Sh[0][h]), s1 = fma(Tof, bg1, Sh[1][h]), s2 = fma(Tof, bg2, Sh[2][h]);
+            if (a.seg_color) {
+                a.seg_color[pix] = s0; a.seg_color[HW + pix] = s1; a.seg_color[2 * HW + pix] = s2;
+            }
+            if (a.sem_seg) {
+                a.sem_seg[3 * pix] = (uint8_t)(int)mul(s0, 255.0f);
+                a.sem_seg[3 * pix + 1] = (uint8_t)(int)mul(s1, 255.0f);
+                a.sem_seg[3 * pix + 2] = (uint8_t)(int)mul(s2, 255.0f);
+            }
+            if (a.visible) {
+                for (int c = 0; c < a.num_colors; ++c) {
+                    float d0 = sub(s0, a.set_color[c][0]), d1 = sub(s1, a.set_color[c][1]), d2 = sub(s2, a.set_color[c][2]);
+                    float dist = sqrt(add(add(mul(d0, d0), mul(d1, d1)), mul(d2, d2)));
+                    a.visible[(size_t)c * HW + pix] = dist <= 0.1f ? 1 : 0;
+                }
+            }
+            if (a.silhouette) {
+                for (int kk = 0; kk < K; ++kk) {
+                    const int ci = a.color_index[kk];
+                    const float2 t2 = my_tk[kk * 128];
+                    const float tk = fabsf(h == 0 ? t2.x : t2.y);
+                    const float4 ec = sm_eff[kk];
+                    const float w = sub(1.0f, tk);
+                    float i0 = fma(tk, bg0, mul(ec.x, w));
+                    float i1 = fma(tk, bg1, mul(ec.y, w));
+                    float i2 = fma(tk, bg2, mul(ec.z, w));
+                    float d0 = sub(i0, a.set_color[ci][0]), d1 = sub(i1, a.set_color[ci][1]), d2 = sub(i2, a.set_color[ci][2]);
+                    float dist = sqrt(add(add(mul(d0, d0), mul(d1, d1)), mul(d2, d2)));
+                    a.silhouette[(size_t)ci * HW + pix] = dist <= 0.1f ? 1 : 0;
+                }
+            }
+        }
+    }
+    if (STATS) flush_stats(a.stats, n_eval, n_exp, n_blend);
+}
+
+template <bool MASKS, bool STATS, int STAGES, int ILP, int MINB>
+static int launch_two(const CompArgs& a, dim3 grid, cudaStream_t stream) {
+    static int attr_smem = 0;
+    const int smem = (int)sizeof(CompSmemT<STAGES>) +
+                     (MASKS ? (int)(PG_MAX_OBJECTS * sizeof(float4)) + a.num_objects * 256 * (int)sizeof(float) : 0);
+    if (smem > attr_smem) {
+        PG_CUDA_CHECK(cudaFuncSetAttribute(composite2_kernel<MASKS, STATS, STAGES, ILP, MINB>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        // residency is bounded by shared memory (~39 KB per CTA): ask for the largest carve-out
+        PG_CUDA_CHECK(cudaFuncSetAttribute(composite2_kernel<MASKS, STATS, STAGES, ILP, MINB>,
+                                           cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        attr_smem = smem;
+    }
+    composite2_kernel<MASKS, STATS, STAGES, ILP, MINB><<<grid, COMP2_THREADS, smem, stream>>>(a);
+    return PG_OK;
+}
+
 template <bool MASKS, bool STATS, int STAGES, int ILP, int MINB, int WAITNS = 0, bool FASTEXP = false>
 static int launch_one(const CompArgs& a, dim3 grid, cudaStream_t stream) {
     static int attr_smem = 0;
@@ -529,14 +923,16 @@ static int launch_one(const CompArgs& a, dim3 grid, cudaStream_t stream) {
     return PG_OK;
 }
 
-// PG_COMP_VARIANT (tuning only, read once).  Measured on B200, C2 workload (profiles/README.md, r1t):
-// 0: 4 stages, ILP 1 -> 1.235 ms; 1: 6 stages 1.222; 2: 8 stages (3 CTAs/SM) 1.355; 3: ILP 2 1.139;
-// 4 (default): ILP 2, registers bounded for 3 CTAs/SM 1.119; 5: 6 stages + ILP 2 1.120.
+// PG_COMP_VARIANT (tuning only, read once).  Measured on B200, C2 workload (profiles/README.md):
+//  1-pixel kernel (r1t): 0: 4 stages, ILP 1 -> 1.235 ms; 1: 6 stages 1.222; 3: ILP 2 1.139; 4: ILP 2, registers
+//    bounded for 3 CTAs/SM 1.119; 9: variant 4 with MUFU ex2 (NOT bit-reproducible, measurement only) 1.019.
+//  2-pixel packed kernel (r1ac): 20 (default): ILP 2, 79 registers, 5 CTAs/SM 1.051 ms; 22: 72 registers 1.098;
+//    21: ILP 1 1.176; 28 / 26 / 27: 3-stage ring for 5-6 CTAs/SM 1.175 / 1.211 / 1.261.
 static int comp_variant() {
     static int v = -1;
     if (v < 0) {
         const char* e = getenv("PG_COMP_VARIANT");
-        v = e ? atoi(e) : 4;
+        v = e ? atoi(e) : 20;
     }
     return v;
 }
@@ -544,23 +940,34 @@ static int comp_variant() {
 int launch_composite(const CompArgs& a, int gy, bool masks, cudaStream_t stream) {
     dim3 grid(a.gx * gy);
     const bool st = a.stats != nullptr;
+    const int var = comp_variant();
     int rc;
-    if (!masks) rc = st ? launch_one<false, true, 4, 1, 4>(a, grid, stream) : launch_one<false, false, 4, 1, 4>(a, grid, stream);
+    if (var >= 20) {
+        // 2 pixels per thread, packed FP32 (composite2_kernel).  20: ILP 2, 4 CTAs/SM; 21: ILP 1, 5 CTAs/SM;
+        // 22: ILP 2, 5 CTAs/SM; 23: ILP 2, 6 stages; 24: ILP 1, 6 CTAs/SM; 25: ILP 2, 3 CTAs/SM
+        if (!masks) rc = st ? launch_two<false, true, 4, 1, 4>(a, grid, stream) : launch_two<false, false, 4, 2, 4>(a, grid, stream);
+        else if (st) rc = launch_two<true, true, 4, 1, 4>(a, grid, stream);
+        else {
+            switch (var) {
+                case 21: rc = launch_two<true, false, 4, 1, 5>(a, grid, stream); break;
+                case 22: rc = launch_two<true, false, 4, 2, 5>(a, grid, stream); break;
+                case 23: rc = launch_two<true, false, 6, 2, 4>(a, grid, stream); break;
+                case 24: rc = launch_two<true, false, 4, 1, 6>(a, grid, stream); break;
+                case 25: rc = launch_two<true, false, 4, 2, 3>(a, grid, stream); break;
+                case 26: rc = launch_two<true, false, 3, 2, 6>(a, grid, stream); break;
+                case 27: rc = launch_two<true, false, 3, 1, 6>(a, grid, stream); break;
+                case 28: rc = launch_two<true, false, 3, 2, 5>(a, grid, stream); break;
+                default: rc = launch_two<true, false, 4, 2, 4>(a, grid, stream); break;
+            }
+        }
+    } else if (!masks) rc = st ? launch_one<false, true, 4, 1, 4>(a, grid, stream) : launch_one<false, false, 4, 1, 4>(a, grid, stream);
     else if (st) rc = launch_one<true, true, 4, 1, 4>(a, grid, stream);
     else {
-        switch (comp_variant()) {
+        switch (var) {
             case 1: rc = launch_one<true, false, 6, 1, 4>(a, grid, stream); break;
-            case 2: rc = launch_one<true, false, 8, 1, 4>(a, grid, stream); break;
             case 3: rc = launch_one<true, false, 4, 2, 4>(a, grid, stream); break;
-            case 5: rc = launch_one<true, false, 6, 2, 3>(a, grid, stream); break;
-            case 6: rc = launch_one<true, false, 4, 1, 3>(a, grid, stream); break;
             case 0: rc = launch_one<true, false, 4, 1, 4>(a, grid, stream); break;
-            case 7: rc = launch_one<true, false, 4, 2, 3, 20>(a, grid, stream); break;
-            case 8: rc = launch_one<true, false, 4, 2, 3, 100>(a, grid, stream); break;
             case 9: rc = launch_one<true, false, 4, 2, 3, 0, true>(a, grid, stream); break;
-            case 10: rc = launch_one<true, false, 4, 2, 3, 400>(a, grid, stream); break;
-            case 11: rc = launch_one<true, false, 4, 2, 3, -100>(a, grid, stream); break;
-            case 12: rc = launch_one<true, false, 4, 2, 3, -400>(a, grid, stream); break;
             default: rc = launch_one<true, false, 4, 2, 3>(a, grid, stream); break;
         }
     }

@@ -74,6 +74,34 @@ static int g_prof_max = 0;
 static std::atomic<int> g_prof_frames{0};
 static thread_local int t_prof_frame = -1;  // slot of the forward in flight on this thread
 static thread_local cudaEvent_t t_scene_read_event = nullptr;  // pg_set_scene_read_event (one-shot)
+// pg_set_composite_stream (one-shot)
+static thread_local cudaStream_t t_comp_stream = nullptr;
+static thread_local cudaEvent_t t_comp_fork = nullptr, t_comp_join = nullptr;
+static thread_local bool t_comp_split = false;
+
+// Takes the one-shot request: returns the stream compositing runs on and makes it wait for everything
+// enqueued on `stream` so far.
+static bool take_comp_request() {  // every entry point consumes the request, also when it fails early
+    const bool on = t_comp_split;
+    t_comp_split = false;
+    return on;
+}
+static int comp_fork(bool split, cudaStream_t stream, cudaStream_t* cs, cudaEvent_t* join) {
+    *cs = stream;
+    *join = nullptr;
+    if (!split) return PG_OK;
+    PG_CUDA_CHECK(cudaEventRecord(t_comp_fork, stream));
+    PG_CUDA_CHECK(cudaStreamWaitEvent(t_comp_stream, t_comp_fork, 0));
+    *cs = t_comp_stream;
+    *join = t_comp_join;
+    return PG_OK;
+}
+static int comp_join(cudaStream_t stream, cudaStream_t cs, cudaEvent_t join) {
+    if (!join) return PG_OK;
+    PG_CUDA_CHECK(cudaEventRecord(join, cs));
+    PG_CUDA_CHECK(cudaStreamWaitEvent(stream, join, 0));
+    return PG_OK;
+}
 
 static void prof_begin_frame() {
     t_prof_frame = -1;
@@ -219,6 +247,7 @@ size_t pg_workspace_bytes(int32_t P, int32_t width, int32_t height, uint64_t pai
 int pg_rasterize_forward(const pg_raster_settings* s, const pg_gaussians* g, const pg_raster_outputs* out,
                          void* ws, size_t ws_bytes, uint64_t pair_capacity, pg_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
+    const bool split = take_comp_request();
     int rc = check_common(s, g, pair_capacity);
     if (rc) return rc;
     if (!out || !out->color || !out->radii || !out->depth || !ws) { set_error("null output/workspace"); return PG_ERR_INVALID; }
@@ -229,18 +258,23 @@ int pg_rasterize_forward(const pg_raster_settings* s, const pg_gaussians* g, con
     const bool keep_all = (s->debug & 4) != 0 || out->n_contrib != nullptr;
     rc = run_binning(s, g, nullptr, out->radii, ws, L, pair_capacity, keep_all, stream);
     if (rc) return rc;
+    cudaStream_t cs; cudaEvent_t join;
+    rc = comp_fork(split, stream, &cs, &join);
+    if (rc) return rc;
     rc = launch_composite_from_abi(at<uint2>(ws, L.ranges), at<uint32_t>(ws, L.tile_order), sorted_point_list(ws, L), at<GeomRec>(ws, L.recs),
                                    s->image_width, s->image_height, s->bg, out, nullptr, nullptr,
                                    (uint32_t)g->P, at<uint32_t>(ws, L.tile_obj_count),
-                                   (s->debug & 2) ? at<Counters>(ws, L.counters)->stats : nullptr, stream);
+                                   (s->debug & 2) ? at<Counters>(ws, L.counters)->stats : nullptr, cs);
+    const int rj = comp_join(stream, cs, join);
     prof_mark(7, stream);
-    return rc;
+    return rc ? rc : rj;
 }
 
 int pg_render_composed(const pg_raster_settings* s, const pg_gaussians* g, const pg_object_table* objs,
                        const pg_frame_outputs* out, void* ws, size_t ws_bytes, uint64_t pair_capacity,
                        pg_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
+    const bool split = take_comp_request();
     int rc = check_common(s, g, pair_capacity);
     if (rc) return rc;
     if (!objs || !out || !out->color || !out->radii || !out->depth || !ws) { set_error("null argument"); return PG_ERR_INVALID; }
@@ -258,18 +292,32 @@ int pg_render_composed(const pg_raster_settings* s, const pg_gaussians* g, const
     rc = run_binning(s, g, objs, out->radii, ws, L, pair_capacity, (s->debug & 4) != 0, stream);
     if (rc) return rc;
     const uint32_t n_env = objs->num_objects > 0 ? (uint32_t)objs->first[0] : (uint32_t)g->P;
+    cudaStream_t cs; cudaEvent_t join;
+    rc = comp_fork(split, stream, &cs, &join);
+    if (rc) return rc;
     if (out->silhouette && objs->num_colors > 0)
-        PG_CUDA_CHECK(cudaMemsetAsync(out->silhouette, 0, (size_t)objs->num_colors * s->image_width * s->image_height, stream));
+        PG_CUDA_CHECK(cudaMemsetAsync(out->silhouette, 0, (size_t)objs->num_colors * s->image_width * s->image_height, cs));
     rc = launch_composite_from_abi(at<uint2>(ws, L.ranges), at<uint32_t>(ws, L.tile_order), sorted_point_list(ws, L), at<GeomRec>(ws, L.recs),
                                    s->image_width, s->image_height, s->bg, nullptr, out, objs, n_env,
                                    at<uint32_t>(ws, L.tile_obj_count),
-                                   (s->debug & 2) ? at<Counters>(ws, L.counters)->stats : nullptr, stream);
+                                   (s->debug & 2) ? at<Counters>(ws, L.counters)->stats : nullptr, cs);
+    const int rj = comp_join(stream, cs, join);
     prof_mark(7, stream);
-    return rc;
+    return rc ? rc : rj;
 }
 
 int pg_set_scene_read_event(pg_event_t event) {
     t_scene_read_event = (cudaEvent_t)event;
+    return PG_OK;
+}
+
+int pg_set_composite_stream(pg_stream_t composite_stream, pg_event_t fork_event, pg_event_t join_event) {
+    if (!composite_stream) { t_comp_split = false; return PG_OK; }
+    if (!fork_event || !join_event) { set_error("pg_set_composite_stream needs a fork and a join event"); return PG_ERR_INVALID; }
+    t_comp_stream = (cudaStream_t)composite_stream;
+    t_comp_fork = (cudaEvent_t)fork_event;
+    t_comp_join = (cudaEvent_t)join_event;
+    t_comp_split = true;
     return PG_OK;
 }
 

@@ -69,7 +69,8 @@ class DatasetGenerator:
     """Renders a camera path over a ComposedScene and hands packed frame products to a writer."""
 
     def __init__(self, scene: ComposedScene, width: int, height: int, bg: Optional[torch.Tensor] = None,
-                 frames_in_flight: int = 3, host_sets: Optional[int] = None, writer_threads: int = 4):
+                 frames_in_flight: int = 3, host_sets: Optional[int] = None, writer_threads: int = 4,
+                 overlap_compositing: bool = True):
         self.scene = scene
         self.dev = scene.device
         self.W, self.H = int(width), int(height)
@@ -79,7 +80,13 @@ class DatasetGenerator:
         self.K = len(scene.object_ids)
         self.writer_threads = max(1, int(writer_threads))
         dev, W, H, nc = self.dev, self.W, self.H, self.nc
-        self.streams = [torch.cuda.Stream(device=dev) for _ in range(self.nslot)]
+        # Each slot owns a HIGH-priority stream (pose, per-Gaussian stage, sorts, packing, copies) and a
+        # normal-priority one for the compositing kernel (pg_set_composite_stream): the latency-bound
+        # stages of frame i+1 take the SM slots frame i's compositing CTAs free and co-run with them.
+        self.overlap = bool(overlap_compositing) and self.nslot > 1
+        self.streams = [torch.cuda.Stream(device=dev, priority=-1 if self.overlap else 0) for _ in range(self.nslot)]
+        self.comp_streams = [torch.cuda.Stream(device=dev, priority=0) if self.overlap else None
+                             for _ in range(self.nslot)]
         self.outs = [scene.alloc_outputs(W, H, masks=True) for _ in range(self.nslot)]
         self.packs = [dict(rgb=torch.empty((H, W, 3), dtype=torch.uint8, device=dev),
                            depth=torch.empty((H, W), dtype=torch.int16, device=dev)) for _ in range(self.nslot)]
@@ -136,7 +143,7 @@ class DatasetGenerator:
                 sc.apply_pose_packets(self.pose_dev[sl])
             o = self.outs[sl]
             sc.render(cs, self.bg, masks=True, out=o, sync_check=False, pair_capacity=self.pair_capacity, slot=sl,
-                      scene_read_event=self.read_ev[sl] if dynamic else None)
+                      scene_read_event=self.read_ev[sl] if dynamic else None, composite_stream=self.comp_streams[sl])
             _lib.check(L.pg_pack_frame(self.W, self.H, C.c_void_p(o["color"].data_ptr()),
                                        C.c_void_p(o["depth"].data_ptr()), C.c_void_p(self.packs[sl]["rgb"].data_ptr()),
                                        C.c_void_p(self.packs[sl]["depth"].data_ptr()), C.c_void_p(st.cuda_stream)),

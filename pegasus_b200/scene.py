@@ -173,14 +173,18 @@ class ComposedScene:
     def render(self, cam, bg: torch.Tensor, masks: bool = True, out: Optional[Dict] = None, sh_degree: int = 3,
                sync_check: bool = True, pair_capacity: Optional[int] = None, debug: int = 0,
                reference_lists: bool = False, slot: int = 0,
-               scene_read_event: Optional[torch.cuda.Event] = None) -> Dict[str, torch.Tensor]:
+               scene_read_event: Optional[torch.cuda.Event] = None,
+               composite_stream: Optional[torch.cuda.Stream] = None) -> Dict[str, torch.Tensor]:
         """One frame: RGB + depth (+ seg render, sem-seg, visible and silhouette masks when
         masks=True) — everything the reference's K+3 passes produce (src/gs/render.py:14-129).
 
         The frame is enqueued on the current CUDA stream.  `slot` selects the workspace: frames in
         flight concurrently on different streams need distinct slots (and distinct `out` buffers).
         `scene_read_event` is recorded right after the per-Gaussian stage, the last reader of the scene
-        arrays: the next frame's apply_pose_packets (on another stream) only has to wait for it."""
+        arrays: the next frame's apply_pose_packets (on another stream) only has to wait for it.
+        `composite_stream`: the compositing kernel runs there (pg_set_composite_stream), forked from and
+        joined back into the current stream; give the current stream the higher priority and the
+        following frame's per-Gaussian / sort stages co-run with this frame's compositing."""
         L = _lib.load()
         H, W = int(cam.image_height), int(cam.image_width)
         if out is None:
@@ -211,6 +215,11 @@ class ComposedScene:
                 if scene_read_event is not None:
                     scene_read_event.record(stream)  # creates the lazily-initialised handle; re-recorded by the library
                     _lib.check(L.pg_set_scene_read_event(C.c_void_p(scene_read_event.cuda_event)), "pg_set_scene_read_event")
+                if composite_stream is not None:
+                    fork, join = _split_events(self.device, slot, stream)
+                    _lib.check(L.pg_set_composite_stream(C.c_void_p(composite_stream.cuda_stream),
+                                                         C.c_void_p(fork.cuda_event), C.c_void_p(join.cuda_event)),
+                               "pg_set_composite_stream")
                 rc = L.pg_render_composed(C.byref(s), C.byref(g), C.byref(table), C.byref(fo),
                                           C.c_void_p(buf.data_ptr()), buf.numel(), cap,
                                           C.c_void_p(stream.cuda_stream))
@@ -254,6 +263,22 @@ class ComposedScene:
         stream.synchronize()
         return dict(num_rendered=int(ws.status_host[0]) & 0xFFFFFFFF, overflow=int(ws.status_host[1]),
                     num_visible=int(ws.status_host[2]), num_stored=int(ws.status_host[3]) & 0xFFFFFFFF)
+
+
+_SPLIT_EVENTS: Dict = {}
+
+
+def _split_events(device, slot: int, stream):
+    """Fork / join events of one workspace slot (created once; torch creates the CUDA handle at the first
+    record)."""
+    key = (torch.device(device).index, slot)
+    ev = _SPLIT_EVENTS.get(key)
+    if ev is None:
+        ev = (torch.cuda.Event(), torch.cuda.Event())
+        for e in ev:
+            e.record(stream)
+        _SPLIT_EVENTS[key] = ev
+    return ev
 
 
 def export_binning(device, P: int, W: int, H: int, pair_capacity: int, num_rendered: int):

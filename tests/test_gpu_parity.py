@@ -416,10 +416,12 @@ def test_render_helpers_return_reference_shapes():
     assert ((vis == 1) & (sil == 0)).sum() <= 5
 
 
-def test_pipelined_frames_on_three_streams_match_sequential():
+@pytest.mark.parametrize("split", [False, True])
+def test_pipelined_frames_on_three_streams_match_sequential(split):
     """Several frames in flight (one stream + workspace slot + output set each), a new pose every frame:
-    the pose kernel of frame i+1 waits only for frame i's scene-read event.  Products must equal the
-    one-frame-at-a-time results bit for bit."""
+    the pose kernel of frame i+1 waits only for frame i's scene-read event.  With `split` every slot's
+    compositing kernel runs on its own lower-priority stream (pg_set_composite_stream), forked from and
+    joined back into the slot's stream.  Products must equal the one-frame-at-a-time results bit for bit."""
     from pegasus_b200 import ComposedScene, Camera, synth
     env, objs = util.small_scene(n_env=30000, n_obj=(5000, 4000), seed=71)
     colors = oracle.generate_colors(2)
@@ -437,7 +439,8 @@ def test_pipelined_frames_on_three_streams_match_sequential():
     torch.cuda.synchronize()
     assert not torch.equal(want[0]["color"], want[1]["color"])
     n_slot = 3
-    streams = [torch.cuda.Stream() for _ in range(n_slot)]
+    streams = [torch.cuda.Stream(priority=-1 if split else 0) for _ in range(n_slot)]
+    comp_streams = [torch.cuda.Stream(priority=0) if split else None for _ in range(n_slot)]
     outs = [sc.alloc_outputs(640, 480) for _ in range(n_slot)]
     read_ev = [torch.cuda.Event() for _ in range(n_slot)]
     got = [None] * len(cams)
@@ -451,7 +454,8 @@ def test_pipelined_frames_on_three_streams_match_sequential():
             if f > 0:
                 streams[sl].wait_event(read_ev[(f - 1) % n_slot])
             sc.apply_pose_packets(packets[f])
-            sc.render(cam, bg, out=outs[sl], sync_check=False, slot=sl, scene_read_event=read_ev[sl])
+            sc.render(cam, bg, out=outs[sl], sync_check=False, slot=sl, scene_read_event=read_ev[sl],
+                      composite_stream=comp_streams[sl])
     for f in range(len(cams) - n_slot, len(cams)):
         with torch.cuda.stream(streams[f % n_slot]):
             got[f] = {k: outs[f % n_slot][k].clone() for k in keys}
