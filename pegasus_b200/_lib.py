@@ -86,7 +86,7 @@ def load():
     global _LIB
     if _LIB is not None:
         return _LIB
-    path = _build.OUT
+    path = os.environ.get("PG_LIB_PATH") or _build.OUT  # PG_LIB_PATH: a tuning build of the same sources
     if not os.path.exists(path):
         path = _build.build()  # raises if nvcc is unavailable or compilation fails
     L = C.CDLL(path)

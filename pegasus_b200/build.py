@@ -21,18 +21,19 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, out: str = OUT, defines=()) -> str:
+    """`out` / `defines` build a tuning variant beside the product (selected with PG_LIB_PATH)."""
+    if out == OUT and not force and not needs_build():
         return OUT
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-          [os.path.join(CSRC, s) for s in SOURCES] + ["-o", OUT]
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [f"-D{d}" for d in defines] + \
+          [os.path.join(CSRC, s) for s in SOURCES] + ["-o", out]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed building libpegasus_b200.so")
-    return OUT
+    return out
 
 
 if __name__ == "__main__":

@@ -2,7 +2,8 @@
 //   emit_kernel      : fused scan of the stored pairs per Gaussian (decoupled look-back over chunks of
 //                      512 Gaussians, in DEPTH order) + key duplication, one thread per rectangle ROW:
 //                      writes (tile id, Gaussian index) pairs.  12 B read per Gaussian, 8 B written per pair.
-//   tile_hist_kernel : digit histograms of both tile-sort passes from the emitted tile ids (warp votes).
+//                      also accumulates the digit histograms of both tile-sort passes (shared-memory
+//                      reductions: per pair for the low digit, per run for the high digit).
 //   tile_scan_kernel : exclusive digit bases of both tile-sort passes.
 //   ranges_kernel    : identifyTileRanges on the sorted tile ids.
 //   export_keys_kernel (tests only): rebuilds the reference's 64-bit tile|depth keys.
@@ -15,7 +16,11 @@ constexpr uint32_t E_FLAG_AGG = 1u << 30;
 constexpr uint32_t E_FLAG_INCL = 2u << 30;
 constexpr uint32_t E_VAL_MASK = (1u << 30) - 1;
 
-constexpr int EMIT_THREADS = 256;
+#ifndef PG_EMIT_THREADS
+#define PG_EMIT_THREADS 256
+#endif
+constexpr int EMIT_THREADS = PG_EMIT_THREADS;
+constexpr int EMIT_WARPS = EMIT_THREADS / 32;
 constexpr int EMIT_EPT = EMIT_CHUNK / EMIT_THREADS;  // entries per thread (blocked = depth order)
 constexpr int EMIT_RPT = 14;                         // rows per thread in the row scan
 constexpr int EMIT_ROWCAP = EMIT_THREADS * EMIT_RPT; // tile rows of one window (3584)
@@ -32,23 +37,28 @@ struct EmitSmem {
     // per tile row of the current window
     uint32_t rowinfo[EMIT_ROWCAP];     // ta | tb << 11 | entry << 22   (run [ta, tb) of this row; gx <= 2047)
     uint32_t rowoff[EMIT_ROWCAP + 1];  // exclusive scan of the rows' stored pairs (window-relative)
-    uint32_t scan[8];
+    uint32_t scan[EMIT_WARPS];
     uint32_t chunk, base;
+    uint32_t hist[2][RADIX];           // digit histograms of this chunk's stored pairs (both tile-sort passes)
 };
 static_assert(EMIT_CHUNK <= 1024 && EMIT_CHUNK % EMIT_THREADS == 0, "entry id is packed into 10 bits");
 
 // One stored pair.  flag: the tile cannot receive a contribution (KEEP_ALL lists only).
 __device__ __forceinline__ void emit_pair(bool valid, uint32_t dst, uint32_t tile, uint32_t g, bool flag,
                                           uint32_t n_env, uint32_t* __restrict__ tkeys,
-                                          uint32_t* __restrict__ tvals, uint32_t* __restrict__ tile_obj_count) {
+                                          uint32_t* __restrict__ tvals, uint32_t* __restrict__ tile_obj_count,
+                                          uint32_t* __restrict__ hist_lo, uint32_t mask_lo) {
     if (valid) {
+        // low digit of the tile sort: the tiles of a run are consecutive, so the lanes of a warp hit distinct
+        // counters (shared-memory reduction without return value)
+        atomicAdd(&hist_lo[tile & mask_lo], 1u);
         tkeys[dst] = tile;
         tvals[dst] = flag ? (g | PG_CULL_FLAG) : g;
         if (g >= n_env && !flag) atomicAdd(&tile_obj_count[tile], 1u);
     }
 }
 
-// CTA-wide exclusive scan of one value per thread (256 threads); returns the exclusive prefix, *total = sum.
+// CTA-wide exclusive scan of one value per thread (EMIT_THREADS threads); returns the exclusive prefix, *total = sum.
 __device__ __forceinline__ uint32_t cta_excl_scan(uint32_t v, uint32_t* s_scan, uint32_t* total) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t x = v;
@@ -62,7 +72,7 @@ __device__ __forceinline__ uint32_t cta_excl_scan(uint32_t v, uint32_t* s_scan, 
     __syncthreads();
     uint32_t wb = 0, tot = 0;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) {
+    for (int w = 0; w < EMIT_WARPS; ++w) {
         const uint32_t c = s_scan[w];
         if (w < warp) wb += c;
         tot += c;
@@ -92,12 +102,15 @@ emit_kernel(const uint32_t* __restrict__ sorted_dkey, const uint32_t* __restrict
             const ushort4* __restrict__ rects, const GeomRec* __restrict__ recs, uint32_t P, uint32_t gx,
             int W, int H, uint32_t* __restrict__ tkeys,
             uint32_t* __restrict__ tvals, uint32_t R_cap, uint32_t* __restrict__ status,
-            uint32_t n_env, uint32_t* __restrict__ tile_obj_count, Counters* __restrict__ counters) {
+            uint32_t n_env, uint32_t* __restrict__ tile_obj_count, Counters* __restrict__ counters,
+            int bits_lo, uint32_t* __restrict__ hist /*[2][RADIX]*/) {
     extern __shared__ __align__(16) unsigned char emit_smem_raw[];
     EmitSmem& sm = *reinterpret_cast<EmitSmem*>(emit_smem_raw);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t mask_lo = (1u << bits_lo) - 1u;
     if (tid == 0) sm.chunk = atomicAdd(&counters->tile_counter[4], 1u);
+    for (int i = tid; i < 2 * RADIX; i += EMIT_THREADS) (&sm.hist[0][0])[i] = 0;
     __syncthreads();
     const uint32_t chunk = sm.chunk;
     // Culled Gaussians carry the largest depth key and sort behind every visible one: only the first
@@ -275,10 +288,19 @@ emit_kernel(const uint32_t* __restrict__ sorted_dkey, const uint32_t* __restrict
             const uint32_t dst0 = off + o0;                    // may wrap only beyond R_cap (checked below)
             const uint32_t room = dst0 < R_cap ? R_cap - dst0 : 0u;
             const uint32_t tile0 = (uint32_t)ty * gx + (uint32_t)x0;
+            // high digit of the tile sort: once per run (a run crosses a digit boundary at most every
+            // 2^bits_lo tiles); only pairs that are really stored count
+            for (uint32_t tcur = tile0, left = min(len, room); left > 0;) {
+                const uint32_t n1 = min(left, (((tcur >> bits_lo) + 1u) << bits_lo) - tcur);
+                atomicAdd(&sm.hist[1][(tcur >> bits_lo) & 255u], n1);
+                tcur += n1;
+                left -= n1;
+            }
             if (len <= (uint32_t)EMIT_SMALL) {
                 for (uint32_t i = 0; i < len; ++i)
                     emit_pair(i < room, dst0 + i, tile0 + i, g,
-                              KEEP_ALL && !(x0 + (int)i >= ta && x0 + (int)i < tb), n_env, tkeys, tvals, tile_obj_count);
+                              KEEP_ALL && !(x0 + (int)i >= ta && x0 + (int)i < tb), n_env, tkeys, tvals, tile_obj_count,
+                              sm.hist[0], mask_lo);
             }
             // long runs: the whole warp, lanes over tiles
             uint32_t big = __ballot_sync(0xffffffffu, len > (uint32_t)EMIT_SMALL);
@@ -295,66 +317,15 @@ emit_kernel(const uint32_t* __restrict__ sorted_dkey, const uint32_t* __restrict
                 for (uint32_t i = lane; i < b_len; i += 32)
                     emit_pair(i < b_room, b_dst + i, b_tile + i, b_g,
                               KEEP_ALL && !(b_x0 + (int)i >= b_ta && b_x0 + (int)i < b_tb), n_env, tkeys, tvals,
-                              tile_obj_count);
+                              tile_obj_count, sm.hist[0], mask_lo);
             }
         }
         off = (uint32_t)min((uint64_t)off + win_total, (uint64_t)0xFFFFFFFFu);
         if (nwin > 1) __syncthreads();  // the next window overwrites rowinfo / rowoff
     }
-}
-
-// Digit histograms of both tile-sort passes from the emitted tile ids.  Shared-memory atomics cost
-// ~64 cycles per warp instruction on this part, so counting is done with warp votes instead: one
-// ballot per digit bit gives every lane the set of lanes with the same digit, the lowest of them adds
-// the group size to a warp-private counter (plain load/store).  ~30 vote-pipe cycles per 32 keys.
-constexpr int THIST_IPT = 16;
-__global__ void __launch_bounds__(256)
-tile_hist_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ n_ptr, int bits_lo, int bits_hi,
-                 uint32_t* __restrict__ hist /*[2][256]*/) {
-    __shared__ uint32_t s_h[8][2][RADIX];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < 8 * 2 * RADIX; i += 256) (&s_h[0][0][0])[i] = 0;
     __syncthreads();
-    const uint32_t n = *n_ptr;
-    const uint32_t mask_lo = (1u << bits_lo) - 1u;
-    const uint32_t lt = (1u << lane) - 1u;
-    const uint32_t tile_items = 256 * THIST_IPT;
-    for (uint32_t base = blockIdx.x * tile_items; base < n; base += gridDim.x * tile_items) {
-        const uint32_t wbase = base + warp * (32 * THIST_IPT) + lane;
-        uint32_t k[THIST_IPT];
-#pragma unroll
-        for (int i = 0; i < THIST_IPT; ++i) k[i] = (wbase + i * 32 < n) ? keys[wbase + i * 32] : 0xFFFFFFFFu;
-#pragma unroll
-        for (int i = 0; i < THIST_IPT; ++i) {
-            const bool valid = wbase + i * 32 < n;
-            const uint32_t vm = __ballot_sync(0xffffffffu, valid);
-            const uint32_t dlo = k[i] & mask_lo, dhi = (k[i] >> bits_lo) & 255u;
-            uint32_t plo = vm, phi = vm;
-#pragma unroll
-            for (int b = 0; b < 8; ++b) {
-                if (b < bits_lo) {
-                    uint32_t bal, bit = (dlo >> b) & 1u;
-                    asm volatile("{\n.reg .pred p;\nsetp.ne.u32 p, %1, 0;\nvote.sync.ballot.b32 %0, p, 0xffffffff;\n}\n"
-                                 : "=r"(bal) : "r"(bit));
-                    plo &= bal ^ (bit - 1u);
-                }
-                if (b < bits_hi) {
-                    uint32_t bal, bit = (dhi >> b) & 1u;
-                    asm volatile("{\n.reg .pred p;\nsetp.ne.u32 p, %1, 0;\nvote.sync.ballot.b32 %0, p, 0xffffffff;\n}\n"
-                                 : "=r"(bal) : "r"(bit));
-                    phi &= bal ^ (bit - 1u);
-                }
-            }
-            if (valid && (plo & lt) == 0) s_h[warp][0][dlo] += __popc(plo);
-            if (valid && (phi & lt) == 0) s_h[warp][1][dhi] += __popc(phi);
-            __syncwarp();
-        }
-    }
-    __syncthreads();
-    for (int i = tid; i < 2 * RADIX; i += 256) {
-        uint32_t c = 0;
-#pragma unroll
-        for (int w = 0; w < 8; ++w) c += (&s_h[w][0][0])[i];
+    for (int i = tid; i < 2 * RADIX; i += EMIT_THREADS) {
+        const uint32_t c = (&sm.hist[0][0])[i];
         if (c) atomicAdd(&hist[i], c);
     }
 }
@@ -466,7 +437,8 @@ __global__ void export_keys_kernel(const uint2* __restrict__ ranges, uint32_t ti
 
 int launch_emit(bool keep_all, const uint32_t* sorted_dkey, const uint32_t* perm, const ushort4* rects, const GeomRec* recs,
                 uint32_t P, uint32_t gx, int W, int H, uint32_t* tkeys, uint32_t* tvals, uint32_t R_cap, uint32_t* status,
-                uint32_t n_env, uint32_t* tile_obj_count, Counters* counters, cudaStream_t stream) {
+                uint32_t n_env, uint32_t* tile_obj_count, Counters* counters, int bits_lo, uint32_t* hist_tile,
+                cudaStream_t stream) {
     uint32_t chunks = (P + EMIT_CHUNK - 1) / EMIT_CHUNK;
     if (chunks == 0) return PG_OK;
     static bool attr_set = false;
@@ -477,21 +449,10 @@ int launch_emit(bool keep_all, const uint32_t* sorted_dkey, const uint32_t* perm
     }
     if (keep_all)
         emit_kernel<true><<<chunks, EMIT_THREADS, sizeof(EmitSmem), stream>>>(sorted_dkey, perm, rects, recs, P, gx, W, H, tkeys, tvals, R_cap, status,
-                                                      n_env, tile_obj_count, counters);
+                                                      n_env, tile_obj_count, counters, bits_lo, hist_tile);
     else
         emit_kernel<false><<<chunks, EMIT_THREADS, sizeof(EmitSmem), stream>>>(sorted_dkey, perm, rects, recs, P, gx, W, H, tkeys, tvals, R_cap, status,
-                                                       n_env, tile_obj_count, counters);
-    count_launch(1);
-    PG_CUDA_CHECK(cudaGetLastError());
-    return PG_OK;
-}
-
-int launch_tile_hist(const uint32_t* keys, const uint32_t* n_ptr, uint32_t max_n, int bits_lo, int bits_hi, uint32_t* hist,
-                     cudaStream_t stream) {
-    if (max_n == 0) return PG_OK;
-    const uint32_t tiles = (max_n + 256 * THIST_IPT - 1) / (256 * THIST_IPT);
-    const uint32_t blocks = min(tiles, (uint32_t)(PG_SM_COUNT * 8));
-    tile_hist_kernel<<<blocks, 256, 0, stream>>>(keys, n_ptr, bits_lo, bits_hi, hist);
+                                                       n_env, tile_obj_count, counters, bits_lo, hist_tile);
     count_launch(1);
     PG_CUDA_CHECK(cudaGetLastError());
     return PG_OK;

@@ -6,7 +6,8 @@
 //   hist_kernel + scan_rows_kernel              digit histograms of the depth keys (4 x 8 bit)
 //   onesweep_pass_kernel x4                     P Gaussians by depth (stable; values = index)
 //   emit_kernel                                 tile-row culling + scan + (tile, index) pairs in depth order
-//   tile_hist_kernel + tile_scan_kernel         digit histograms / bases of the tile sort
+//                                               + digit histograms of the tile sort
+//   tile_scan_kernel                            digit bases of the tile sort
 //   onesweep_pass_kernel x2                     stored pairs by tile id (stable)  => reference order
 //   ranges_kernel                               ranges[tile] from the sorted tile ids
 //   composite_kernel | composite_masks_kernel   A.7 (+ fused K+3 passes)
@@ -47,9 +48,8 @@ int launch_onesweep_pass(bool iota, bool write_keys, const uint32_t* keys_in, ui
                          cudaStream_t stream);
 int launch_emit(bool keep_all, const uint32_t* sorted_dkey, const uint32_t* perm, const ushort4* rects, const GeomRec* recs,
                 uint32_t P, uint32_t gx, int W, int H, uint32_t* tkeys, uint32_t* tvals, uint32_t R_cap, uint32_t* status,
-                uint32_t n_env, uint32_t* tile_obj_count, Counters* counters, cudaStream_t stream);
-int launch_tile_hist(const uint32_t* keys, const uint32_t* n_ptr, uint32_t max_n, int bits_lo, int bits_hi, uint32_t* hist,
-                     cudaStream_t stream);
+                uint32_t n_env, uint32_t* tile_obj_count, Counters* counters, int bits_lo, uint32_t* hist_tile,
+                cudaStream_t stream);
 int launch_tile_scan(const uint32_t* hist_tile, uint32_t* bins, Counters* counters, cudaStream_t stream);
 int launch_ranges(const uint32_t* sorted_tile_keys, const uint32_t* n_ptr, uint32_t max_n, uint2* ranges, cudaStream_t stream);
 int launch_tile_order(const uint2* ranges, uint32_t tiles, uint32_t* order, cudaStream_t stream);
@@ -189,12 +189,9 @@ static int run_binning(const pg_raster_settings* s, const pg_gaussians* g, const
     rc = launch_emit(keep_all, ka, va, at<ushort4>(ws, L.rect), at<GeomRec>(ws, L.recs), (uint32_t)P, gx, W, H,
                      at<uint32_t>(ws, L.tkey_a),
                      at<uint32_t>(ws, L.tval_a), (uint32_t)R_cap, at<uint32_t>(ws, L.status_emit),
-                     n_env, at<uint32_t>(ws, L.tile_obj_count), counters, stream);
+                     n_env, at<uint32_t>(ws, L.tile_obj_count), counters, bits_lo, at<uint32_t>(ws, L.hist_tile), stream);
     if (rc) return rc;
     prof_mark(4, stream);
-    rc = launch_tile_hist(at<uint32_t>(ws, L.tkey_a), &counters->sort_n, (uint32_t)R_cap, bits_lo, bits_hi,
-                          at<uint32_t>(ws, L.hist_tile), stream);
-    if (rc) return rc;
     rc = launch_tile_scan(at<uint32_t>(ws, L.hist_tile), at<uint32_t>(ws, L.bins_tile), counters, stream);
     if (rc) return rc;
     prof_mark(5, stream);

@@ -92,7 +92,10 @@ constexpr int SORT_THREADS = 256;
 constexpr int SORT_IPT = 16;
 constexpr int SORT_TILE = SORT_THREADS * SORT_IPT;  // 4096 items per CTA-tile
 constexpr int RADIX = 256;
-constexpr int EMIT_CHUNK = 512;
+#ifndef PG_EMIT_CHUNK
+#define PG_EMIT_CHUNK 512
+#endif
+constexpr int EMIT_CHUNK = PG_EMIT_CHUNK;  // Gaussians per emit CTA (2 per thread)
 
 struct Layout {
     // all offsets in bytes from the workspace base; every region 256-B aligned
