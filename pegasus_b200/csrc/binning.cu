@@ -24,7 +24,6 @@ constexpr int EMIT_WARPS = EMIT_THREADS / 32;
 constexpr int EMIT_EPT = EMIT_CHUNK / EMIT_THREADS;  // entries per thread (blocked = depth order)
 constexpr int EMIT_RPT = 14;                         // rows per thread in the row scan
 constexpr int EMIT_ROWCAP = EMIT_THREADS * EMIT_RPT; // tile rows of one window (3584)
-constexpr int EMIT_SMALL = 4;                        // runs of at most this many tiles are written by their own thread
 constexpr uint32_t EMIT_OK = 0x80000000u;            // s_g bit 31: the row test may cull (CullGauss::ok)
 
 struct EmitSmem {
@@ -40,6 +39,7 @@ struct EmitSmem {
     uint32_t scan[EMIT_WARPS];
     uint32_t chunk, base;
     uint32_t hist[2][RADIX];           // digit histograms of this chunk's stored pairs (both tile-sort passes)
+    uint8_t widx[EMIT_WARPS][32];      // write phase: rank among a warp's non-empty rows -> lane
 };
 static_assert(EMIT_CHUNK <= 1024 && EMIT_CHUNK % EMIT_THREADS == 0, "entry id is packed into 10 bits");
 
@@ -93,8 +93,8 @@ __device__ __forceinline__ uint32_t cta_excl_scan(uint32_t v, uint32_t* s_scan, 
 //       EMIT_ROWCAP rows; one window is the common case and its runs stay cached in shared memory);
 //   (2) one thread per row: closed-form run [ta, tb) of tiles that can contribute; scan of run lengths;
 //   (3) decoupled look-back over chunks -> output offset of the chunk;
-//   (4) one thread per row writes its run (adjacent lanes -> adjacent addresses); runs longer than
-//       EMIT_SMALL are written by the whole warp, lanes over tiles.
+//   (4) every warp writes the runs of its 32 rows pair-parallel (slot j of the concatenated runs -> lane
+//       j % 32): coalesced stores, no lane walks a long run alone.
 // Output order = entry order (depth), rows top to bottom, tiles left to right = the reference's order.
 template <bool KEEP_ALL>
 __global__ void __launch_bounds__(EMIT_THREADS)
@@ -296,29 +296,42 @@ emit_kernel(const uint32_t* __restrict__ sorted_dkey, const uint32_t* __restrict
                 tcur += n1;
                 left -= n1;
             }
-            if (len <= (uint32_t)EMIT_SMALL) {
-                for (uint32_t i = 0; i < len; ++i)
-                    emit_pair(i < room, dst0 + i, tile0 + i, g,
-                              KEEP_ALL && !(x0 + (int)i >= ta && x0 + (int)i < tb), n_env, tkeys, tvals, tile_obj_count,
-                              sm.hist[0], mask_lo);
+            // The warp writes the pairs of its 32 rows PAIR-parallel: slot j of the group's concatenated output
+            // goes to lane j % 32, so stores are fully coalesced and no lane walks a long run alone.  Row of a
+            // slot: non-empty rows have distinct start offsets s; per batch of 32 slots the heads falling into
+            // it form a bit mask (one warp reduction), a popcount gives every slot the rank of its row among
+            // the non-empty rows, and widx maps the rank back to the lane that holds the row.
+            const uint32_t NE = __ballot_sync(0xffffffffu, len > 0);
+            if (NE == 0) continue;  // warp-uniform
+            const uint32_t gbase = __shfl_sync(0xffffffffu, o0, 0);  // NE != 0: the warp's first row exists
+            const uint32_t L = __reduce_add_sync(0xffffffffu, len);
+            const uint32_t srow = o0 - gbase;                        // start slot of this lane's row
+            const uint32_t tms = tile0 - srow;                       // tile of slot j in this row = tms + j
+            const int xms = x0 - (int)srow;
+            if (len > 0) sm.widx[warp][__popc(NE & ((1u << lane) - 1u))] = (uint8_t)lane;
+            __syncwarp();
+            const uint32_t gdst = off + gbase;
+            const uint32_t groom = gdst < R_cap ? R_cap - gdst : 0u;
+            uint32_t base_rank = 0;  // non-empty rows that start before the current batch
+            for (uint32_t jb = 0; jb < L; jb += 32) {
+                const uint32_t rel = srow - jb;  // wraps for rows that started earlier
+                const uint32_t hm = __reduce_or_sync(0xffffffffu, (len > 0 && rel < 32u) ? (1u << rel) : 0u);
+                const uint32_t j = jb + lane;
+                const uint32_t rank = base_rank + __popc(hm & (0xFFFFFFFFu >> (31 - lane))) - 1u;
+                const int src = sm.widx[warp][rank & 31u];
+                const uint32_t p_tms = __shfl_sync(0xffffffffu, tms, src);
+                const uint32_t p_g = __shfl_sync(0xffffffffu, g, src);
+                bool flag = false;
+                if (KEEP_ALL) {
+                    const int x = __shfl_sync(0xffffffffu, xms, src) + (int)j;
+                    const int p_ta = __shfl_sync(0xffffffffu, ta, src), p_tb = __shfl_sync(0xffffffffu, tb, src);
+                    flag = !(x >= p_ta && x < p_tb);
+                }
+                emit_pair(j < L && j < groom, gdst + j, p_tms + j, p_g, flag, n_env, tkeys, tvals, tile_obj_count,
+                          sm.hist[0], mask_lo);
+                base_rank += __popc(hm);
             }
-            // long runs: the whole warp, lanes over tiles
-            uint32_t big = __ballot_sync(0xffffffffu, len > (uint32_t)EMIT_SMALL);
-            while (big) {
-                const int src = __ffs(big) - 1;
-                big &= big - 1;
-                const uint32_t b_len = __shfl_sync(0xffffffffu, len, src);
-                const uint32_t b_dst = __shfl_sync(0xffffffffu, dst0, src);
-                const uint32_t b_room = __shfl_sync(0xffffffffu, room, src);
-                const uint32_t b_tile = __shfl_sync(0xffffffffu, tile0, src);
-                const uint32_t b_g = __shfl_sync(0xffffffffu, g, src);
-                const int b_x0 = __shfl_sync(0xffffffffu, x0, src);
-                const int b_ta = __shfl_sync(0xffffffffu, ta, src), b_tb = __shfl_sync(0xffffffffu, tb, src);
-                for (uint32_t i = lane; i < b_len; i += 32)
-                    emit_pair(i < b_room, b_dst + i, b_tile + i, b_g,
-                              KEEP_ALL && !(b_x0 + (int)i >= b_ta && b_x0 + (int)i < b_tb), n_env, tkeys, tvals,
-                              tile_obj_count, sm.hist[0], mask_lo);
-            }
+            __syncwarp();  // widx is rewritten by the next group
         }
         off = (uint32_t)min((uint64_t)off + win_total, (uint64_t)0xFFFFFFFFu);
         if (nwin > 1) __syncthreads();  // the next window overwrites rowinfo / rowoff
@@ -356,15 +369,33 @@ tile_scan_kernel(const uint32_t* __restrict__ hist /*[2][256]*/, uint32_t* __res
 }
 
 // identifyTileRanges on the sorted tile ids: ranges[tile] = [first, last + 1); tiles without pairs keep
-// the (0, 0) of the per-frame clear.  n lives on the device (stored pairs).
+// the (0, 0) of the per-frame clear.  n lives on the device (stored pairs).  Four consecutive ids per
+// thread (one 16-byte load + the two neighbours, which hit L1): the kernel is a pure 4 B/pair stream.
 __global__ void __launch_bounds__(256)
 ranges_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ n_ptr, uint2* __restrict__ ranges) {
     const uint32_t n = *n_ptr;
+    const uint32_t nvec = (n + 3u) / 4u;
     const uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const uint32_t k = keys[i];
-        if (i == 0 || keys[i - 1] != k) ranges[k].x = i;
-        if (i == n - 1 || keys[i + 1] != k) ranges[k].y = i + 1;
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < nvec; j += stride) {
+        const uint32_t i0 = 4u * j;
+        uint32_t k[6];  // k[0] = id before the group, k[1..4] = the group, k[5] = id after it
+        if (i0 + 4u <= n) {
+            const uint4 v = *reinterpret_cast<const uint4*>(keys + i0);
+            k[1] = v.x; k[2] = v.y; k[3] = v.z; k[4] = v.w;
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) k[1 + e] = (i0 + e < n) ? keys[i0 + e] : 0xFFFFFFFFu;
+        }
+        k[0] = i0 > 0 ? keys[i0 - 1] : 0xFFFFFFFFu;          // never a tile id
+        k[5] = (i0 + 4u < n) ? keys[i0 + 4u] : 0xFFFFFFFFu;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const uint32_t i = i0 + e;
+            if (i < n) {
+                if (k[e] != k[1 + e]) ranges[k[1 + e]].x = i;
+                if (i == n - 1 || k[2 + e] != k[1 + e]) ranges[k[1 + e]].y = i + 1;
+            }
+        }
     }
 }
 
@@ -467,7 +498,7 @@ int launch_tile_scan(const uint32_t* hist_tile, uint32_t* bins, Counters* counte
 
 int launch_ranges(const uint32_t* sorted_tile_keys, const uint32_t* n_ptr, uint32_t max_n, uint2* ranges, cudaStream_t stream) {
     if (max_n == 0) return PG_OK;
-    const uint32_t blocks = min((max_n + 255u) / 256u, (uint32_t)(PG_SM_COUNT * 16));
+    const uint32_t blocks = min((max_n / 4u + 255u) / 256u + 1u, (uint32_t)(PG_SM_COUNT * 16));
     ranges_kernel<<<blocks, 256, 0, stream>>>(sorted_tile_keys, n_ptr, ranges);
     count_launch(1);
     PG_CUDA_CHECK(cudaGetLastError());
