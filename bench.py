@@ -505,7 +505,7 @@ def run_ours(args):
             traffic = json.load(open(tp)).get(dom["stage"])
         except Exception:
             traffic = None
-    roofline = {"kernel": {"composite": "composite_masks_kernel", "tile_sort": "onesweep_pass_kernel (tile id)",
+    roofline = {"kernel": {"composite": "composite2_kernel<MASKS> (2 pixels per thread, packed FP32)", "tile_sort": "onesweep_pass_kernel (tile id)",
                            "depth_sort": "onesweep_pass_kernel (depth)", "preprocess": "preprocess_kernel",
                            "emit": "emit_kernel"}.get(dom["stage"], dom["stage"]),
                 "bound": dom.get("bound"), "achieved": dom.get("achieved"), "peak": dom.get("peak"),

@@ -892,10 +892,21 @@ __global__ void __launch_bounds__(COMP2_THREADS, MINB) composite2_kernel(const C
     if (STATS) flush_stats(a.stats, n_eval, n_exp, n_blend);
 }
 
+// PG_COMP_SMEM_PAD (tuning only): extra dynamic shared memory per compositing CTA, i.e. a cap on the CTAs
+// per SM, which leaves registers / shared memory for another frame's binning kernels to co-run.
+static int comp_smem_pad() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("PG_COMP_SMEM_PAD");
+        v = e ? atoi(e) : 0;
+    }
+    return v;
+}
+
 template <bool MASKS, bool STATS, int STAGES, int ILP, int MINB>
 static int launch_two(const CompArgs& a, dim3 grid, cudaStream_t stream) {
     static int attr_smem = 0;
-    const int smem = (int)sizeof(CompSmemT<STAGES>) +
+    const int smem = (int)sizeof(CompSmemT<STAGES>) + comp_smem_pad() +
                      (MASKS ? (int)(PG_MAX_OBJECTS * sizeof(float4)) + a.num_objects * 256 * (int)sizeof(float) : 0);
     if (smem > attr_smem) {
         PG_CUDA_CHECK(cudaFuncSetAttribute(composite2_kernel<MASKS, STATS, STAGES, ILP, MINB>,
