@@ -89,7 +89,10 @@ struct Counters {
 
 // Onesweep tile geometry
 constexpr int SORT_THREADS = 256;
-constexpr int SORT_IPT = 16;
+#ifndef PG_SORT_IPT
+#define PG_SORT_IPT 16
+#endif
+constexpr int SORT_IPT = PG_SORT_IPT;
 constexpr int SORT_TILE = SORT_THREADS * SORT_IPT;  // 4096 items per CTA-tile
 constexpr int RADIX = 256;
 #ifndef PG_EMIT_CHUNK

@@ -59,6 +59,9 @@ def test_argument_errors_do_not_need_a_gpu():
     assert rc == -1 and b"null" in L.pg_last_error()
     with pytest.raises(RuntimeError):
         _lib.check(rc, "pg_rasterize_forward")
+    # pg_set_composite_stream: a stream needs both events; a null stream clears the request
+    assert L.pg_set_composite_stream(C.c_void_p(1), None, None) == -1 and b"fork" in L.pg_last_error()
+    assert L.pg_set_composite_stream(None, None, None) == 0
 
 
 def test_product_never_imports_the_oracle():
