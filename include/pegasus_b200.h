@@ -26,8 +26,8 @@
  *                             render_semanticsegmentation_mask) driven by pegasus.py:295-332.
  *   pg_export_binning      <- test/debug only: the reference keeps these in its binningBuffer /
  *                             imgBuffer (point_list_keys, point_list, ranges).
- *   pg_pack_frame          <- the host-side conversions in pegasus.py:340-358 (rgb*255 -> u8,
- *                             depth*1000 -> u16) done on the device before the D2H copy.
+ *   pg_pack_frame,         <- the host-side conversions in pegasus.py:340-358 (rgb*255 -> u8,
+ *   pg_pack_masks             depth*1000 -> u16, masks -> 0/255 u8) done on the device before the D2H copy.
  */
 #ifndef PEGASUS_B200_H
 #define PEGASUS_B200_H
@@ -217,6 +217,13 @@ int pg_read_stats(const void* workspace, uint64_t* host_stats4, pg_stream_t stre
 /* rgb [3,H,W] f32 -> [H,W,3] u8 ; depth [1,H,W] f32 metres -> [H,W] u16 millimetres. */
 int pg_pack_frame(int32_t width, int32_t height, const float* color, const float* depth,
                   uint8_t* rgb_u8, uint16_t* depth_u16, pg_stream_t stream);
+
+/* n_planes mask planes [n_planes,H,W] u8 (0 / non-zero: the `visible` / `silhouette` outputs) ->
+ * [n_planes,H,ceil(W/8)] bytes, pixel x in bit x % 8 of byte x / 8 (numpy.unpackbits(..., bitorder="little")).
+ * The masks are 2 x n_colours of the 3+2+3+2 x n_colours bytes per pixel a frame sends to the host; packed
+ * they cross PCIe as one bit per pixel and are expanded by the writer thread that encodes the PNG. */
+int pg_pack_masks(int32_t width, int32_t height, int32_t n_planes, const uint8_t* masks, uint8_t* bits,
+                  pg_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -70,7 +70,7 @@ EXPORTS = ["pg_version", "pg_last_error", "pg_workspace_bytes", "pg_rasterize_fo
            "pg_render_composed", "pg_read_status", "pg_mark_visible", "pg_pose_apply",
            "pg_export_binning", "pg_pack_frame", "pg_profile_enable", "pg_profile_frames",
            "pg_profile_read", "pg_launch_count", "pg_read_stats", "pg_set_scene_read_event",
-           "pg_set_composite_stream"]
+           "pg_set_composite_stream", "pg_pack_masks"]
 
 NUM_STAGES = 7
 STAGE_NAMES = ["clear", "preprocess", "depth_sort", "emit", "tile_scan", "tile_sort", "composite"]
@@ -107,6 +107,8 @@ def load():
                                     C.c_void_p, C.c_void_p, C.c_void_p]
     L.pg_pack_frame.argtypes = [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                 C.c_void_p]
+    L.pg_pack_masks.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.pg_pack_masks.restype = C.c_int
     L.pg_profile_enable.argtypes = [C.c_int32]
     L.pg_profile_frames.restype = C.c_int32
     L.pg_profile_read.argtypes = [C.c_int32, C.POINTER(C.c_float)]

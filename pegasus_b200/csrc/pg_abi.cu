@@ -59,6 +59,7 @@ int launch_pose(int K, const int32_t* first, const PoseDev* poses_dev, const pg_
                 int scene_offset, const pg_scene* scene, cudaStream_t stream);
 int launch_pack(int W, int H, const float* color, const float* depth, uint8_t* rgb_u8, uint16_t* depth_u16,
                 cudaStream_t stream);
+int launch_pack_masks(int W, int H, int n_planes, const uint8_t* masks, uint8_t* bits, cudaStream_t stream);
 int launch_composite_from_abi(const uint2* ranges, const uint32_t* tile_order, const uint32_t* point_list, const GeomRec* recs, int W,
                               int H, const float* bg, const pg_raster_outputs* ro, const pg_frame_outputs* fo,
                               const pg_object_table* objs, uint32_t n_env, const uint32_t* tile_obj_count,
@@ -384,6 +385,12 @@ int pg_pack_frame(int32_t width, int32_t height, const float* color, const float
                   uint16_t* depth_u16, pg_stream_t stream) {
     if (width <= 0 || height <= 0 || (rgb_u8 && !color) || (depth_u16 && !depth)) { set_error("bad argument"); return PG_ERR_INVALID; }
     return launch_pack(width, height, color, depth, rgb_u8, depth_u16, (cudaStream_t)stream);
+}
+
+int pg_pack_masks(int32_t width, int32_t height, int32_t n_planes, const uint8_t* masks, uint8_t* bits,
+                  pg_stream_t stream) {
+    if (width <= 0 || height <= 0 || n_planes < 0 || (n_planes > 0 && (!masks || !bits))) { set_error("bad argument"); return PG_ERR_INVALID; }
+    return launch_pack_masks(width, height, n_planes, masks, bits, (cudaStream_t)stream);
 }
 
 }  // extern "C"

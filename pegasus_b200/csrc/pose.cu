@@ -198,6 +198,38 @@ __global__ void pack_kernel(int W, int H, const float* __restrict__ color, const
     }
 }
 
+// one thread per output byte: 8 mask pixels of one row -> 1 byte, least-significant bit first
+__global__ void pack_masks_kernel(int W, int H, int n_planes, const uint8_t* __restrict__ masks, uint8_t* __restrict__ bits) {
+    const int Wb = (W + 7) / 8;
+    const size_t total = (size_t)n_planes * H * Wb;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int xb = (int)(i % Wb);
+    const size_t row = i / Wb;  // plane * H + y
+    const uint8_t* src = masks + row * W + 8 * (size_t)xb;
+    uint32_t b = 0;
+    if (8 * xb + 8 <= W && (reinterpret_cast<uintptr_t>(src) & 7) == 0) {
+        const uint2 v = *reinterpret_cast<const uint2*>(src);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            b |= (((v.x >> (8 * k)) & 255u) ? 1u : 0u) << k;
+            b |= (((v.y >> (8 * k)) & 255u) ? 1u : 0u) << (4 + k);
+        }
+    } else {
+        for (int k = 0; k < 8 && 8 * xb + k < W; ++k) b |= (src[k] ? 1u : 0u) << k;
+    }
+    bits[i] = (uint8_t)b;
+}
+
+int launch_pack_masks(int W, int H, int n_planes, const uint8_t* masks, uint8_t* bits, cudaStream_t stream) {
+    const size_t total = (size_t)n_planes * H * ((W + 7) / 8);
+    if (total == 0) return PG_OK;
+    pack_masks_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(W, H, n_planes, masks, bits);
+    count_launch(1);
+    PG_CUDA_CHECK(cudaGetLastError());
+    return PG_OK;
+}
+
 int launch_pack(int W, int H, const float* color, const float* depth, uint8_t* rgb_u8, uint16_t* depth_u16,
                 cudaStream_t stream) {
     size_t HW = (size_t)W * H;

@@ -6,8 +6,9 @@ rasterizations, pulls K+2 float images to the host, thresholds colour distances 
 to u8/u16 on the host, starts a PNG-writer thread and appends the pose ground truth.
 
 Here, per frame: one H2D copy of the camera (+ the pose packets in dynamic mode), the pose kernel,
-ONE fused frame (pg_render_composed), the packing kernel (pg_pack_frame: u8 RGB HWC, u16 depth mm),
-and D2H copies of the packed products into a pinned host buffer set.  `frames_in_flight` frames
+ONE fused frame (pg_render_composed), the packing kernels (pg_pack_frame: u8 RGB HWC, u16 depth mm;
+pg_pack_masks: the 2 x n_colours mask planes as one bit per pixel), and D2H copies of the packed products
+into a pinned host buffer set.  `frames_in_flight` frames
 are pipelined, each on its own CUDA stream + workspace slot, so frame i+1's per-Gaussian and binning
 stages overlap frame i's compositing and copies.  Host buffer sets are recycled through a free list:
 a set goes back only after the writer (thread pool, like pegasus.py:346) is done with it, which
@@ -88,8 +89,12 @@ class DatasetGenerator:
         self.comp_streams = [torch.cuda.Stream(device=dev, priority=0) if self.overlap else None
                              for _ in range(self.nslot)]
         self.outs = [scene.alloc_outputs(W, H, masks=True) for _ in range(self.nslot)]
+        self.Wb = (W + 7) // 8  # bytes per row of a bit-packed mask plane (pg_pack_masks)
         self.packs = [dict(rgb=torch.empty((H, W, 3), dtype=torch.uint8, device=dev),
-                           depth=torch.empty((H, W), dtype=torch.int16, device=dev)) for _ in range(self.nslot)]
+                           depth=torch.empty((H, W), dtype=torch.int16, device=dev),
+                           visible=torch.empty((nc, H, self.Wb), dtype=torch.uint8, device=dev),
+                           silhouette=torch.empty((nc, H, self.Wb), dtype=torch.uint8, device=dev))
+                      for _ in range(self.nslot)]
         self.cam_dev = [_CameraSlot(dev) for _ in range(self.nslot)]
         self.pose_dev = [torch.zeros((max(self.K, 1), POSE_WORDS), dtype=torch.float32, device=dev)
                          for _ in range(self.nslot)]
@@ -101,10 +106,12 @@ class DatasetGenerator:
             self._free.put(dict(rgb=torch.empty((H, W, 3), dtype=torch.uint8).pin_memory(),
                                 depth=torch.empty((H, W), dtype=torch.int16).pin_memory(),
                                 sem_seg=torch.empty((H, W, 3), dtype=torch.uint8).pin_memory(),
-                                visible=torch.empty((nc, H, W), dtype=torch.uint8).pin_memory(),
-                                silhouette=torch.empty((nc, H, W), dtype=torch.uint8).pin_memory()))
+                                visible=torch.empty((nc, H, self.Wb), dtype=torch.uint8).pin_memory(),
+                                silhouette=torch.empty((nc, H, self.Wb), dtype=torch.uint8).pin_memory()))
         self.h2d_bytes_per_frame = 35 * 4
-        self.d2h_bytes_per_frame = W * H * (3 + 2 + 3 + 2 * nc)
+        # u8 RGB + u16 depth + u8 sem-seg per pixel, the 2 x nc masks as ONE BIT per pixel: they are most of the
+        # planes of a frame, and with 8 GPUs per host the D2H stream is what the host side saturates first
+        self.d2h_bytes_per_frame = W * H * (3 + 2 + 3) + 2 * nc * H * self.Wb
         self.pair_capacity: Optional[int] = None
 
     # ------------------------------------------------------------------ capacity
@@ -148,11 +155,15 @@ class DatasetGenerator:
                                        C.c_void_p(o["depth"].data_ptr()), C.c_void_p(self.packs[sl]["rgb"].data_ptr()),
                                        C.c_void_p(self.packs[sl]["depth"].data_ptr()), C.c_void_p(st.cuda_stream)),
                        "pg_pack_frame")
+            for name in ("visible", "silhouette"):
+                _lib.check(L.pg_pack_masks(self.W, self.H, self.nc, C.c_void_p(o[name].data_ptr()),
+                                           C.c_void_p(self.packs[sl][name].data_ptr()), C.c_void_p(st.cuda_stream)),
+                           "pg_pack_masks")
             host["rgb"].copy_(self.packs[sl]["rgb"], non_blocking=True)
             host["depth"].copy_(self.packs[sl]["depth"], non_blocking=True)
             host["sem_seg"].copy_(o["sem_seg"], non_blocking=True)
-            host["visible"].copy_(o["visible"], non_blocking=True)
-            host["silhouette"].copy_(o["silhouette"], non_blocking=True)
+            host["visible"].copy_(self.packs[sl]["visible"], non_blocking=True)
+            host["silhouette"].copy_(self.packs[sl]["silhouette"], non_blocking=True)
             self.done_ev[sl].record(st)
 
     # ------------------------------------------------------------------ the loop
@@ -165,8 +176,9 @@ class DatasetGenerator:
         (static mode: PegasusSetup.static_object_pose) or a list over frames of such lists (dynamic mode:
         dynamic_object_pose + update_object_pose, in absolute form).  `pose_packets` may pass the same
         thing as an already packed (frames, K, 103) HOST tensor (e.g. received by broadcast).
-        writer: a BOPDatasetWriter or None.  on_frame(f, products) sees numpy views of the pinned set,
-        valid until it returns.  Returns counters."""
+        writer: a BOPDatasetWriter or None.  on_frame(f, products) runs on a writer thread and sees numpy
+        views of the pinned set (the masks expanded from their bit-packed wire format), valid until it
+        returns.  Returns counters."""
         for d in data_points:
             if d not in DATA_POINTS:
                 raise ValueError(f"unknown data point {d!r}")
@@ -214,11 +226,17 @@ class DatasetGenerator:
             self.done_ev[sl].synchronize()
             inflight[sl] = None
             stats["frames"] += 1
-            prods = dict(rgb=host["rgb"].numpy() if want_rgb else None,
-                         depth=host["depth"].numpy().view(np.uint16) if want_rgb else None,
-                         sem_seg=host["sem_seg"].numpy() if want_sem else None,
-                         visible=host["visible"].numpy() if want_vis else None,
-                         silhouette=host["silhouette"].numpy() if want_sil else None)
+            W_ = self.W
+
+            def make_products():
+                # runs on the writer thread: the masks cross PCIe bit-packed and are expanded to the u8 0/1
+                # planes the writer / callback expects only here
+                unpack = lambda b: np.unpackbits(b.numpy(), axis=-1, bitorder="little")[..., :W_]
+                return dict(rgb=host["rgb"].numpy() if want_rgb else None,
+                            depth=host["depth"].numpy().view(np.uint16) if want_rgb else None,
+                            sem_seg=host["sem_seg"].numpy() if want_sem else None,
+                            visible=unpack(host["visible"]) if want_vis else None,
+                            silhouette=unpack(host["silhouette"]) if want_sil else None)
             if writer is not None:
                 writer.add_scene_camera_json(frame_id=f)
                 if metas is not None and self.K:
@@ -231,6 +249,7 @@ class DatasetGenerator:
 
             def work():
                 try:
+                    prods = make_products()
                     if writer is not None:
                         writer._write(f, prods["rgb"], prods["depth"], prods["visible"], prods["silhouette"], prods["sem_seg"])
                     if on_frame is not None:

@@ -46,6 +46,34 @@ def _sequential(scene, cams, poses):
     return out
 
 
+@pytest.mark.parametrize("W,H,n", [(1920, 8, 3), (333, 7, 2), (5, 3, 1), (16, 2, 4)])
+def test_mask_bit_packing_round_trips_through_numpy_unpackbits(W, H, n):
+    """pg_pack_masks: [n,H,W] u8 (0 / non-zero) -> [n,H,ceil(W/8)] bytes, pixel x in bit x % 8 — the wire format
+    of the visible / silhouette masks; the writer thread expands it with numpy.unpackbits(bitorder="little")."""
+    import ctypes as C
+    from pegasus_b200 import _lib
+    d = torch.device("cuda", 0)
+    g = torch.Generator().manual_seed(W * 131 + H)
+    m = (torch.rand((n, H, W), generator=g) < 0.4).to(torch.uint8)
+    m[0, 0, : min(W, 9)] = torch.tensor([1, 0, 0, 1, 1, 0, 1, 0, 1][: min(W, 9)], dtype=torch.uint8)
+    m = m * torch.randint(1, 256, (n, H, W), generator=g).to(torch.uint8)  # any non-zero byte is "set"
+    src = m.to(d)
+    if W % 8:  # exercise the unaligned path as well
+        src = torch.cat([torch.zeros(3, dtype=torch.uint8, device=d), src.reshape(-1)])[3:].reshape(n, H, W)
+    Wb = (W + 7) // 8
+    bits = torch.full((n, H, Wb), 0xAA, dtype=torch.uint8, device=d)
+    L = _lib.load()
+    st = torch.cuda.current_stream(d)
+    _lib.check(L.pg_pack_masks(W, H, n, C.c_void_p(src.data_ptr()), C.c_void_p(bits.data_ptr()),
+                               C.c_void_p(st.cuda_stream)), "pg_pack_masks")
+    torch.cuda.synchronize()
+    got = np.unpackbits(bits.cpu().numpy(), axis=-1, bitorder="little")[..., :W]
+    np.testing.assert_array_equal(got, (m.numpy() != 0).astype(np.uint8))
+    # padding bits of the last byte are zero
+    if W % 8:
+        assert int((bits.cpu().numpy()[..., -1] >> (W % 8)).max()) == 0
+
+
 def test_pack_kernel_matches_reference_host_conversion():
     import ctypes as C
     from pegasus_b200 import _lib
