@@ -1,17 +1,24 @@
-// composite.cu — per-tile front-to-back alpha compositing, one CTA of 256
-// threads per 16x16 tile, each warp owning an 8x4 pixel block.
+// composite.cu — per-tile front-to-back alpha compositing, one CTA per 16x16 tile,
+// warp-specialised: one PRODUCER warp stages the tile's sorted list, the CONSUMER warps own pixel blocks.
 //
-// Walk of a tile's sorted list, per batch of up to 256 entries:
-//   1. ids are read coalesced (4 B each); entries the binning stage proved invisible for the whole
-//      tile (PG_CULL_FLAG) and, once every main chain has terminated, environment entries are
-//      dropped by a ballot compaction — they are never fetched;
-//   2. each surviving id's 48-byte record {xy, conic, opacity, depth, cut|object, rgb} is GATHERED
-//      into shared memory by its own TMA bulk copy (cp.async.bulk + mbarrier, 2-stage ring: batch
-//      k+1 lands while batch k is composited);
-//   3. every warp tests the batch against its 8x4 pixel block LANE-PARALLEL (lane l tests entry
-//      32c+l: exact minimum of the conic's quadratic form over the block vs. the entry's alpha<1/255
-//      cut) and ballots the hits into 8 masks;
-//   4. the warp walks only its hits, in list order, with broadcast 16-byte shared loads.
+//   composite2_kernel (default): 4 consumer warps, 8x8 pixels each, TWO pixels per lane in packed FP32
+//                                (FFMA2 / FMUL2 / FADD2), branch-free blending — see the block comment above it.
+//   composite_kernel           : the 1-pixel-per-lane kernel it replaced (8 consumer warps, 8x4 pixels each);
+//                                kept as PG_COMP_VARIANT=0..9 for A/B measurements and as a second
+//                                implementation of the same arithmetic.
+//
+// Walk of a tile's sorted list, per batch of up to COMP_BATCH entries:
+//   1. ids are prefetched by TMA bulk copies (1 KB chunks, double-buffered); entries the binning stage proved
+//      invisible for the whole tile (PG_CULL_FLAG) and, once every main chain has terminated, environment
+//      entries are dropped by a ballot compaction — they are never fetched;
+//   2. each surviving id's 48-byte record {xy, conic, opacity, depth, cut|object, rgb} is GATHERED into a
+//      shared-memory ring by 16-byte cp.async whose completion arrives on the stage's `full` mbarrier
+//      (4-stage ring: later batches land while the current one is composited);
+//   3. every consumer warp tests the batch against its pixel block LANE-PARALLEL (lane l tests entry 32c+l:
+//      exact minimum of the conic's quadratic form over the block vs. the entry's alpha<1/255 cut) and
+//      ballots the hits;
+//   4. the warp walks only its hits, in list order, with broadcast 16-byte shared loads, then releases the
+//      stage on its `empty` mbarrier.  No CTA-wide barrier in the steady state.
 // Culling is conservative (a margin covers float rounding), so every (pixel, Gaussian) pair that
 // the reference would blend is blended with the reference's operation order: results are unchanged.
 //
@@ -20,8 +27,7 @@
 //             render (visible masks, sem-seg) and one transmittance chain per object (silhouettes);
 //             alpha is evaluated once per (pixel, Gaussian).
 //
-// Issue-bound on the FP32/ALU pipes (exp is a 12-op FMA polynomial so that results are
-// bit-reproducible on the CPU oracle).
+// exp is a 12-op FMA polynomial so that results are bit-reproducible on the CPU oracle.
 #include <cstdlib>
 #include <cstring>
 
