@@ -54,7 +54,7 @@ def parse_args():
     ap.add_argument("--no-gpu-baseline", action="store_true")
     ap.add_argument("--gpu-baseline-frames", type=int, default=10)
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline sample")
-    ap.add_argument("--ref-seconds", type=float, default=240.0, help="cap of the --impl reference run")
+    ap.add_argument("--ref-seconds", type=float, default=150.0, help="cap of the --impl reference run")
     return ap.parse_args()
 
 
