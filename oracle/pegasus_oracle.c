@@ -18,6 +18,11 @@
  *   - quaternion -> rotation    : GSP/utils/general_utils.py:78-99 (build_rotation)
  *   - covariance R S S^T R^T    : GSP/utils/general_utils.py:101-110, src/gs/gaussian_model.py:38-42
  *   - view / projection matrices: GSP/utils/graphics_utils.py:38-71, GSP/scene/cameras.py:54-57
+ * Cross-checks that stand in for the missing rasterizer vectors (they narrow "unpinned", they do not lift
+ * it): tests/test_oracle_analytic.py (an independent float64 numpy restatement of the published equations:
+ * radii, tile rectangles and pair counts exactly, images within float32 round-off; a closed-form
+ * single-Gaussian known answer) and baseline/upstream_style.cu (a second GPU implementation in the
+ * upstream's expression form, tests/test_gpu_baseline.py).
  *
  * NUMERICAL SPEC.  Every floating-point operation below is an individually rounded IEEE-754
  * binary32 operation in the stated order; fused multiply-adds appear only where FMA() is written.
