@@ -5,7 +5,8 @@
 //                      also accumulates the digit histograms of both tile-sort passes (shared-memory
 //                      reductions: per pair for the low digit, per run for the high digit).
 //   tile_scan_kernel : exclusive digit bases of both tile-sort passes.
-//   ranges_kernel    : identifyTileRanges on the sorted tile ids.
+//   tile_order_kernel: normalises the tile ranges the last sort pass reduced (identifyTileRanges happens
+//                      inside that pass) and orders the tiles by descending list length for compositing.
 //   export_keys_kernel (tests only): rebuilds the reference's 64-bit tile|depth keys.
 #include "pg_common.cuh"
 #include "tile_cull.h"
@@ -368,51 +369,23 @@ tile_scan_kernel(const uint32_t* __restrict__ hist /*[2][256]*/, uint32_t* __res
     bins[tid] = wb + x - v;
 }
 
-// identifyTileRanges on the sorted tile ids: ranges[tile] = [first, last + 1); tiles without pairs keep
-// the (0, 0) of the per-frame clear.  n lives on the device (stored pairs).  Four consecutive ids per
-// thread (one 16-byte load + the two neighbours, which hit L1): the kernel is a pure 4 B/pair stream.
-__global__ void __launch_bounds__(256)
-ranges_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ n_ptr, uint2* __restrict__ ranges) {
-    const uint32_t n = *n_ptr;
-    const uint32_t nvec = (n + 3u) / 4u;
-    const uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < nvec; j += stride) {
-        const uint32_t i0 = 4u * j;
-        uint32_t k[6];  // k[0] = id before the group, k[1..4] = the group, k[5] = id after it
-        if (i0 + 4u <= n) {
-            const uint4 v = *reinterpret_cast<const uint4*>(keys + i0);
-            k[1] = v.x; k[2] = v.y; k[3] = v.z; k[4] = v.w;
-        } else {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) k[1 + e] = (i0 + e < n) ? keys[i0 + e] : 0xFFFFFFFFu;
-        }
-        k[0] = i0 > 0 ? keys[i0 - 1] : 0xFFFFFFFFu;          // never a tile id
-        k[5] = (i0 + 4u < n) ? keys[i0 + 4u] : 0xFFFFFFFFu;
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const uint32_t i = i0 + e;
-            if (i < n) {
-                if (k[e] != k[1 + e]) ranges[k[1 + e]].x = i;
-                if (i == n - 1 || k[2 + e] != k[1 + e]) ranges[k[1 + e]].y = i + 1;
-            }
-        }
-    }
-}
-
 // Compositing launch order: tile ids by descending list length (longest-processing-time-first keeps
 // the SMs evenly loaded to the end of the kernel; natural order leaves a ~14 % idle tail).  One CTA:
 // counting sort on length / 16 (4096 buckets, longer lists clipped into the first bucket); the order
 // inside a bucket is irrelevant.
 constexpr int ORDER_BUCKETS = 4096;
 __global__ void __launch_bounds__(1024)
-tile_order_kernel(const uint2* __restrict__ ranges, uint32_t tiles, uint32_t* __restrict__ order) {
+tile_order_kernel(uint2* __restrict__ ranges, uint32_t tiles, uint32_t* __restrict__ order) {
     __shared__ uint32_t s_cnt[ORDER_BUCKETS];
     __shared__ uint32_t s_warp[32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < ORDER_BUCKETS; i += 1024) s_cnt[i] = 0;
     __syncthreads();
     for (uint32_t t = tid; t < tiles; t += 1024) {
-        const uint2 r = ranges[t];
+        // the last sort pass left (~first, last + 1), or (0, 0) for a tile without pairs: normalise to [first, last + 1)
+        uint2 r = ranges[t];
+        r = r.y == 0 ? make_uint2(0u, 0u) : make_uint2(~r.x, r.y);
+        ranges[t] = r;
         const uint32_t b = (ORDER_BUCKETS - 1) - min((r.y - r.x) >> 4, (uint32_t)(ORDER_BUCKETS - 1));
         atomicAdd(&s_cnt[b], 1u);
     }
@@ -496,16 +469,7 @@ int launch_tile_scan(const uint32_t* hist_tile, uint32_t* bins, Counters* counte
     return PG_OK;
 }
 
-int launch_ranges(const uint32_t* sorted_tile_keys, const uint32_t* n_ptr, uint32_t max_n, uint2* ranges, cudaStream_t stream) {
-    if (max_n == 0) return PG_OK;
-    const uint32_t blocks = min((max_n / 4u + 255u) / 256u + 1u, (uint32_t)(PG_SM_COUNT * 16));
-    ranges_kernel<<<blocks, 256, 0, stream>>>(sorted_tile_keys, n_ptr, ranges);
-    count_launch(1);
-    PG_CUDA_CHECK(cudaGetLastError());
-    return PG_OK;
-}
-
-int launch_tile_order(const uint2* ranges, uint32_t tiles, uint32_t* order, cudaStream_t stream) {
+int launch_tile_order(uint2* ranges, uint32_t tiles, uint32_t* order, cudaStream_t stream) {
     tile_order_kernel<<<1, 1024, 0, stream>>>(ranges, tiles, order);
     count_launch(1);
     PG_CUDA_CHECK(cudaGetLastError());

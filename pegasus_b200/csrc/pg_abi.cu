@@ -8,8 +8,9 @@
 //   emit_kernel                                 tile-row culling + scan + (tile, index) pairs in depth order
 //                                               + digit histograms of the tile sort
 //   tile_scan_kernel                            digit bases of the tile sort
-//   onesweep_pass_kernel x2                     stored pairs by tile id (stable)  => reference order
-//   ranges_kernel                               ranges[tile] from the sorted tile ids
+//   onesweep_pass_kernel x2                     stored pairs by tile id (stable)  => reference order; the last
+//                                               pass also reduces the tile ranges (identifyTileRanges)
+//   tile_order_kernel                           normalises the ranges, tiles by descending list length
 //   composite_kernel | composite_masks_kernel   A.7 (+ fused K+3 passes)
 //
 // Nothing here synchronises with the host: R stays on the device (grids are sized by the pair
@@ -44,15 +45,14 @@ int launch_hist(const uint32_t* keys, uint32_t n, int npass, uint32_t* hist, cud
 int launch_onesweep_pass(bool iota, bool write_keys, const uint32_t* keys_in, uint32_t* keys_out,
                          const uint32_t* vals_in, uint32_t* vals_out, const uint32_t* n_ptr,
                          uint32_t n_imm, uint32_t max_tiles, int begin_bit, int num_bits,
-                         const uint32_t* bin_base, uint32_t* status, uint32_t* ticket,
+                         const uint32_t* bin_base, uint32_t* status, uint32_t* ticket, uint2* ranges_raw,
                          cudaStream_t stream);
 int launch_emit(bool keep_all, const uint32_t* sorted_dkey, const uint32_t* perm, const ushort4* rects, const GeomRec* recs,
                 uint32_t P, uint32_t gx, int W, int H, uint32_t* tkeys, uint32_t* tvals, uint32_t R_cap, uint32_t* status,
                 uint32_t n_env, uint32_t* tile_obj_count, Counters* counters, int bits_lo, uint32_t* hist_tile,
                 cudaStream_t stream);
 int launch_tile_scan(const uint32_t* hist_tile, uint32_t* bins, Counters* counters, cudaStream_t stream);
-int launch_ranges(const uint32_t* sorted_tile_keys, const uint32_t* n_ptr, uint32_t max_n, uint2* ranges, cudaStream_t stream);
-int launch_tile_order(const uint2* ranges, uint32_t tiles, uint32_t* order, cudaStream_t stream);
+int launch_tile_order(uint2* ranges, uint32_t tiles, uint32_t* order, cudaStream_t stream);
 int launch_export_keys(const uint2* ranges, uint32_t tiles, const uint32_t* point_list, const GeomRec* recs,
                        uint64_t* keys, uint32_t* point_list_out, uint32_t* ranges_out, cudaStream_t stream);
 int launch_pose(int K, const int32_t* first, const PoseDev* poses_dev, const pg_canonical* canon,
@@ -176,7 +176,7 @@ static int run_binning(const pg_raster_settings* s, const pg_gaussians* g, const
     for (int p = 0; p < 4; ++p) {
         rc = launch_onesweep_pass(p == 0, true, ka, kb, va, vb, nullptr, (uint32_t)P, L.tilesP, 8 * p, 8,
                                   hist + p * RADIX, st + (size_t)p * L.tilesP * RADIX,
-                                  &counters->tile_counter[p], stream);
+                                  &counters->tile_counter[p], nullptr, stream);
         if (rc) return rc;
         uint32_t* t = ka; ka = kb; kb = t;
         t = va; va = vb; vb = t;
@@ -199,22 +199,20 @@ static int run_binning(const pg_raster_settings* s, const pg_gaussians* g, const
     uint32_t* bins = at<uint32_t>(ws, L.bins_tile);
     uint32_t* stt = at<uint32_t>(ws, L.status_tile);
     const bool two = bits_hi > 0;
-    // pass lo: a -> b ; pass hi: b -> a.  With a single pass the result lands in b.  The sorted tile
-    // ids are kept: ranges_kernel finds the tile boundaries in them.
-    rc = launch_onesweep_pass(false, true, at<uint32_t>(ws, L.tkey_a), at<uint32_t>(ws, L.tkey_b),
+    // pass lo: a -> b ; pass hi: b -> a.  With a single pass the result lands in b.  The LAST pass does not
+    // write the sorted tile ids: it reduces the tile ranges instead (raw form, normalised by tile_order_kernel).
+    uint2* ranges_raw = at<uint2>(ws, L.ranges);
+    rc = launch_onesweep_pass(false, two, at<uint32_t>(ws, L.tkey_a), at<uint32_t>(ws, L.tkey_b),
                               at<uint32_t>(ws, L.tval_a), at<uint32_t>(ws, L.tval_b), &counters->sort_n, 0,
-                              L.tilesR, 0, bits_lo, bins, stt, &counters->tile_counter[5], stream);
+                              L.tilesR, 0, bits_lo, bins, stt, &counters->tile_counter[5], two ? nullptr : ranges_raw, stream);
     if (rc) return rc;
     if (two) {
-        rc = launch_onesweep_pass(false, true, at<uint32_t>(ws, L.tkey_b), at<uint32_t>(ws, L.tkey_a),
+        rc = launch_onesweep_pass(false, false, at<uint32_t>(ws, L.tkey_b), at<uint32_t>(ws, L.tkey_a),
                                   at<uint32_t>(ws, L.tval_b), at<uint32_t>(ws, L.tval_a), &counters->sort_n, 0,
                                   L.tilesR, bits_lo, bits_hi, bins + RADIX, stt + (size_t)L.tilesR * RADIX,
-                                  &counters->tile_counter[6], stream);
+                                  &counters->tile_counter[6], ranges_raw, stream);
         if (rc) return rc;
     }
-    rc = launch_ranges(at<uint32_t>(ws, two ? L.tkey_a : L.tkey_b), &counters->sort_n, (uint32_t)R_cap,
-                       at<uint2>(ws, L.ranges), stream);
-    if (rc) return rc;
     rc = launch_tile_order(at<uint2>(ws, L.ranges), L.tiles, at<uint32_t>(ws, L.tile_order), stream);
     if (rc) return rc;
     prof_mark(6, stream);

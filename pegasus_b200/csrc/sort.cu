@@ -61,7 +61,7 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, uint32_t* __restrict_
                      const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ vals_out,
                      const uint32_t* __restrict__ n_ptr, uint32_t n_imm, int begin_bit, int num_bits,
                      const uint32_t* __restrict__ bin_base, uint32_t* __restrict__ status,
-                     uint32_t* __restrict__ ticket) {
+                     uint32_t* __restrict__ ticket, uint2* __restrict__ ranges_raw) {
     constexpr int WARPS = SORT_THREADS / 32;
     // s_warp_pos[w][d]: first the number of digit-d items of warp w (early counts), then the running
     // position inside the CTA-tile's digit-sorted staging buffer where warp w's next digit-d item goes
@@ -201,6 +201,14 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, uint32_t* __restrict_
         uint32_t dst = s_gbase[d] + j;
         if (WRITE_KEYS) keys_out[dst] = k;
         vals_out[dst] = s_vals[j];
+        // Last pass of the tile sort (keys are whole tile ids): identifyTileRanges happens here.  Where the id
+        // changes inside this CTA-tile's staging buffer, a run of that id starts / ends at a known output
+        // position; the tile's range is the union over CTA-tiles: max of the ends, min of the starts (kept
+        // bit-inverted, so that the per-frame clear to zero is the identity of both reductions).
+        if (ranges_raw) {
+            if (j == 0 || s_keys[j - 1] != k) atomicMax(&ranges_raw[k].x, ~dst);
+            if (j + 1 == tile_n || s_keys[j + 1] != k) atomicMax(&ranges_raw[k].y, dst + 1u);
+        }
     }
 }
 
@@ -219,18 +227,18 @@ int launch_hist(const uint32_t* keys, uint32_t n, int npass, uint32_t* hist, cud
 int launch_onesweep_pass(bool iota, bool write_keys, const uint32_t* keys_in, uint32_t* keys_out,
                          const uint32_t* vals_in, uint32_t* vals_out, const uint32_t* n_ptr,
                          uint32_t n_imm, uint32_t max_tiles, int begin_bit, int num_bits,
-                         const uint32_t* bin_base, uint32_t* status, uint32_t* ticket,
+                         const uint32_t* bin_base, uint32_t* status, uint32_t* ticket, uint2* ranges_raw,
                          cudaStream_t stream) {
     if (max_tiles == 0) return PG_OK;
     dim3 grid(max_tiles), block(SORT_THREADS);
     if (iota && write_keys)
-        onesweep_pass_kernel<true, true><<<grid, block, 0, stream>>>(keys_in, keys_out, vals_in, vals_out, n_ptr, n_imm, begin_bit, num_bits, bin_base, status, ticket);
+        onesweep_pass_kernel<true, true><<<grid, block, 0, stream>>>(keys_in, keys_out, vals_in, vals_out, n_ptr, n_imm, begin_bit, num_bits, bin_base, status, ticket, ranges_raw);
     else if (!iota && write_keys)
-        onesweep_pass_kernel<false, true><<<grid, block, 0, stream>>>(keys_in, keys_out, vals_in, vals_out, n_ptr, n_imm, begin_bit, num_bits, bin_base, status, ticket);
+        onesweep_pass_kernel<false, true><<<grid, block, 0, stream>>>(keys_in, keys_out, vals_in, vals_out, n_ptr, n_imm, begin_bit, num_bits, bin_base, status, ticket, ranges_raw);
     else if (!iota && !write_keys)
-        onesweep_pass_kernel<false, false><<<grid, block, 0, stream>>>(keys_in, keys_out, vals_in, vals_out, n_ptr, n_imm, begin_bit, num_bits, bin_base, status, ticket);
+        onesweep_pass_kernel<false, false><<<grid, block, 0, stream>>>(keys_in, keys_out, vals_in, vals_out, n_ptr, n_imm, begin_bit, num_bits, bin_base, status, ticket, ranges_raw);
     else
-        onesweep_pass_kernel<true, false><<<grid, block, 0, stream>>>(keys_in, keys_out, vals_in, vals_out, n_ptr, n_imm, begin_bit, num_bits, bin_base, status, ticket);
+        onesweep_pass_kernel<true, false><<<grid, block, 0, stream>>>(keys_in, keys_out, vals_in, vals_out, n_ptr, n_imm, begin_bit, num_bits, bin_base, status, ticket, ranges_raw);
     PG_CUDA_CHECK(cudaGetLastError());
     count_launch(1);
     return PG_OK;

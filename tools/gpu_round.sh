@@ -18,9 +18,9 @@ timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > $OUT/bench_r
 echo "reference exit $?"; tail -c 300 $OUT/bench_reference.json
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
   --log-file $OUT/launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-gpu-baseline > $OUT/launches_run.log 2>&1
-# frames before the timed ones: 3 calibration + 3 stats + 3 slot sizing + 1 warm-up = 10 frames x 14 pegasus kernels
+# frames before the timed ones: 3 calibration + 3 stats + 3 slot sizing + 1 warm-up = 10 frames x 13 pegasus kernels
 timeout 900 ncu --set full --clock-control none --import-source on \
-  -k regex:'composite|emit|onesweep|preprocess|hist_kernel|scan_rows|tile_scan|ranges|tile_order' -s 140 -c 14 -o $OUT/prof \
+  -k regex:'composite|emit|onesweep|preprocess|hist_kernel|scan_rows|tile_scan|tile_order' -s 130 -c 13 -o $OUT/prof \
   python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-gpu-baseline > $OUT/prof_run.log 2>&1
 python tools/ncu_summary.py $OUT/prof.ncu-rep $OUT/ncu_full_summary.json > /dev/null 2>&1
 ls -la $OUT
