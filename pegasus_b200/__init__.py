@@ -18,6 +18,7 @@ from .render import (render_rgb_and_depth, render_silhouette_mask, render_visib_
 from .sh_rotation import generate_pose_packets  # noqa: F401
 from .generate import DatasetGenerator  # noqa: F401
 from .bop_writer import BOPDatasetWriter, ObjectMeta  # noqa: F401
+from . import sweep  # noqa: F401
 
 __all__ = ["GaussianRasterizationSettings", "GaussianRasterizer", "ComposedScene", "Camera", "focal2fov",
            "fov2focal", "render_rgb_and_depth", "render_silhouette_mask", "render_visib_mask",

@@ -171,11 +171,13 @@ class DatasetGenerator:
                  data_points: Sequence[str] = DATA_POINTS, metas: Optional[Sequence] = None,
                  pose_source: str = "reference", rank: int = 0, world: int = 1,
                  on_frame: Optional[Callable[[int, Dict[str, np.ndarray]], None]] = None,
-                 pose_packets: Optional[torch.Tensor] = None) -> Dict[str, int]:
+                 pose_packets: Optional[torch.Tensor] = None,
+                 frames: Optional[Sequence[int]] = None) -> Dict[str, int]:
         """cams[f]: camera of frame f.  poses: None (keep the scene's current pose), one list [(R, t)] * K
         (static mode: PegasusSetup.static_object_pose) or a list over frames of such lists (dynamic mode:
         dynamic_object_pose + update_object_pose, in absolute form).  `pose_packets` may pass the same
         thing as an already packed (frames, K, 103) HOST tensor (e.g. received by broadcast).
+        frames: explicit frame list instead of the rank / world round robin.
         writer: a BOPDatasetWriter or None.  on_frame(f, products) runs on a writer thread and sees numpy
         views of the pinned set (the masks expanded from their bit-packed wire format), valid until it
         returns.  Returns counters."""
@@ -184,7 +186,11 @@ class DatasetGenerator:
                 raise ValueError(f"unknown data point {d!r}")
         sc = self.scene
         n = len(cams)
-        mine = list(range(rank, n, world))
+        # frames of this call: round-robin over the ranks, or an explicit list (a WorkItem of pegasus_b200.sweep:
+        # a contiguous range of one scene's views, frame ids staying those of the whole camera path)
+        mine = [int(f) for f in frames] if frames is not None else list(range(rank, n, world))
+        if any(f < 0 or f >= n for f in mine):
+            raise ValueError("frames must index cams")
         per_frame = None
         if pose_packets is not None:
             per_frame = pose_packets if pose_packets.dim() == 3 else pose_packets[None]
