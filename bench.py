@@ -581,7 +581,8 @@ def run_ours(args):
             "roofline": roofline,
             "roofline_stages": stages,
             "sequential_ms_per_step": seq_ms_per_step,
-            "compositing_stats": {"pairs_evaluated": ev_, "pairs_reaching_exp": ex_, "pairs_blended": bl_},
+            "compositing_stats": {"pairs_evaluated": ev_, "pairs_reaching_exp": ex_, "pairs_blended": bl_,
+                                  "pixel_slots_walked": float(np.mean([s.get("pixel_slots", 0) for s in stats]))},
             "cpu_baseline": cpu_baseline,
             "gpu_baseline": gpu_baseline,
         }

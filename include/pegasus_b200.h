@@ -211,8 +211,10 @@ int pg_profile_enable(int32_t max_frames);
 int32_t pg_profile_frames(void);
 int pg_profile_read(int32_t frame, float* stage_ms /*[PG_NUM_STAGES]*/);
 uint64_t pg_launch_count(void); /* kernels this library has launched in this process */
-/* settings.debug bit 1: {pairs evaluated, pairs reaching exp, pairs blended, 0} of the last forward */
-int pg_read_stats(const void* workspace, uint64_t* host_stats4, pg_stream_t stream);
+/* settings.debug bit 1: {pixel-Gaussian pairs evaluated, reaching exp, blended, pixel slots walked,
+ * warp-hits of environment entries, of object entries while a main chain lives, of object entries afterwards,
+ * 32-entry cull passes afterwards} of the last forward */
+int pg_read_stats(const void* workspace, uint64_t* host_stats8, pg_stream_t stream);
 
 /* rgb [3,H,W] f32 -> [H,W,3] u8 ; depth [1,H,W] f32 metres -> [H,W] u16 millimetres. */
 int pg_pack_frame(int32_t width, int32_t height, const float* color, const float* depth,

@@ -348,10 +348,10 @@ int pg_export_binning(const void* ws, int32_t P, int32_t width, int32_t height, 
                               (cudaStream_t)stream);
 }
 
-int pg_read_stats(const void* ws, uint64_t* host_stats4, pg_stream_t stream) {
-    if (!ws || !host_stats4) { set_error("null argument"); return PG_ERR_INVALID; }
+int pg_read_stats(const void* ws, uint64_t* host_stats8, pg_stream_t stream) {
+    if (!ws || !host_stats8) { set_error("null argument"); return PG_ERR_INVALID; }
     const char* src = reinterpret_cast<const char*>(ws) + offsetof(Counters, stats);
-    PG_CUDA_CHECK(cudaMemcpyAsync(host_stats4, src, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    PG_CUDA_CHECK(cudaMemcpyAsync(host_stats8, src, 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     return PG_OK;
 }
 

@@ -69,10 +69,16 @@ __device__ __forceinline__ bool block_culled(float gx, float gy, float qa, float
     return pd && (qmin * 0.9999f - 1e-3f > -cut);
 }
 
+// Bit 6 of GeomRec::b.w: the record needs the compositing kernel's general path (opacity > 0.99, where the
+// reference's min(0.99, .) can bind, or a non-finite field); all other records take the lean path.
+#define PG_REC_GENERAL 0x40
+#define PG_REC_FLAGS 0x7F
+
 // ---- per-Gaussian record staged into shared memory by the compositing kernel (48 B) ----------
 struct __align__(16) GeomRec {
     float4 a;  // x, y, conic.x, conic.y
-    float4 b;  // conic.z, opacity, depth, cut (power below which alpha < 1/255; low 6 mantissa bits = object id)
+    float4 b;  // conic.z, opacity, depth, cut (power below which alpha < 1/255; mantissa bits 0-5 = object id,
+               // bit 6 = PG_REC_GENERAL)
     float4 c;  // r, g, b, object id (as int bits; 0 = environment, k+1 = object k)
 };
 
@@ -83,7 +89,8 @@ struct Counters {
     uint32_t num_visible;
     uint32_t sort_n;         // pairs stored = min(pairs kept by the binning stage, pair capacity): what the tile sort processes
     uint32_t tile_counter[8];  // dynamic CTA-tile tickets: [0..3] depth-sort passes, [4] emit, [5..6] tile-sort passes
-    unsigned long long stats[4];  // debug&2: pairs evaluated, pairs reaching exp, pairs blended (all chains), spare
+    unsigned long long stats[8];  // debug&2: pairs evaluated, pairs reaching exp, pairs blended (all chains), pixel slots walked,
+                                  // warp-hits: environment, object while a main chain lives, object afterwards; cull passes afterwards
     unsigned long long rendered_full;  // sum of all tile-rectangle areas = the reference's num_rendered
 };
 

@@ -237,11 +237,17 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const PreArgs a) {
                 rec.a = make_float4(pixx, pixy, conx, cony);
                 // cut: alpha = min(.99, op*exp(power)) < 1/255 is certain for power < -(ln(255*op) + 0.01)
                 // (the 1 % margin dwarfs the error of logf and of the exp polynomial); never above 0.
-                // The object id rides in the low 6 mantissa bits (makes the cut at most 63 ulp more negative).
+                // __logf is the one approximate operation here (abs. error < 1e-5 on this range): it only moves the
+                // cut inside the 0.01 margin.  The low 7 mantissa bits carry the object id (bits 0-5) and the
+                // "general path" flag (bit 6: opacity > 0.99, so min(0.99, .) can bind, or a non-finite record);
+                // clearing them makes the cut at most 127 ulp (< 2e-3 at -80, < 1e-4 typically) LESS negative,
+                // which the margin covers as well.
                 float cut = -80.0f;
                 if (op > 0.0f) cut = fminf(-(__logf(255.0f * op) + 0.01f), -1e-6f);
                 if (!(cut > -80.0f)) cut = -80.0f;
-                cut = __int_as_float((__float_as_int(cut) & ~63) | obj);
+                const bool plain = op <= 0.99f && isfinite(pixx) && isfinite(pixy) && isfinite(conx) && isfinite(cony) &&
+                                   isfinite(conz) && isfinite(pv[2]) && isfinite(rgb[0]) && isfinite(rgb[1]) && isfinite(rgb[2]);
+                cut = __int_as_float((__float_as_int(cut) & ~127) | obj | (plain ? 0 : PG_REC_GENERAL));
                 rec.b = make_float4(conz, op, pv[2], cut);
                 rec.c = make_float4(rgb[0], rgb[1], rgb[2], __int_as_float(obj));
                 a.recs[idx] = rec;

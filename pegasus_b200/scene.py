@@ -246,12 +246,14 @@ class ComposedScene:
         """Compositing statistics of the last render(debug=2); synchronises."""
         L = _lib.load()
         ws = workspace_for(self.device, slot)
-        host = torch.zeros(4, dtype=torch.int64).pin_memory()
+        host = torch.zeros(8, dtype=torch.int64).pin_memory()
         stream = torch.cuda.current_stream(self.device)
         _lib.check(L.pg_read_stats(C.c_void_p(ws.buf.data_ptr()), C.c_void_p(host.data_ptr()),
                                    C.c_void_p(stream.cuda_stream)), "pg_read_stats")
         stream.synchronize()
-        return dict(pairs_evaluated=int(host[0]), pairs_exp=int(host[1]), pairs_blended=int(host[2]))
+        return dict(pairs_evaluated=int(host[0]), pairs_exp=int(host[1]), pairs_blended=int(host[2]),
+                    pixel_slots=int(host[3]), hits_env=int(host[4]), hits_obj_main=int(host[5]),
+                    hits_obj_after=int(host[6]), cull_passes_after=int(host[7]))
 
     def read_status(self, slot: int = 0) -> Dict[str, int]:
         """Status of the last (possibly still running) render on this device; synchronises."""
