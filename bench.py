@@ -345,7 +345,7 @@ def run_ours(args):
     # overlap frame i's compositing.  Every frame's complete work lies inside the timed region.
     NSLOT = max(1, int(os.environ.get("PG_SLOTS", "3")))
     # PG_SPLIT=1 (default): every slot has a high-priority stream for the per-Gaussian / sort stages and a
-    # normal-priority one for compositing (pg_set_composite_stream), so the latency-bound stages of frame
+    # normal-priority one for compositing (pg_launch_opts.composite_stream), so the latency-bound stages of frame
     # i+1 co-run with the issue-bound compositing of frame i on every SM.
     SPLIT = NSLOT > 1 and os.environ.get("PG_SPLIT", "1") != "0"
     main = torch.cuda.current_stream(dev)
@@ -376,6 +376,7 @@ def run_ours(args):
     for i in range(W_steps):
         frame_on_slot(i)
     torch.cuda.synchronize()
+    overflow0 = [scene.read_status(slot=sl)["overflow_frames"] for sl in range(NSLOT)]
     pgd.barrier()
     launches0 = int(L.pg_launch_count())
     sampler = ClockSampler(local)
@@ -399,8 +400,8 @@ def run_ours(args):
     ms = ev0.elapsed_time(ev1)
     launches = int(L.pg_launch_count()) - launches0
     clocks = sampler.stop()
-    for sl in range(NSLOT):
-        if scene.read_status(slot=sl)["overflow"]:
+    for sl in range(NSLOT):  # sticky counter: covers every frame rendered on the slot since `overflow0` was taken
+        if scene.read_status(slot=sl)["overflow_frames"] != overflow0[sl]:
             raise RuntimeError("pair capacity overflowed inside the timed region; the measurement is invalid")
     # per-stage kernel durations: the same frames once more with ONE frame in flight (with several in
     # flight a pair of CUDA events around one kernel also covers other frames' kernels)

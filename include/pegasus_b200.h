@@ -4,8 +4,11 @@
  *
  * Every entry point takes plain pointers and sizes (device pointers unless stated), never a torch
  * type, and enqueues work on the caller's CUDA stream.  The library allocates no device memory and
- * keeps no state except a thread-local error string: inputs, outputs and the workspace belong to
- * the caller (the reference's binding hands the extension three grow-only torch buffers the same way).
+ * keeps no state between calls except a thread-local error string (and the opt-in profiling events):
+ * inputs, outputs and the workspace belong to the caller (the reference's binding hands the extension
+ * three grow-only torch buffers the same way); everything that modifies how ONE call is issued
+ * (a second stream for compositing, an event to record, the numerics mode) travels in that call's
+ * pg_launch_opts.
  *
  * Which reference interface each entry replaces (paths relative to /root/reference,
  * GSP = submodules/gaussian-splatting-pegasus):
@@ -150,7 +153,40 @@ typedef struct pg_status {
     uint32_t overflow;     /* !=0: the stored pairs exceeded the workspace's pair capacity; outputs are invalid */
     uint32_t num_visible;
     uint32_t num_stored;   /* pairs actually stored and sorted (== R with debug bit 2), clamped to the capacity */
+    /* sticky: accumulated over every forward that used this workspace since pg_workspace_init (a forward clears
+     * the four fields above, never these two), so a caller that checks once after many frames misses nothing */
+    uint32_t overflow_frames;  /* forwards whose stored pairs exceeded the pair capacity */
+    uint32_t max_pairs_needed; /* largest stored-pair demand seen (what pair_capacity should have been), <= 2^30 */
 } pg_status;
+
+/* Numerics of the compositing stage. */
+#define PG_NUMERICS_EXACT 0 /* every float op an individually rounded IEEE op in the reference's order, exp as an
+                             * FMA polynomial: images bit-reproducible on the CPU oracle */
+#define PG_NUMERICS_FAST 1  /* exp through MUFU ex2.approx (as the reference's own expf is) and the blend weight
+                             * alpha*T formed once per Gaussian: within the reference tolerances (RGB 1e-3,
+                             * depth 1e-4 relative), not bit-reproducible on a CPU */
+
+/* Per-call options of pg_rasterize_forward / pg_render_composed (NULL = all defaults).  Plain data, read
+ * during the call only.
+ *  scene_read_event : recorded on `stream` right after the per-Gaussian stage, the last stage that reads the
+ *                     scene arrays (means3D, shs, opacities, scales, rotations): a pg_pose_apply for the
+ *                     following frame on another stream only has to wait for this event.
+ *  composite_stream : the compositing kernel runs there instead of on `stream`; fork_event is recorded on
+ *                     `stream` after the binning stages and waited for by composite_stream, join_event is
+ *                     recorded on composite_stream after compositing and waited for by `stream`, so for the
+ *                     caller the whole frame is still ordered on `stream`.  With `stream` created at a HIGHER
+ *                     priority the latency-bound stages of the following frame (another stream pair) co-run
+ *                     with this frame's compositing.  Needs both events.
+ *  status_host      : PINNED host memory; the status block is copied there at the end of the frame (on
+ *                     `stream`), so the caller can check every frame for overflow when it retires it. */
+typedef struct pg_launch_opts {
+    pg_event_t scene_read_event;
+    pg_stream_t composite_stream;
+    pg_event_t fork_event;
+    pg_event_t join_event;
+    pg_status* status_host;
+    int32_t numerics; /* PG_NUMERICS_* */
+} pg_launch_opts;
 
 const char* pg_version(void);
 const char* pg_last_error(void);
@@ -158,29 +194,17 @@ const char* pg_last_error(void);
 /* Bytes of workspace needed for P Gaussians, a WxH image and at most pair_capacity pairs. */
 size_t pg_workspace_bytes(int32_t P, int32_t width, int32_t height, uint64_t pair_capacity);
 
+/* Once per (re)allocated workspace, before its first use: clears the sticky status fields. */
+int pg_workspace_init(void* workspace, size_t workspace_bytes, pg_stream_t stream);
+
 int pg_rasterize_forward(const pg_raster_settings* settings, const pg_gaussians* g,
                          const pg_raster_outputs* out, void* workspace, size_t workspace_bytes,
-                         uint64_t pair_capacity, pg_stream_t stream);
+                         uint64_t pair_capacity, const pg_launch_opts* opts, pg_stream_t stream);
 
 int pg_render_composed(const pg_raster_settings* settings, const pg_gaussians* g,
                        const pg_object_table* objects, const pg_frame_outputs* out, void* workspace,
-                       size_t workspace_bytes, uint64_t pair_capacity, pg_stream_t stream);
-
-/* Pipelining frames on several streams: the NEXT forward / composed render issued by the calling thread
- * records `event` on its stream right after its per-Gaussian stage — the last stage that reads the
- * scene arrays (means3D, shs, opacities, scales, rotations).  A pg_pose_apply for the following frame
- * on another stream only has to wait for this event, not for the whole frame.  One-shot; NULL clears. */
-int pg_set_scene_read_event(pg_event_t event);
-
-/* Overlapping frames: the NEXT forward / composed render issued by the calling thread launches its
- * compositing kernel on `composite_stream` instead of `stream`: `fork_event` is recorded on `stream`
- * after the binning stages and waited for by `composite_stream`; `join_event` is recorded on
- * `composite_stream` after compositing and waited for by `stream`, so for the caller the whole frame
- * is still ordered on `stream`.  With `stream` created at a HIGHER priority than `composite_stream`
- * the latency-bound per-Gaussian / sort stages of the following frame (another stream pair) take the
- * SM slots that the issue-bound compositing CTAs of this frame free, and the two co-run on every SM.
- * One-shot; a NULL composite_stream clears. */
-int pg_set_composite_stream(pg_stream_t composite_stream, pg_event_t fork_event, pg_event_t join_event);
+                       size_t workspace_bytes, uint64_t pair_capacity, const pg_launch_opts* opts,
+                       pg_stream_t stream);
 
 /* Asynchronously copies the workspace's status block to host_status (pinned host memory). */
 int pg_read_status(const void* workspace, pg_status* host_status, pg_stream_t stream);

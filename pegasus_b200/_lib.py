@@ -63,19 +63,47 @@ class Scene(C.Structure):
 
 class Status(C.Structure):
     _fields_ = [("num_rendered", C.c_uint32), ("overflow", C.c_uint32), ("num_visible", C.c_uint32),
-                ("num_stored", C.c_uint32)]
+                ("num_stored", C.c_uint32), ("overflow_frames", C.c_uint32), ("max_pairs_needed", C.c_uint32)]
 
 
-EXPORTS = ["pg_version", "pg_last_error", "pg_workspace_bytes", "pg_rasterize_forward",
+STATUS_WORDS = C.sizeof(Status) // 4  # 6
+
+NUMERICS_EXACT, NUMERICS_FAST = 0, 1
+
+
+class LaunchOpts(C.Structure):
+    _fields_ = [("scene_read_event", _f), ("composite_stream", _f), ("fork_event", _f), ("join_event", _f),
+                ("status_host", _f), ("numerics", C.c_int32)]
+
+
+EXPORTS = ["pg_version", "pg_last_error", "pg_workspace_bytes", "pg_workspace_init", "pg_rasterize_forward",
            "pg_render_composed", "pg_read_status", "pg_mark_visible", "pg_pose_apply",
            "pg_export_binning", "pg_pack_frame", "pg_profile_enable", "pg_profile_frames",
-           "pg_profile_read", "pg_launch_count", "pg_read_stats", "pg_set_scene_read_event",
-           "pg_set_composite_stream", "pg_pack_masks"]
+           "pg_profile_read", "pg_launch_count", "pg_read_stats", "pg_pack_masks"]
 
 NUM_STAGES = 7
 STAGE_NAMES = ["clear", "preprocess", "depth_sort", "emit", "tile_scan", "tile_sort", "composite"]
 
 _LIB = None
+
+# Process-wide default of pg_launch_opts.numerics for calls that do not name one (set_numerics() / PG_NUMERICS).
+_NUMERICS = {"exact": NUMERICS_EXACT, "fast": NUMERICS_FAST}
+_default_numerics = _NUMERICS.get(os.environ.get("PG_NUMERICS", "exact").lower(), NUMERICS_EXACT)
+
+
+def set_numerics(mode: str) -> None:
+    """'exact': compositing bit-reproducible on the CPU oracle; 'fast': MUFU exp + one blend weight per Gaussian,
+    within the reference tolerances (include/pegasus_b200.h, PG_NUMERICS_*)."""
+    global _default_numerics
+    _default_numerics = _NUMERICS[mode.lower()]
+
+
+def numerics_code(mode=None) -> int:
+    if mode is None:
+        return _default_numerics
+    if isinstance(mode, int):
+        return int(mode)
+    return _NUMERICS[mode.lower()]
 
 
 def lib_path() -> str:
@@ -94,11 +122,14 @@ def load():
     L.pg_last_error.restype = C.c_char_p
     L.pg_workspace_bytes.restype = C.c_size_t
     L.pg_workspace_bytes.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_uint64]
+    L.pg_workspace_init.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
+    L.pg_workspace_init.restype = C.c_int
     L.pg_rasterize_forward.argtypes = [C.POINTER(RasterSettings), C.POINTER(Gaussians),
                                        C.POINTER(RasterOutputs), C.c_void_p, C.c_size_t, C.c_uint64,
-                                       C.c_void_p]
+                                       C.POINTER(LaunchOpts), C.c_void_p]
     L.pg_render_composed.argtypes = [C.POINTER(RasterSettings), C.POINTER(Gaussians), C.POINTER(ObjectTable),
-                                     C.POINTER(FrameOutputs), C.c_void_p, C.c_size_t, C.c_uint64, C.c_void_p]
+                                     C.POINTER(FrameOutputs), C.c_void_p, C.c_size_t, C.c_uint64,
+                                     C.POINTER(LaunchOpts), C.c_void_p]
     L.pg_read_status.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.pg_mark_visible.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.pg_pose_apply.argtypes = [C.c_int32, C.POINTER(C.c_int32), C.c_void_p, C.POINTER(Canonical), C.c_int32,
@@ -114,10 +145,6 @@ def load():
     L.pg_profile_read.argtypes = [C.c_int32, C.POINTER(C.c_float)]
     L.pg_launch_count.restype = C.c_uint64
     L.pg_read_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
-    L.pg_set_scene_read_event.argtypes = [C.c_void_p]
-    L.pg_set_scene_read_event.restype = C.c_int
-    L.pg_set_composite_stream.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
-    L.pg_set_composite_stream.restype = C.c_int
     for name in ("pg_profile_enable", "pg_profile_read", "pg_read_stats"):
         getattr(L, name).restype = C.c_int
     for name in ("pg_rasterize_forward", "pg_render_composed", "pg_read_status", "pg_mark_visible",

@@ -104,7 +104,7 @@ emit_kernel(const uint32_t* __restrict__ sorted_dkey, const uint32_t* __restrict
             int W, int H, uint32_t* __restrict__ tkeys,
             uint32_t* __restrict__ tvals, uint32_t R_cap, uint32_t* __restrict__ status,
             uint32_t n_env, uint32_t* __restrict__ tile_obj_count, Counters* __restrict__ counters,
-            int bits_lo, uint32_t* __restrict__ hist /*[2][RADIX]*/) {
+            Sticky* __restrict__ sticky, int bits_lo, uint32_t* __restrict__ hist /*[2][RADIX]*/) {
     extern __shared__ __align__(16) unsigned char emit_smem_raw[];
     EmitSmem& sm = *reinterpret_cast<EmitSmem*>(emit_smem_raw);
 
@@ -258,7 +258,11 @@ emit_kernel(const uint32_t* __restrict__ sorted_dkey, const uint32_t* __restrict
             if (chunk == num_chunks - 1) {
                 uint64_t R = (uint64_t)prev + total;
                 counters->sort_n = (uint32_t)min(R, (uint64_t)R_cap);
-                if (R > R_cap) counters->overflow = 1;
+                if (R > R_cap) {
+                    counters->overflow = 1;
+                    atomicAdd(&sticky->overflow_frames, 1u);
+                }
+                atomicMax(&sticky->max_pairs_needed, (uint32_t)min(R, (uint64_t)E_VAL_MASK + 1u));
             }
         }
     }
@@ -441,22 +445,19 @@ __global__ void export_keys_kernel(const uint2* __restrict__ ranges, uint32_t ti
 
 int launch_emit(bool keep_all, const uint32_t* sorted_dkey, const uint32_t* perm, const ushort4* rects, const GeomRec* recs,
                 uint32_t P, uint32_t gx, int W, int H, uint32_t* tkeys, uint32_t* tvals, uint32_t R_cap, uint32_t* status,
-                uint32_t n_env, uint32_t* tile_obj_count, Counters* counters, int bits_lo, uint32_t* hist_tile,
-                cudaStream_t stream) {
+                uint32_t n_env, uint32_t* tile_obj_count, Counters* counters, Sticky* sticky, int bits_lo,
+                uint32_t* hist_tile, cudaStream_t stream) {
     uint32_t chunks = (P + EMIT_CHUNK - 1) / EMIT_CHUNK;
     if (chunks == 0) return PG_OK;
-    static bool attr_set = false;
-    if (!attr_set) {
-        PG_CUDA_CHECK(cudaFuncSetAttribute(emit_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EmitSmem)));
-        PG_CUDA_CHECK(cudaFuncSetAttribute(emit_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EmitSmem)));
-        attr_set = true;
-    }
-    if (keep_all)
+    if (keep_all) {
+        PG_CUDA_CHECK(ensure_dynamic_smem(emit_kernel<true>, (int)sizeof(EmitSmem)));
         emit_kernel<true><<<chunks, EMIT_THREADS, sizeof(EmitSmem), stream>>>(sorted_dkey, perm, rects, recs, P, gx, W, H, tkeys, tvals, R_cap, status,
-                                                      n_env, tile_obj_count, counters, bits_lo, hist_tile);
-    else
+                                                      n_env, tile_obj_count, counters, sticky, bits_lo, hist_tile);
+    } else {
+        PG_CUDA_CHECK(ensure_dynamic_smem(emit_kernel<false>, (int)sizeof(EmitSmem)));
         emit_kernel<false><<<chunks, EMIT_THREADS, sizeof(EmitSmem), stream>>>(sorted_dkey, perm, rects, recs, P, gx, W, H, tkeys, tvals, R_cap, status,
-                                                       n_env, tile_obj_count, counters, bits_lo, hist_tile);
+                                                       n_env, tile_obj_count, counters, sticky, bits_lo, hist_tile);
+    }
     count_launch(1);
     PG_CUDA_CHECK(cudaGetLastError());
     return PG_OK;

@@ -618,31 +618,19 @@ static int comp_smem_pad() {
 
 template <bool MASKS, bool STATS, int STAGES, int ILP, int MINB>
 static int launch_two(const CompArgs& a, dim3 grid, cudaStream_t stream) {
-    static int attr_smem = 0;
     const int smem = (int)sizeof(CompSmemT<STAGES>) + comp_smem_pad() +
                      (MASKS ? (int)(PG_MAX_OBJECTS * sizeof(float4)) + a.num_objects * 256 * (int)sizeof(float) : 0);
-    if (smem > attr_smem) {
-        PG_CUDA_CHECK(cudaFuncSetAttribute(composite2_kernel<MASKS, STATS, STAGES, ILP, MINB>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        // residency is bounded by shared memory (~39 KB per CTA): ask for the largest carve-out
-        PG_CUDA_CHECK(cudaFuncSetAttribute(composite2_kernel<MASKS, STATS, STAGES, ILP, MINB>,
-                                           cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        attr_smem = smem;
-    }
+    // residency is bounded by shared memory (~39 KB per CTA): ask for the largest carve-out
+    PG_CUDA_CHECK(ensure_dynamic_smem(composite2_kernel<MASKS, STATS, STAGES, ILP, MINB>, smem, true));
     composite2_kernel<MASKS, STATS, STAGES, ILP, MINB><<<grid, COMP2_THREADS, smem, stream>>>(a);
     return PG_OK;
 }
 
 template <bool MASKS, bool STATS, int STAGES, int ILP, int MINB, int WAITNS = 0, bool FASTEXP = false>
 static int launch_one(const CompArgs& a, dim3 grid, cudaStream_t stream) {
-    static int attr_smem = 0;
     const int smem = (int)sizeof(CompSmemT<STAGES>) +
                      (MASKS ? (int)(PG_MAX_OBJECTS * sizeof(float4)) + a.num_objects * 256 * (int)sizeof(float) : 0);
-    if (smem > attr_smem) {
-        PG_CUDA_CHECK(cudaFuncSetAttribute(composite_kernel<MASKS, STATS, STAGES, ILP, MINB, WAITNS, FASTEXP>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_smem = smem;
-    }
+    PG_CUDA_CHECK(ensure_dynamic_smem(composite_kernel<MASKS, STATS, STAGES, ILP, MINB, WAITNS, FASTEXP>, smem));
     composite_kernel<MASKS, STATS, STAGES, ILP, MINB, WAITNS, FASTEXP><<<grid, COMP_THREADS, smem, stream>>>(a);
     return PG_OK;
 }
@@ -711,15 +699,11 @@ int launch_composite(const CompArgs& a, int gy, bool masks, cudaStream_t stream)
 int launch_composite_from_abi(const uint2* ranges, const uint32_t* tile_order, const uint32_t* point_list, const GeomRec* recs, int W,
                               int H, const float* bg, const pg_raster_outputs* ro, const pg_frame_outputs* fo,
                               const pg_object_table* objs, uint32_t n_env, const uint32_t* tile_obj_count,
-                              unsigned long long* stats, cudaStream_t stream) {
+                              unsigned long long* stats, bool fast, cudaStream_t stream) {
     CompArgs a;
     memset(&a, 0, sizeof(a));
     a.stats = stats;
-    {   // TEMPORARY: numerics mode from the environment until pg_launch_opts carries it
-        static int fast_env = -1;
-        if (fast_env < 0) { const char* e = getenv("PG_NUMERICS"); fast_env = (e && !strcmp(e, "fast")) ? 1 : 0; }
-        a.fast = fast_env;
-    }
+    a.fast = fast ? 1 : 0;
     a.ranges = ranges; a.tile_order = tile_order; a.point_list = point_list; a.recs = recs;
     a.W = W; a.H = H; a.gx = (W + PG_TILE - 1) / PG_TILE;
     const int gy = (H + PG_TILE - 1) / PG_TILE;

@@ -393,11 +393,7 @@ template <bool MASKS, bool NCONTRIB, bool FAST, int STAGES, int MINB, bool BRANC
 static int launch_three(const CompArgs& a, dim3 grid, cudaStream_t stream) {
     const int smem = (int)sizeof(CompSmemT<STAGES>) +
                      (MASKS ? (int)(PG_MAX_OBJECTS * sizeof(float4)) + a.num_objects * 256 * (int)sizeof(float) : 0);
-    // per device and cheap: set on every launch (a process may drive several devices)
-    PG_CUDA_CHECK(cudaFuncSetAttribute(composite3_kernel<MASKS, NCONTRIB, FAST, STAGES, MINB, BRANCHY>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    PG_CUDA_CHECK(cudaFuncSetAttribute(composite3_kernel<MASKS, NCONTRIB, FAST, STAGES, MINB, BRANCHY>,
-                                       cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    PG_CUDA_CHECK(ensure_dynamic_smem(composite3_kernel<MASKS, NCONTRIB, FAST, STAGES, MINB, BRANCHY>, smem, true));
     composite3_kernel<MASKS, NCONTRIB, FAST, STAGES, MINB, BRANCHY><<<grid, COMP2_THREADS, smem, stream>>>(a);
     return PG_OK;
 }

@@ -19,6 +19,9 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <map>
+#include <mutex>
+#include <utility>
 #include <vector>
 
 #include "pg_common.cuh"
@@ -32,6 +35,16 @@ void set_error(const char* fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
+}
+
+// (kernel, device) -> dynamic shared memory already granted with cudaFuncSetAttribute
+int smem_granted(const void* kernel, int device, int bytes, bool record) {
+    static std::mutex mu;
+    static std::map<std::pair<const void*, int>, int> granted;
+    std::lock_guard<std::mutex> lock(mu);
+    int& g = granted[std::make_pair(kernel, device)];
+    if (record && bytes > g) g = bytes;
+    return g;
 }
 
 struct CompArgs;
@@ -49,8 +62,8 @@ int launch_onesweep_pass(bool iota, bool write_keys, const uint32_t* keys_in, ui
                          cudaStream_t stream);
 int launch_emit(bool keep_all, const uint32_t* sorted_dkey, const uint32_t* perm, const ushort4* rects, const GeomRec* recs,
                 uint32_t P, uint32_t gx, int W, int H, uint32_t* tkeys, uint32_t* tvals, uint32_t R_cap, uint32_t* status,
-                uint32_t n_env, uint32_t* tile_obj_count, Counters* counters, int bits_lo, uint32_t* hist_tile,
-                cudaStream_t stream);
+                uint32_t n_env, uint32_t* tile_obj_count, Counters* counters, Sticky* sticky, int bits_lo,
+                uint32_t* hist_tile, cudaStream_t stream);
 int launch_tile_scan(const uint32_t* hist_tile, uint32_t* bins, Counters* counters, cudaStream_t stream);
 int launch_tile_order(uint2* ranges, uint32_t tiles, uint32_t* order, cudaStream_t stream);
 int launch_export_keys(const uint2* ranges, uint32_t tiles, const uint32_t* point_list, const GeomRec* recs,
@@ -63,7 +76,7 @@ int launch_pack_masks(int W, int H, int n_planes, const uint8_t* masks, uint8_t*
 int launch_composite_from_abi(const uint2* ranges, const uint32_t* tile_order, const uint32_t* point_list, const GeomRec* recs, int W,
                               int H, const float* bg, const pg_raster_outputs* ro, const pg_frame_outputs* fo,
                               const pg_object_table* objs, uint32_t n_env, const uint32_t* tile_obj_count,
-                              unsigned long long* stats, cudaStream_t stream);
+                              unsigned long long* stats, bool fast, cudaStream_t stream);
 
 // ---- opt-in profiling (bench / tests): CUDA events at stage boundaries, launch counter ----------
 static std::atomic<unsigned long long> g_launches{0};
@@ -74,33 +87,32 @@ static std::vector<cudaEvent_t> g_events;  // [max_frames][kStageEvents]
 static int g_prof_max = 0;
 static std::atomic<int> g_prof_frames{0};
 static thread_local int t_prof_frame = -1;  // slot of the forward in flight on this thread
-static thread_local cudaEvent_t t_scene_read_event = nullptr;  // pg_set_scene_read_event (one-shot)
-// pg_set_composite_stream (one-shot)
-static thread_local cudaStream_t t_comp_stream = nullptr;
-static thread_local cudaEvent_t t_comp_fork = nullptr, t_comp_join = nullptr;
-static thread_local bool t_comp_split = false;
 
-// Takes the one-shot request: returns the stream compositing runs on and makes it wait for everything
-// enqueued on `stream` so far.
-static bool take_comp_request() {  // every entry point consumes the request, also when it fails early
-    const bool on = t_comp_split;
-    t_comp_split = false;
-    return on;
-}
-static int comp_fork(bool split, cudaStream_t stream, cudaStream_t* cs, cudaEvent_t* join) {
-    *cs = stream;
-    *join = nullptr;
-    if (!split) return PG_OK;
-    PG_CUDA_CHECK(cudaEventRecord(t_comp_fork, stream));
-    PG_CUDA_CHECK(cudaStreamWaitEvent(t_comp_stream, t_comp_fork, 0));
-    *cs = t_comp_stream;
-    *join = t_comp_join;
+static int check_opts(const pg_launch_opts* o) {
+    if (!o) return PG_OK;
+    if (o->composite_stream && (!o->fork_event || !o->join_event)) {
+        set_error("pg_launch_opts.composite_stream needs a fork and a join event");
+        return PG_ERR_INVALID;
+    }
+    if (o->numerics != PG_NUMERICS_EXACT && o->numerics != PG_NUMERICS_FAST) {
+        set_error("pg_launch_opts.numerics must be PG_NUMERICS_EXACT or PG_NUMERICS_FAST");
+        return PG_ERR_INVALID;
+    }
     return PG_OK;
 }
-static int comp_join(cudaStream_t stream, cudaStream_t cs, cudaEvent_t join) {
-    if (!join) return PG_OK;
-    PG_CUDA_CHECK(cudaEventRecord(join, cs));
-    PG_CUDA_CHECK(cudaStreamWaitEvent(stream, join, 0));
+// The stream compositing runs on; with a composite_stream it first waits for everything enqueued on `stream`.
+static int comp_fork(const pg_launch_opts* o, cudaStream_t stream, cudaStream_t* cs) {
+    *cs = stream;
+    if (!o || !o->composite_stream) return PG_OK;
+    PG_CUDA_CHECK(cudaEventRecord((cudaEvent_t)o->fork_event, stream));
+    PG_CUDA_CHECK(cudaStreamWaitEvent((cudaStream_t)o->composite_stream, (cudaEvent_t)o->fork_event, 0));
+    *cs = (cudaStream_t)o->composite_stream;
+    return PG_OK;
+}
+static int comp_join(const pg_launch_opts* o, cudaStream_t stream) {
+    if (!o || !o->composite_stream) return PG_OK;
+    PG_CUDA_CHECK(cudaEventRecord((cudaEvent_t)o->join_event, (cudaStream_t)o->composite_stream));
+    PG_CUDA_CHECK(cudaStreamWaitEvent(stream, (cudaEvent_t)o->join_event, 0));
     return PG_OK;
 }
 
@@ -147,7 +159,8 @@ static int check_common(const pg_raster_settings* s, const pg_gaussians* g, uint
 
 // everything up to (and including) the tile sort
 static int run_binning(const pg_raster_settings* s, const pg_gaussians* g, const pg_object_table* objs,
-                       int32_t* radii, void* ws, const Layout& L, uint64_t R_cap, bool keep_all, cudaStream_t stream) {
+                       int32_t* radii, void* ws, const Layout& L, uint64_t R_cap, bool keep_all,
+                       const pg_launch_opts* opts, cudaStream_t stream) {
     const int P = g->P;
     const int W = s->image_width, H = s->image_height;
     const uint32_t gx = (W + PG_TILE - 1) / PG_TILE;
@@ -159,11 +172,8 @@ static int run_binning(const pg_raster_settings* s, const pg_gaussians* g, const
     int rc = launch_preprocess(s, g, objs, radii, at<GeomRec>(ws, L.recs), at<ushort4>(ws, L.rect),
                                at<uint32_t>(ws, L.dkey_a), counters, stream);
     if (rc) return rc;
-    if (t_scene_read_event) {  // nothing after this point reads the caller's scene arrays
-        cudaEvent_t ev = t_scene_read_event;
-        t_scene_read_event = nullptr;
-        PG_CUDA_CHECK(cudaEventRecord(ev, stream));
-    }
+    if (opts && opts->scene_read_event)  // nothing after this point reads the caller's scene arrays
+        PG_CUDA_CHECK(cudaEventRecord((cudaEvent_t)opts->scene_read_event, stream));
     prof_mark(2, stream);
     if (s->debug & 1) PG_CUDA_CHECK(cudaStreamSynchronize(stream));
     // depth sort: a -> b -> a -> b -> a
@@ -190,7 +200,8 @@ static int run_binning(const pg_raster_settings* s, const pg_gaussians* g, const
     rc = launch_emit(keep_all, ka, va, at<ushort4>(ws, L.rect), at<GeomRec>(ws, L.recs), (uint32_t)P, gx, W, H,
                      at<uint32_t>(ws, L.tkey_a),
                      at<uint32_t>(ws, L.tval_a), (uint32_t)R_cap, at<uint32_t>(ws, L.status_emit),
-                     n_env, at<uint32_t>(ws, L.tile_obj_count), counters, bits_lo, at<uint32_t>(ws, L.hist_tile), stream);
+                     n_env, at<uint32_t>(ws, L.tile_obj_count), counters, at<Sticky>(ws, L.sticky), bits_lo,
+                     at<uint32_t>(ws, L.hist_tile), stream);
     if (rc) return rc;
     prof_mark(4, stream);
     rc = launch_tile_scan(at<uint32_t>(ws, L.hist_tile), at<uint32_t>(ws, L.bins_tile), counters, stream);
@@ -240,39 +251,57 @@ size_t pg_workspace_bytes(int32_t P, int32_t width, int32_t height, uint64_t pai
     return make_layout(P, width, height, pair_capacity).total;
 }
 
+static int copy_status(const void* ws, pg_status* host, cudaStream_t stream) {
+    const Layout L = make_layout(0, 16, 16, 1);  // the head of the workspace does not depend on the problem size
+    const char* b = reinterpret_cast<const char*>(ws);
+    static_assert(sizeof(pg_status) == 16 + sizeof(Sticky), "pg_status = 4 counter words + Sticky");
+    PG_CUDA_CHECK(cudaMemcpyAsync(host, b + L.counters, 16, cudaMemcpyDeviceToHost, stream));
+    PG_CUDA_CHECK(cudaMemcpyAsync(reinterpret_cast<char*>(host) + 16, b + L.sticky, sizeof(Sticky), cudaMemcpyDeviceToHost, stream));
+    return PG_OK;
+}
+
+int pg_workspace_init(void* ws, size_t ws_bytes, pg_stream_t stream) {
+    if (!ws || ws_bytes < make_layout(0, 16, 16, 1).counters + sizeof(Counters)) { set_error("workspace too small"); return PG_ERR_WORKSPACE; }
+    PG_CUDA_CHECK(cudaMemsetAsync(at<char>(ws, make_layout(0, 16, 16, 1).sticky), 0, sizeof(Sticky), (cudaStream_t)stream));
+    return PG_OK;
+}
+
 int pg_rasterize_forward(const pg_raster_settings* s, const pg_gaussians* g, const pg_raster_outputs* out,
-                         void* ws, size_t ws_bytes, uint64_t pair_capacity, pg_stream_t stream_) {
+                         void* ws, size_t ws_bytes, uint64_t pair_capacity, const pg_launch_opts* opts,
+                         pg_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
-    const bool split = take_comp_request();
     int rc = check_common(s, g, pair_capacity);
     if (rc) return rc;
+    if ((rc = check_opts(opts))) return rc;
     if (!out || !out->color || !out->radii || !out->depth || !ws) { set_error("null output/workspace"); return PG_ERR_INVALID; }
     Layout L = make_layout(g->P, s->image_width, s->image_height, pair_capacity);
     if (ws_bytes < L.total) { set_error("workspace too small: %zu < %zu", ws_bytes, L.total); return PG_ERR_WORKSPACE; }
     // the reference's complete pair lists are kept when asked for (debug bit 2) or needed (n_contrib
     // is a position in the reference's list)
     const bool keep_all = (s->debug & 4) != 0 || out->n_contrib != nullptr;
-    rc = run_binning(s, g, nullptr, out->radii, ws, L, pair_capacity, keep_all, stream);
+    rc = run_binning(s, g, nullptr, out->radii, ws, L, pair_capacity, keep_all, opts, stream);
     if (rc) return rc;
-    cudaStream_t cs; cudaEvent_t join;
-    rc = comp_fork(split, stream, &cs, &join);
+    cudaStream_t cs;
+    rc = comp_fork(opts, stream, &cs);
     if (rc) return rc;
     rc = launch_composite_from_abi(at<uint2>(ws, L.ranges), at<uint32_t>(ws, L.tile_order), sorted_point_list(ws, L), at<GeomRec>(ws, L.recs),
                                    s->image_width, s->image_height, s->bg, out, nullptr, nullptr,
                                    (uint32_t)g->P, at<uint32_t>(ws, L.tile_obj_count),
-                                   (s->debug & 2) ? at<Counters>(ws, L.counters)->stats : nullptr, cs);
-    const int rj = comp_join(stream, cs, join);
+                                   (s->debug & 2) ? at<Counters>(ws, L.counters)->stats : nullptr,
+                                   opts && opts->numerics == PG_NUMERICS_FAST, cs);
+    const int rj = comp_join(opts, stream);
     prof_mark(7, stream);
+    if (!rc && !rj && opts && opts->status_host) return copy_status(ws, opts->status_host, stream);
     return rc ? rc : rj;
 }
 
 int pg_render_composed(const pg_raster_settings* s, const pg_gaussians* g, const pg_object_table* objs,
                        const pg_frame_outputs* out, void* ws, size_t ws_bytes, uint64_t pair_capacity,
-                       pg_stream_t stream_) {
+                       const pg_launch_opts* opts, pg_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
-    const bool split = take_comp_request();
     int rc = check_common(s, g, pair_capacity);
     if (rc) return rc;
+    if ((rc = check_opts(opts))) return rc;
     if (!objs || !out || !out->color || !out->radii || !out->depth || !ws) { set_error("null argument"); return PG_ERR_INVALID; }
     if (objs->num_objects < 0 || objs->num_objects > PG_MAX_OBJECTS || objs->num_colors < 0 || objs->num_colors > PG_MAX_COLORS) {
         set_error("too many objects/colours"); return PG_ERR_INVALID;
@@ -285,42 +314,28 @@ int pg_render_composed(const pg_raster_settings* s, const pg_gaussians* g, const
     }
     Layout L = make_layout(g->P, s->image_width, s->image_height, pair_capacity);
     if (ws_bytes < L.total) { set_error("workspace too small: %zu < %zu", ws_bytes, L.total); return PG_ERR_WORKSPACE; }
-    rc = run_binning(s, g, objs, out->radii, ws, L, pair_capacity, (s->debug & 4) != 0, stream);
+    rc = run_binning(s, g, objs, out->radii, ws, L, pair_capacity, (s->debug & 4) != 0, opts, stream);
     if (rc) return rc;
     const uint32_t n_env = objs->num_objects > 0 ? (uint32_t)objs->first[0] : (uint32_t)g->P;
-    cudaStream_t cs; cudaEvent_t join;
-    rc = comp_fork(split, stream, &cs, &join);
+    cudaStream_t cs;
+    rc = comp_fork(opts, stream, &cs);
     if (rc) return rc;
     if (out->silhouette && objs->num_colors > 0)
         PG_CUDA_CHECK(cudaMemsetAsync(out->silhouette, 0, (size_t)objs->num_colors * s->image_width * s->image_height, cs));
     rc = launch_composite_from_abi(at<uint2>(ws, L.ranges), at<uint32_t>(ws, L.tile_order), sorted_point_list(ws, L), at<GeomRec>(ws, L.recs),
                                    s->image_width, s->image_height, s->bg, nullptr, out, objs, n_env,
                                    at<uint32_t>(ws, L.tile_obj_count),
-                                   (s->debug & 2) ? at<Counters>(ws, L.counters)->stats : nullptr, cs);
-    const int rj = comp_join(stream, cs, join);
+                                   (s->debug & 2) ? at<Counters>(ws, L.counters)->stats : nullptr,
+                                   opts && opts->numerics == PG_NUMERICS_FAST, cs);
+    const int rj = comp_join(opts, stream);
     prof_mark(7, stream);
+    if (!rc && !rj && opts && opts->status_host) return copy_status(ws, opts->status_host, stream);
     return rc ? rc : rj;
-}
-
-int pg_set_scene_read_event(pg_event_t event) {
-    t_scene_read_event = (cudaEvent_t)event;
-    return PG_OK;
-}
-
-int pg_set_composite_stream(pg_stream_t composite_stream, pg_event_t fork_event, pg_event_t join_event) {
-    if (!composite_stream) { t_comp_split = false; return PG_OK; }
-    if (!fork_event || !join_event) { set_error("pg_set_composite_stream needs a fork and a join event"); return PG_ERR_INVALID; }
-    t_comp_stream = (cudaStream_t)composite_stream;
-    t_comp_fork = (cudaEvent_t)fork_event;
-    t_comp_join = (cudaEvent_t)join_event;
-    t_comp_split = true;
-    return PG_OK;
 }
 
 int pg_read_status(const void* ws, pg_status* host_status, pg_stream_t stream) {
     if (!ws || !host_status) { set_error("null argument"); return PG_ERR_INVALID; }
-    PG_CUDA_CHECK(cudaMemcpyAsync(host_status, ws, sizeof(pg_status), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
-    return PG_OK;
+    return copy_status(ws, host_status, (cudaStream_t)stream);
 }
 
 int pg_mark_visible(int32_t P, const float* means3D, const float* viewmatrix, uint8_t* present, pg_stream_t stream) {
@@ -350,7 +365,7 @@ int pg_export_binning(const void* ws, int32_t P, int32_t width, int32_t height, 
 
 int pg_read_stats(const void* ws, uint64_t* host_stats8, pg_stream_t stream) {
     if (!ws || !host_stats8) { set_error("null argument"); return PG_ERR_INVALID; }
-    const char* src = reinterpret_cast<const char*>(ws) + offsetof(Counters, stats);
+    const char* src = reinterpret_cast<const char*>(ws) + make_layout(0, 16, 16, 1).counters + offsetof(Counters, stats);
     PG_CUDA_CHECK(cudaMemcpyAsync(host_stats8, src, 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     return PG_OK;
 }

@@ -94,6 +94,13 @@ struct Counters {
     unsigned long long rendered_full;  // sum of all tile-rectangle areas = the reference's num_rendered
 };
 
+// Sticky status behind the Counters (never cleared by a forward; pg_workspace_init clears it): pg_status is
+// {Counters' first four words, Sticky}.
+struct Sticky {
+    uint32_t overflow_frames;   // forwards whose stored pairs exceeded the pair capacity
+    uint32_t max_pairs_needed;  // largest stored-pair demand seen
+};
+
 // Onesweep tile geometry
 constexpr int SORT_THREADS = 256;
 #ifndef PG_SORT_IPT
@@ -109,6 +116,7 @@ constexpr int EMIT_CHUNK = PG_EMIT_CHUNK;  // Gaussians per emit CTA (2 per thre
 
 struct Layout {
     // all offsets in bytes from the workspace base; every region 256-B aligned
+    size_t sticky;       // Sticky (first, so that it lies outside the cleared range)
     size_t counters;     // Counters
     size_t zero_begin;   // [zero_begin, zero_end) is cleared at the start of every forward
     size_t hist_depth;   // u32[4][256]  depth-sort digit histograms -> exclusive bases
@@ -142,6 +150,7 @@ inline Layout make_layout(int P, int W, int H, uint64_t R_cap) {
     L.chunks = (uint32_t)((P + EMIT_CHUNK - 1) / EMIT_CHUNK);
     if (L.chunks == 0) L.chunks = 1;
     size_t o = 0;
+    L.sticky = o; o = align_up(o + sizeof(Sticky));
     L.counters = o; o = align_up(o + sizeof(Counters));
     L.zero_begin = L.counters;
     L.hist_depth = o; o = align_up(o + 4 * RADIX * 4);
@@ -177,6 +186,29 @@ inline int tile_bits(uint32_t tiles) {
 
 void set_error(const char* fmt, ...);
 void count_launch(int n);
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute of a kernel: what has been granted is
+// remembered per (kernel, device) — keyed by the function's address, because kernels with the same signature
+// share one instantiation of this template — behind a mutex, so several host threads / devices are fine.
+int smem_granted(const void* kernel, int device, int bytes, bool record);
+#if defined(__CUDACC__)
+template <typename Kernel>
+inline cudaError_t ensure_dynamic_smem(Kernel kernel, int bytes, bool max_carveout = false) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const void* key = reinterpret_cast<const void*>(kernel);
+    if (smem_granted(key, dev, bytes, false) >= bytes) return cudaSuccess;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) return e;
+    if (max_carveout) {
+        e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        if (e != cudaSuccess) return e;
+    }
+    smem_granted(key, dev, bytes, true);
+    return cudaSuccess;
+}
+#endif
 
 }  // namespace pg
 

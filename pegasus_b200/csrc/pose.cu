@@ -164,11 +164,7 @@ int launch_pose(int K, const int32_t* first, const PoseDev* poses_dev, const pg_
     a.scene_offset = scene_offset;
     a.means = scene->means3D; a.rots = scene->rotations; a.shs = scene->shs;
     const int smem = 256 * 45 * 4 + 512 + 16;
-    static bool attr_set = false;
-    if (!attr_set) {
-        PG_CUDA_CHECK(cudaFuncSetAttribute(pose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_set = true;
-    }
+    PG_CUDA_CHECK(ensure_dynamic_smem(pose_kernel, smem));
     dim3 grid((n_max + 255) / 256, K);
     pose_kernel<<<grid, 256, smem, stream>>>(a);
     count_launch(1);

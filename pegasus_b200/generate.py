@@ -71,7 +71,7 @@ class DatasetGenerator:
 
     def __init__(self, scene: ComposedScene, width: int, height: int, bg: Optional[torch.Tensor] = None,
                  frames_in_flight: int = 3, host_sets: Optional[int] = None, writer_threads: int = 4,
-                 overlap_compositing: bool = True):
+                 overlap_compositing: bool = True, numerics=None):
         self.scene = scene
         self.dev = scene.device
         self.W, self.H = int(width), int(height)
@@ -80,9 +80,10 @@ class DatasetGenerator:
         self.nc = int(scene.color_set.shape[0])
         self.K = len(scene.object_ids)
         self.writer_threads = max(1, int(writer_threads))
+        self.numerics = numerics  # None: process default (pegasus_b200.set_numerics / PG_NUMERICS)
         dev, W, H, nc = self.dev, self.W, self.H, self.nc
         # Each slot owns a HIGH-priority stream (pose, per-Gaussian stage, sorts, packing, copies) and a
-        # normal-priority one for the compositing kernel (pg_set_composite_stream): the latency-bound
+        # normal-priority one for the compositing kernel (pg_launch_opts.composite_stream): the latency-bound
         # stages of frame i+1 take the SM slots frame i's compositing CTAs free and co-run with them.
         self.overlap = bool(overlap_compositing) and self.nslot > 1
         self.streams = [torch.cuda.Stream(device=dev, priority=-1 if self.overlap else 0) for _ in range(self.nslot)]
@@ -107,12 +108,15 @@ class DatasetGenerator:
                                 depth=torch.empty((H, W), dtype=torch.int16).pin_memory(),
                                 sem_seg=torch.empty((H, W, 3), dtype=torch.uint8).pin_memory(),
                                 visible=torch.empty((nc, H, self.Wb), dtype=torch.uint8).pin_memory(),
-                                silhouette=torch.empty((nc, H, self.Wb), dtype=torch.uint8).pin_memory()))
+                                silhouette=torch.empty((nc, H, self.Wb), dtype=torch.uint8).pin_memory(),
+                                # the frame's pg_status, copied by the library at the end of the frame
+                                status=torch.zeros(_lib.STATUS_WORDS, dtype=torch.int32).pin_memory()))
         self.h2d_bytes_per_frame = 35 * 4
         # u8 RGB + u16 depth + u8 sem-seg per pixel, the 2 x nc masks as ONE BIT per pixel: they are most of the
         # planes of a frame, and with 8 GPUs per host the D2H stream is what the host side saturates first
         self.d2h_bytes_per_frame = W * H * (3 + 2 + 3) + 2 * nc * H * self.Wb
         self.pair_capacity: Optional[int] = None
+        self._overflow_seen: Dict[int, int] = {}  # slot -> sticky overflow_frames already reported
 
     # ------------------------------------------------------------------ capacity
     def calibrate(self, cams: Sequence, pose_packets: Optional[torch.Tensor] = None, margin: float = 1.05) -> int:
@@ -123,13 +127,13 @@ class DatasetGenerator:
         for i, cam in enumerate(cams):
             if pose_packets is not None and self.K:
                 sc.apply_pose_packets(pose_packets[i % pose_packets.shape[0]])
-            o = sc.render(cam, self.bg, masks=True, out=self.outs[0], sync_check=True)
+            o = sc.render(cam, self.bg, masks=True, out=self.outs[0], sync_check=True, numerics=self.numerics)
             max_R = max(max_R, o["num_stored"])
         self.pair_capacity = int(max_R * margin) + 4096
         for sl in range(self.nslot):
             with torch.cuda.stream(self.streams[sl]):
                 sc.render(cams[0], self.bg, masks=True, out=self.outs[sl], sync_check=True,
-                          pair_capacity=self.pair_capacity, slot=sl)
+                          pair_capacity=self.pair_capacity, slot=sl, numerics=self.numerics)
         torch.cuda.synchronize(self.dev)
         return self.pair_capacity
 
@@ -150,7 +154,8 @@ class DatasetGenerator:
                 sc.apply_pose_packets(self.pose_dev[sl])
             o = self.outs[sl]
             sc.render(cs, self.bg, masks=True, out=o, sync_check=False, pair_capacity=self.pair_capacity, slot=sl,
-                      scene_read_event=self.read_ev[sl] if dynamic else None, composite_stream=self.comp_streams[sl])
+                      scene_read_event=self.read_ev[sl] if dynamic else None, composite_stream=self.comp_streams[sl],
+                      numerics=self.numerics, status_host=host["status"])
             _lib.check(L.pg_pack_frame(self.W, self.H, C.c_void_p(o["color"].data_ptr()),
                                        C.c_void_p(o["depth"].data_ptr()), C.c_void_p(self.packs[sl]["rgb"].data_ptr()),
                                        C.c_void_p(self.packs[sl]["depth"].data_ptr()), C.c_void_p(st.cuda_stream)),
@@ -223,6 +228,8 @@ class DatasetGenerator:
         inflight: List[Optional[tuple]] = [None] * self.nslot
         futures = []
         stats = dict(frames=0, overflow=0)
+        # sticky overflow counters of the slots' workspaces before this call (calibration may have overflowed on purpose)
+        self._overflow_seen = {sl: sc.read_status(slot=sl)["overflow_frames"] for sl in range(self.nslot)}
 
         def retire(sl):
             job = inflight[sl]
@@ -231,6 +238,13 @@ class DatasetGenerator:
             f, cam, host, pose_row = job
             self.done_ev[sl].synchronize()
             inflight[sl] = None
+            if int(host["status"][1]):
+                # the frame's deepest pairs were dropped: its products are invalid and must not reach the writer
+                need = int(host["status"][5]) & 0xFFFFFFFF
+                self._free.put(host)
+                raise RuntimeError(f"frame {f}: the stored (tile, Gaussian) pairs exceeded the pair capacity "
+                                   f"{self.pair_capacity} (needed {need}); calibrate() over the views rendered or raise "
+                                   "`margin`")
             stats["frames"] += 1
             W_ = self.W
 
@@ -281,8 +295,11 @@ class DatasetGenerator:
             fu.result()
         if pool is not None:
             pool.shutdown()
+        # belt and braces: the sticky counter of every slot's workspace covers all its frames since the last look
         for sl in range(self.nslot):
-            if sc.read_status(slot=sl)["overflow"]:
+            ov = sc.read_status(slot=sl)["overflow_frames"]
+            if ov != self._overflow_seen.get(sl, 0):
+                self._overflow_seen[sl] = ov
                 stats["overflow"] += 1
         if stats["overflow"]:
             raise RuntimeError("pair capacity overflowed while generating; call calibrate() over the views rendered "

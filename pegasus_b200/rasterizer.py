@@ -40,7 +40,7 @@ class _Workspace:
         self.buf: Optional[torch.Tensor] = None
         self.capacity = 0  # pair capacity the layout was sized for
         self.key = None
-        self.status_host = torch.zeros(4, dtype=torch.int32).pin_memory()
+        self.status_host = torch.zeros(_lib.STATUS_WORDS, dtype=torch.int32).pin_memory()
 
     def ensure(self, device, P, W, H, capacity):
         L = _lib.load()
@@ -50,9 +50,26 @@ class _Workspace:
         if self.buf is None or self.buf.device != device or self.buf.numel() < need:
             self.buf = None
             self.buf = torch.empty(need, dtype=torch.uint8, device=device)
+            with torch.cuda.device(device):
+                stream = torch.cuda.current_stream(device)
+                _lib.check(L.pg_workspace_init(C.c_void_p(self.buf.data_ptr()), self.buf.numel(),
+                                               C.c_void_p(stream.cuda_stream)), "pg_workspace_init")
         self.capacity = capacity
         self.key = (P, W, H, capacity)
         return self.buf
+
+    def status(self) -> dict:
+        """The status words last copied into status_host (pg_read_status / pg_launch_opts.status_host)."""
+        h = self.status_host
+        return dict(num_rendered=int(h[0]) & 0xFFFFFFFF, overflow=int(h[1]), num_visible=int(h[2]),
+                    num_stored=int(h[3]) & 0xFFFFFFFF, overflow_frames=int(h[4]) & 0xFFFFFFFF,
+                    max_pairs_needed=int(h[5]) & 0xFFFFFFFF)
+
+
+def grown_capacity(cap: int, st: dict) -> int:
+    """Pair capacity after an overflow: the demand the library measured plus 1/8, at least double."""
+    need = st["max_pairs_needed"]
+    return int(min(max(need + need // 8 + 4096, min(2 * cap, 1 << 30), 1 << 20), 1 << 30))
 
 
 _WORKSPACES = {}
@@ -113,7 +130,7 @@ def make_settings_struct(rs: GaussianRasterizationSettings, device, keep: list) 
 
 def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
                         raster_settings: GaussianRasterizationSettings, want_aux: bool = False,
-                        sync_check: bool = True, reference_lists: bool = False):
+                        sync_check: bool = True, reference_lists: bool = False, numerics=None):
     """Forward rasterization through the C ABI.  Returns (color, radii, depth, aux).
 
     reference_lists=True keeps the reference's complete (tile, Gaussian) pair lists (debug bit 2 of the
@@ -165,26 +182,25 @@ def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales,
         ws = workspace_for(device)
         stream = torch.cuda.current_stream(device)
         cap = default_pair_capacity(P, W, H)
+        opts = _lib.LaunchOpts()
+        opts.numerics = _lib.numerics_code(numerics)
+        if sync_check:
+            opts.status_host = ws.status_host.data_ptr()
         while True:
             buf = ws.ensure(device, P, W, H, cap)
             rc = L.pg_rasterize_forward(C.byref(s), C.byref(g), C.byref(out), C.c_void_p(buf.data_ptr()),
-                                        buf.numel(), cap, C.c_void_p(stream.cuda_stream))
+                                        buf.numel(), cap, C.byref(opts), C.c_void_p(stream.cuda_stream))
             _lib.check(rc, "pg_rasterize_forward")
             if not sync_check:
                 break
-            _lib.check(L.pg_read_status(C.c_void_p(buf.data_ptr()), C.c_void_p(ws.status_host.data_ptr()),
-                                        C.c_void_p(stream.cuda_stream)), "pg_read_status")
             stream.synchronize()
-            R, overflow = int(ws.status_host[0]) & 0xFFFFFFFF, int(ws.status_host[1])
-            aux["num_rendered"] = R
-            aux["num_visible"] = int(ws.status_host[2])
-            aux["num_stored"] = int(ws.status_host[3]) & 0xFFFFFFFF
-            if not overflow:
+            st = ws.status()
+            aux["num_rendered"], aux["num_visible"], aux["num_stored"] = st["num_rendered"], st["num_visible"], st["num_stored"]
+            if not st["overflow"]:
                 break
             if cap >= (1 << 30):
                 raise RuntimeError("the (tile, Gaussian) pairs exceed the supported maximum of 2^30")
-            # the stored count is not known after an overflow (R bounds it from above): grow geometrically
-            cap = int(min(max(2 * cap, 1 << 20), max(R + R // 8, 1 << 20), 1 << 30)) if R > cap else int(min(2 * cap, 1 << 30))
+            cap = grown_capacity(cap, st)
             _PAIR_CAPACITY_HINT[(W, H)] = cap
         aux["pair_capacity"] = cap
         return color, radii, depth, aux
@@ -193,6 +209,7 @@ def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales,
 class GaussianRasterizer(nn.Module):
     sync_check = True  # read back R after each call and transparently grow the workspace on overflow
     reference_lists = False  # True: keep the reference's complete pair lists (aux["n_contrib"], export_binning)
+    numerics = None  # None: the process default (pegasus_b200.set_numerics / PG_NUMERICS), else "exact" | "fast"
 
     def __init__(self, raster_settings: GaussianRasterizationSettings):
         super().__init__()
@@ -224,6 +241,6 @@ class GaussianRasterizer(nn.Module):
             color, radii, depth, aux = rasterize_gaussians(
                 means3D, means2D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp,
                 self.raster_settings, want_aux=True, sync_check=self.sync_check,
-                reference_lists=self.reference_lists)
+                reference_lists=self.reference_lists, numerics=self.numerics)
         self.aux = aux
         return color, radii, depth

@@ -22,7 +22,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .rasterizer import (GaussianRasterizationSettings, default_pair_capacity, make_settings_struct,
+from .rasterizer import (GaussianRasterizationSettings, default_pair_capacity, grown_capacity, make_settings_struct,
                          workspace_for, _PAIR_CAPACITY_HINT)
 from .sh_rotation import POSE_WORDS, pose_packet
 
@@ -174,7 +174,8 @@ class ComposedScene:
                sync_check: bool = True, pair_capacity: Optional[int] = None, debug: int = 0,
                reference_lists: bool = False, slot: int = 0,
                scene_read_event: Optional[torch.cuda.Event] = None,
-               composite_stream: Optional[torch.cuda.Stream] = None) -> Dict[str, torch.Tensor]:
+               composite_stream: Optional[torch.cuda.Stream] = None, numerics=None,
+               status_host: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
         """One frame: RGB + depth (+ seg render, sem-seg, visible and silhouette masks when
         masks=True) — everything the reference's K+3 passes produce (src/gs/render.py:14-129).
 
@@ -182,9 +183,12 @@ class ComposedScene:
         flight concurrently on different streams need distinct slots (and distinct `out` buffers).
         `scene_read_event` is recorded right after the per-Gaussian stage, the last reader of the scene
         arrays: the next frame's apply_pose_packets (on another stream) only has to wait for it.
-        `composite_stream`: the compositing kernel runs there (pg_set_composite_stream), forked from and
+        `composite_stream`: the compositing kernel runs there (pg_launch_opts.composite_stream), forked from and
         joined back into the current stream; give the current stream the higher priority and the
-        following frame's per-Gaussian / sort stages co-run with this frame's compositing."""
+        following frame's per-Gaussian / sort stages co-run with this frame's compositing.
+        `numerics`: "exact" | "fast" | None (process default).  `status_host`: pinned int32[6]; the frame's status
+        block (overflow flag, pair counts) is copied there at the end of the frame, for callers that do not
+        synchronise here (sync_check=False)."""
         L = _lib.load()
         H, W = int(cam.image_height), int(cam.image_width)
         if out is None:
@@ -210,34 +214,35 @@ class ComposedScene:
                 table = _lib.ObjectTable()
                 table.num_objects = 0
                 table.num_colors = 0
+            opts = _lib.LaunchOpts()
+            opts.numerics = _lib.numerics_code(numerics)
+            if scene_read_event is not None:
+                scene_read_event.record(stream)  # creates the lazily-initialised handle; re-recorded by the library
+                opts.scene_read_event = scene_read_event.cuda_event
+            if composite_stream is not None:
+                fork, join = _split_events(self.device, slot, stream)
+                opts.composite_stream = composite_stream.cuda_stream
+                opts.fork_event, opts.join_event = fork.cuda_event, join.cuda_event
+            if sync_check:
+                opts.status_host = ws.status_host.data_ptr()
+            elif status_host is not None:
+                opts.status_host = status_host.data_ptr()
             while True:
                 buf = ws.ensure(self.device, self.P, W, H, cap)
-                if scene_read_event is not None:
-                    scene_read_event.record(stream)  # creates the lazily-initialised handle; re-recorded by the library
-                    _lib.check(L.pg_set_scene_read_event(C.c_void_p(scene_read_event.cuda_event)), "pg_set_scene_read_event")
-                if composite_stream is not None:
-                    fork, join = _split_events(self.device, slot, stream)
-                    _lib.check(L.pg_set_composite_stream(C.c_void_p(composite_stream.cuda_stream),
-                                                         C.c_void_p(fork.cuda_event), C.c_void_p(join.cuda_event)),
-                               "pg_set_composite_stream")
                 rc = L.pg_render_composed(C.byref(s), C.byref(g), C.byref(table), C.byref(fo),
-                                          C.c_void_p(buf.data_ptr()), buf.numel(), cap,
+                                          C.c_void_p(buf.data_ptr()), buf.numel(), cap, C.byref(opts),
                                           C.c_void_p(stream.cuda_stream))
                 _lib.check(rc, "pg_render_composed")
                 if not sync_check:
                     break
-                _lib.check(L.pg_read_status(C.c_void_p(buf.data_ptr()), C.c_void_p(ws.status_host.data_ptr()),
-                                            C.c_void_p(stream.cuda_stream)), "pg_read_status")
                 stream.synchronize()
-                R, overflow = int(ws.status_host[0]) & 0xFFFFFFFF, int(ws.status_host[1])
-                out["num_rendered"] = R
-                out["num_visible"] = int(ws.status_host[2])
-                out["num_stored"] = int(ws.status_host[3]) & 0xFFFFFFFF
-                if not overflow:
+                st = ws.status()
+                out["num_rendered"], out["num_visible"], out["num_stored"] = st["num_rendered"], st["num_visible"], st["num_stored"]
+                if not st["overflow"]:
                     break
                 if cap >= (1 << 30):
                     raise RuntimeError("the (tile, Gaussian) pairs exceed the supported maximum of 2^30")
-                cap = int(min(max(2 * cap, 1 << 20), max(R + R // 8, 1 << 20), 1 << 30)) if R > cap else int(min(2 * cap, 1 << 30))
+                cap = grown_capacity(cap, st)
                 _PAIR_CAPACITY_HINT[(W, H)] = cap
             out["pair_capacity"] = cap
         return out
@@ -256,15 +261,15 @@ class ComposedScene:
                     hits_obj_after=int(host[6]), cull_passes_after=int(host[7]))
 
     def read_status(self, slot: int = 0) -> Dict[str, int]:
-        """Status of the last (possibly still running) render on this device; synchronises."""
+        """Status of the last (possibly still running) render on this device, including the sticky fields
+        (overflow_frames, max_pairs_needed) accumulated since the workspace was created; synchronises."""
         L = _lib.load()
         ws = workspace_for(self.device, slot)
         stream = torch.cuda.current_stream(self.device)
         _lib.check(L.pg_read_status(C.c_void_p(ws.buf.data_ptr()), C.c_void_p(ws.status_host.data_ptr()),
                                     C.c_void_p(stream.cuda_stream)), "pg_read_status")
         stream.synchronize()
-        return dict(num_rendered=int(ws.status_host[0]) & 0xFFFFFFFF, overflow=int(ws.status_host[1]),
-                    num_visible=int(ws.status_host[2]), num_stored=int(ws.status_host[3]) & 0xFFFFFFFF)
+        return ws.status()
 
 
 _SPLIT_EVENTS: Dict = {}

@@ -34,7 +34,7 @@ def test_ctypes_structs_match_the_header(tmp_path):
     structs = {"pg_raster_settings": _lib.RasterSettings, "pg_gaussians": _lib.Gaussians,
                "pg_raster_outputs": _lib.RasterOutputs, "pg_object_table": _lib.ObjectTable,
                "pg_frame_outputs": _lib.FrameOutputs, "pg_pose": _lib.Pose, "pg_canonical": _lib.Canonical,
-               "pg_scene": _lib.Scene, "pg_status": _lib.Status}
+               "pg_scene": _lib.Scene, "pg_status": _lib.Status, "pg_launch_opts": _lib.LaunchOpts}
     prog = "#include <stdio.h>\n#include \"pegasus_b200.h\"\nint main(void){\n"
     for n in structs:
         prog += f'printf("{n} %zu\\n", sizeof({n}));\n'
@@ -55,13 +55,34 @@ def test_argument_errors_do_not_need_a_gpu():
     L = _lib.load()
     assert L.pg_workspace_bytes(-1, 640, 480, 1 << 20) == 0
     assert L.pg_workspace_bytes(1000, 640, 480, 1 << 20) > 0
-    rc = L.pg_rasterize_forward(None, None, None, None, 0, 0, None)
+    rc = L.pg_rasterize_forward(None, None, None, None, 0, 0, None, None)
     assert rc == -1 and b"null" in L.pg_last_error()
     with pytest.raises(RuntimeError):
         _lib.check(rc, "pg_rasterize_forward")
-    # pg_set_composite_stream: a stream needs both events; a null stream clears the request
-    assert L.pg_set_composite_stream(C.c_void_p(1), None, None) == -1 and b"fork" in L.pg_last_error()
-    assert L.pg_set_composite_stream(None, None, None) == 0
+    assert L.pg_workspace_init(None, 0, None) == -3
+    assert C.sizeof(_lib.Status) == 24 and _lib.STATUS_WORDS == 6
+
+
+def test_launch_opts_are_validated_before_any_cuda_call():
+    """pg_launch_opts is plain per-call data (no thread-local side channel): a composite stream needs both
+    events, numerics must be a known mode.  Argument checks come first, so no GPU is needed."""
+    L = _lib.load()
+    s, g, out = _lib.RasterSettings(), _lib.Gaussians(), _lib.RasterOutputs()
+    s.image_width, s.image_height, s.sh_degree = 64, 64, 3
+    g.P, g.sh_coeffs = 0, 16
+    g.shs, g.scales, g.rotations = 1, 1, 1  # non-null dummies: never dereferenced by the argument checks
+    out.color = out.radii = out.depth = 1
+    opts = _lib.LaunchOpts()
+    opts.composite_stream = 1
+    rc = L.pg_rasterize_forward(C.byref(s), C.byref(g), C.byref(out), C.c_void_p(1), 0, 1 << 20, C.byref(opts), None)
+    assert rc == -1 and b"fork" in L.pg_last_error()
+    opts = _lib.LaunchOpts()
+    opts.numerics = 7
+    rc = L.pg_rasterize_forward(C.byref(s), C.byref(g), C.byref(out), C.c_void_p(1), 0, 1 << 20, C.byref(opts), None)
+    assert rc == -1 and b"numerics" in L.pg_last_error()
+    opts.numerics = _lib.NUMERICS_FAST
+    rc = L.pg_rasterize_forward(C.byref(s), C.byref(g), C.byref(out), C.c_void_p(1), 0, 1 << 20, C.byref(opts), None)
+    assert rc == -3 and b"workspace too small" in L.pg_last_error()  # got past the option checks
 
 
 def test_product_never_imports_the_oracle():

@@ -420,7 +420,7 @@ def test_render_helpers_return_reference_shapes():
 def test_pipelined_frames_on_three_streams_match_sequential(split):
     """Several frames in flight (one stream + workspace slot + output set each), a new pose every frame:
     the pose kernel of frame i+1 waits only for frame i's scene-read event.  With `split` every slot's
-    compositing kernel runs on its own lower-priority stream (pg_set_composite_stream), forked from and
+    compositing kernel runs on its own lower-priority stream (pg_launch_opts.composite_stream), forked from and
     joined back into the slot's stream.  Products must equal the one-frame-at-a-time results bit for bit."""
     from pegasus_b200 import ComposedScene, Camera, synth
     env, objs = util.small_scene(n_env=30000, n_obj=(5000, 4000), seed=71)
