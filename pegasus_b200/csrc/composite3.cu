@@ -1,21 +1,26 @@
-// composite3.cu — the default compositing kernel (SURVEY Appendix A.7 + the fused K+3 passes): same CTA shape as
-// composite2_kernel (composite.cu: one CTA per 16x16 tile, a producer warp staging the sorted list into a
-// shared-memory ring, 4 consumer warps of 8x8 pixels, two pixels per lane in packed FP32), with a leaner hit loop.
+// composite3.cu — the default compositing kernel (SURVEY Appendix A.7 + the fused K+3 passes).  Same CTA shape as
+// composite2_kernel (composite.cu): one CTA per 16x16 tile, a producer warp staging the tile's sorted list into a
+// shared-memory ring (TMA bulk copies of the id list, cp.async gathers of the 48-byte records), 4 consumer warps of
+// 8x8 pixels, two pixels per lane in packed FP32.  What differs is how a consumer warp spends its instructions.
 //
-// What the hit loop of composite2_kernel spent per pair of hits (ncu, round 1): 68 packed FP32 instructions and ~60
-// predicate / select / min / integer ones; both the FMA and the ALU pipe ran at 50 % with 4 consumer warps per
-// scheduler.  Here:
-//   * termination is tested once per PAIR of hits: T only decreases, so if T after both hits is still >= 1e-4 at every
-//     pixel of the warp (one min, one compare, one vote) neither hit terminated any chain and both are blended without
-//     per-hit compares / selects; otherwise the pair is redone hit by hit (at most once per pixel of the warp);
-//   * a finished main chain is a predicate folded into the validity test (alpha = 0 makes every update an exact
-//     no-op) instead of a sign trick that costs two selects per chain and hit;
-//   * records whose opacity is <= 0.99 (flagged by preprocess, PG_REC_GENERAL clear) skip min(0.99, .): exp(power) <= 1
-//     for power <= 0, so the minimum cannot bind;
-//   * hits of object Gaussians, flagged records and pairs in which a chain terminates take the general path, which
-//     is composite2_kernel's arithmetic hit by hit.
+// Measured on composite2_kernel (round 2, C2 workload, debug-bit-1 counters): 7.3 M warp-hits per frame, of which
+// 4.9 M are environment entries, 0.8 M object entries met while a main (RGB) chain is alive and 1.6 M object entries
+// met AFTER every main chain of the warp has terminated (the objects-only chains of the fused mask passes keep
+// walking).  That last phase found 1.6 hits per 32-entry cull pass, so most pairs of hits ran half empty, each pass
+// paid its 65-instruction cull, and every hit dragged the dead main chain along: 22 % of the hits cost 44 % of the
+// kernel's instructions.  Here, per staged batch of up to 128 entries:
+//   1. CULL: all four 32-entry chunks are tested lane-parallel against the warp's pixel block back to back (the
+//      four tests interleave) and the hits are appended to a per-warp queue in shared memory, so hits pair up across
+//      chunk boundaries (one half-empty pair per batch at most);
+//   2. WALK: one of two loops, chosen once per batch: the MAIN loop (RGB + depth chain, object chains on object hits)
+//      while a main chain of the warp is alive, else the OBJECT loop, which evaluates alpha and updates only the
+//      objects-only chains (no colour record, no main-chain arithmetic).
+// A finished main chain is a per-pixel threshold folded into the validity test (alpha := 0 makes every update an
+// exact no-op); records whose opacity is <= 0.99 skip min(0.99, .), which cannot bind for them (PG_REC_GENERAL).
+// A silhouette chain is also finished as soon as its mask bit is decided: the bit is ||c_k (1 - T_k) + T_k bg - c_k||
+// <= 0.1, T_k only decreases, so once T_k is below 0.0999 / ||c_k - bg|| the bit is 1 whatever follows.
 // Every float operation of the default (exact) instantiation is the same individually rounded operation in the same
-// order as before, so images, final_T and n_contrib stay bit-identical to the CPU oracle.
+// order as in composite2_kernel, so images, final_T and n_contrib stay bit-identical to the CPU oracle.
 //
 // FAST instantiation (pg_launch_opts.numerics = PG_NUMERICS_FAST): exp through MUFU ex2.approx and the blend weight
 // alpha * T formed once per hit (C += c * (alpha * T) instead of (c * alpha) * T).  Not bit-reproducible on a CPU;
@@ -68,13 +73,21 @@ __device__ __forceinline__ bool block_culled_fast(float gx, float gy, float qa, 
     return pd && (qmin * 0.9999f - 1e-3f > -cut);
 }
 
-template <bool MASKS, bool NCONTRIB, bool FAST, int COMP_STAGES, int MINB, bool BRANCHY>
+
+constexpr int QSTRIDE = COMP_BATCH + 16;  // bytes of one warp's hit queue (entry indices; 0xFF = no second hit)
+
+// Dynamic shared memory: CompSmem | hit queues [COMP2_CW][QSTRIDE] | (MASKS) eff[PG_MAX_OBJECTS] float4 {colour the
+// rasterizer produces for object k's flat SH, silhouette decision threshold} | Tk2[K][128] float2 — the standalone
+// transmittance of object k at the two pixels of each lane (slot = warp * 32 + lane).
+template <bool MASKS, bool NCONTRIB, bool FAST, int COMP_STAGES, int MINB>
 __global__ void __launch_bounds__(COMP2_THREADS, MINB) composite3_kernel(const CompArgs a) {
     using CompSmem = CompSmemT<COMP_STAGES>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     CompSmem& sm = *reinterpret_cast<CompSmem*>(smem_raw);
-    float4* sm_eff = reinterpret_cast<float4*>(smem_raw + sizeof(CompSmem));
-    float2* sm_tk = reinterpret_cast<float2*>(smem_raw + sizeof(CompSmem) + PG_MAX_OBJECTS * sizeof(float4));
+    constexpr int kQueueOff = (int)((sizeof(CompSmem) + 15) / 16 * 16);
+    constexpr int kEffOff = kQueueOff + COMP2_CW * QSTRIDE;
+    float4* sm_eff = reinterpret_cast<float4*>(smem_raw + kEffOff);
+    float2* sm_tk = reinterpret_cast<float2*>(smem_raw + kEffOff + PG_MAX_OBJECTS * sizeof(float4));
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int tile = (int)a.tile_order[blockIdx.x];
@@ -97,8 +110,16 @@ __global__ void __launch_bounds__(COMP2_THREADS, MINB) composite3_kernel(const C
         sm.dummy.c = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (MASKS && tid < a.num_objects)
-        sm_eff[tid] = make_float4(a.eff_color[tid][0], a.eff_color[tid][1], a.eff_color[tid][2], 0.0f);
+    if (MASKS && tid < a.num_objects) {
+        // silhouette of object k: || c_k (1 - T_k) + T_k bg - c_k || = T_k || bg - c_k || <= 0.1 (src/gs/render.py:60-63);
+        // below thr_k = max(1e-4, 0.0999 / || bg - c_k ||) the bit is decided (the 1e-3 margin dwarfs the rounding of
+        // the final test and the 1-ulp gap between the colour set and the rasterized flat colour)
+        const float e0 = a.eff_color[tid][0], e1 = a.eff_color[tid][1], e2 = a.eff_color[tid][2];
+        const float d0 = a.bg[0] - e0, d1 = a.bg[1] - e1, d2 = a.bg[2] - e2;
+        const float nrm = sqrtf(d0 * d0 + d1 * d1 + d2 * d2);
+        const float tau = nrm > 0.0999f ? 0.0999f / nrm : 2.0f;  // 2: decided from the start (T_k <= 1)
+        sm_eff[tid] = make_float4(e0, e1, e2, fmaxf(0.0001f, tau));
+    }
     __syncthreads();
 
     if (warp == COMP2_CW) {
@@ -118,19 +139,96 @@ __global__ void __launch_bounds__(COMP2_THREADS, MINB) composite3_kernel(const C
     const int K = MASKS ? a.num_objects : 0;
     const uint32_t all_k = K >= 32 ? 0xFFFFFFFFu : ((1u << K) - 1u);
     float2* my_tk = sm_tk + (warp * 32 + lane);  // object k's silhouette chains at my_tk[k * 128]
-    if (MASKS)
-        for (int k = 0; k < K; ++k) my_tk[k * 128] = make_float2(in0 ? 1.0f : -1.0f, in1 ? 1.0f : -1.0f);
+    uint8_t* const queue = smem_raw + kQueueOff + warp * QSTRIDE;
 
-    // Main chain: T stays the transmittance (frozen once the chain has terminated); thr0 / thr1 say whether it is alive.
-    // Object chains (To, Tk) keep composite2_kernel's convention: a finished chain holds -|T|.
+    // Main chain: T stays the transmittance (frozen once the chain has terminated); thr0 / thr1 say whether it is alive
+    // (1/255: alive, +inf: finished — see valid_alpha).  Object chains (To, Tk): a finished chain holds -|T|.
     f32x2 T = bc2(1.0f);
-    float thr0 = in0 ? THR_ALIVE : THR_DEAD, thr1 = in1 ? THR_ALIVE : THR_DEAD;  // main chain alive <=> thr == 1/255
+    float thr0 = in0 ? THR_ALIVE : THR_DEAD, thr1 = in1 ? THR_ALIVE : THR_DEAD;
     f32x2 To = pk2((in0 && MASKS) ? 1.0f : -1.0f, (in1 && MASKS) ? 1.0f : -1.0f);
     f32x2 C0 = bc2(0.0f), C1 = C0, C2 = C0, D = C0, S0 = C0, S1 = C0, S2 = C0;
     uint32_t dk0 = (in0 && MASKS) ? 0u : 0xFFFFFFFFu, dk1 = (in1 && MASKS) ? 0u : 0xFFFFFFFFu;
+    if (MASKS)
+        for (int k = 0; k < K; ++k) {
+            // a chain whose bit is decided from the start (colour within 0.1 of the background) never runs
+            const bool decided = sm_eff[k].w > 1.0f;
+            my_tk[k * 128] = make_float2((in0 && !decided) ? 1.0f : -1.0f, (in1 && !decided) ? 1.0f : -1.0f);
+            if (decided) { dk0 |= 1u << k; dk1 |= 1u << k; }
+        }
     uint32_t last0 = 0, last1 = 0;
     bool w_main_done = false, w_done = false;
     const f32x2 ONE = bc2(1.0f), MONE = bc2(-1.0f);
+
+    // power of one Gaussian at the lane's two pixels (A.7 operation order per half)
+    auto power_of = [&](const float4& A, const float4& B) -> f32x2 {
+        const float dx = sub(A.x, pfx);
+        const float t1 = mul(A.z, dx);     // conic.x * dx
+        const float nt2 = mul(-A.w, dx);   // -(conic.y * dx)
+        const f32x2 dy = add2(bc2(A.y), npfy);
+        const f32x2 w = mul2(dy, mul2(bc2(B.x), dy));
+        const f32x2 sq = fma2(bc2(dx), bc2(t1), w);
+        const f32x2 nbxy = mul2(bc2(nt2), dy);
+        return fma2(sq, bc2(-0.5f), nbxy);
+    };
+    // opacity * exp(power) on both halves, before the min(0.99, .)
+    auto raw_alpha = [&](f32x2 pw, float op, float& a0, float& a1) {
+        if (FAST) {
+            float q0, q1;
+            unpk2(mul2(pw, bc2(1.44269502162933349609375f)), q0, q1);
+            unpk2(mul2(pk2(ex2_approx(q0), ex2_approx(q1)), bc2(op)), a0, a1);
+        } else {
+            float e0, e1;
+            exp2_exact_nz(pw, e0, e1);
+            unpk2(mul2(pk2(e0, e1), bc2(op)), a0, a1);
+        }
+    };
+    // C += c * am * Told for the four accumulated channels
+    auto accumulate = [&](const float4& Cc, float depth, f32x2 am, f32x2 Told) {
+        if (FAST) {
+            const f32x2 w = mul2(am, Told);
+            C0 = fma2(bc2(Cc.x), w, C0);
+            C1 = fma2(bc2(Cc.y), w, C1);
+            C2 = fma2(bc2(Cc.z), w, C2);
+            D = fma2(bc2(depth), w, D);
+        } else {
+            C0 = fma2(mul2(bc2(Cc.x), am), Told, C0);
+            C1 = fma2(mul2(bc2(Cc.y), am), Told, C1);
+            C2 = fma2(mul2(bc2(Cc.z), am), Told, C2);
+            D = fma2(mul2(bc2(depth), am), Told, D);
+        }
+    };
+    // the objects-only chains of one object hit: av = alpha where the half blends at all (A.7's three skips,
+    // independent of the main chain), else 0
+    auto object_chains = [&](int obj, float av0, float av1) {
+        const f32x2 om = fma2(pk2(av0, av1), MONE, ONE);
+        const float4 ec = sm_eff[obj - 1];
+        {   // objects-only render (visible masks, sem-seg)
+            const f32x2 tT = mul2(To, om);
+            float n0, n1, o0, o1;
+            unpk2(tT, n0, n1);
+            unpk2(To, o0, o1);
+            const bool d0 = n0 < 0.0001f, d1 = n1 < 0.0001f;  // also true for a finished (negative) chain
+            const f32x2 am = pk2(d0 ? 0.0f : av0, d1 ? 0.0f : av1);
+            const f32x2 Told = To;
+            To = pk2(d0 ? -fabsf(o0) : n0, d1 ? -fabsf(o1) : n1);
+            // a finished chain has Told < 0 and am == 0: the product is -0, the sum unchanged
+            S0 = fma2(mul2(bc2(ec.x), am), Told, S0);
+            S1 = fma2(mul2(bc2(ec.y), am), Told, S1);
+            S2 = fma2(mul2(bc2(ec.z), am), Told, S2);
+        }
+        // silhouette chain of this object: terminated (T (1 - alpha) < 1e-4: keeps T, as the reference's pass would) or
+        // decided (below the object's threshold: keeps the new value); both are stored negative = finished
+        const uint32_t kbit = 1u << ((uint32_t)(obj - 1) & 31u);
+        const float2 tk = my_tk[(obj - 1) * 128];
+        const f32x2 tT = mul2(pk2(tk.x, tk.y), om);
+        float n0, n1;
+        unpk2(tT, n0, n1);
+        const bool d0 = n0 < ec.w, d1 = n1 < ec.w;          // finished now (or before: n <= 0)
+        if (d0) dk0 |= kbit;
+        if (d1) dk1 |= kbit;
+        const float f0 = n0 < 0.0001f ? -fabsf(tk.x) : -n0, f1 = n1 < 0.0001f ? -fabsf(tk.y) : -n1;
+        my_tk[(obj - 1) * 128] = make_float2(d0 ? f0 : n0, d1 ? f1 : n1);
+    };
 
     for (int it = 0;; ++it) {
         const int s = it % COMP_STAGES;
@@ -139,104 +237,48 @@ __global__ void __launch_bounds__(COMP2_THREADS, MINB) composite3_kernel(const C
         if (cnt == 0) break;
         if (!w_done) {
             const GeomRec* sr = sm.rec[s];
-            bool wm = !w_main_done;
-#pragma unroll 1
-            for (int c0 = 0; c0 < cnt; c0 += 32) {
-                const int e = c0 + lane;
-                uint32_t need = 0;
-                if (MASKS && !wm) {
-                    float to0, to1;
-                    unpk2(To, to0, to1);
-                    need = __any_sync(0xffffffffu, to0 > 0.0f || to1 > 0.0f)
-                               ? all_k : (__reduce_or_sync(0xffffffffu, ~(dk0 & dk1)) & all_k);
-                    if (need == 0) break;
+            const bool wm = !w_main_done;  // a main chain of this warp is alive: every entry is wanted
+            // objects some pixel of this warp still needs (bit k-1): every object while an objects-only render chain is
+            // alive, else those whose silhouette chain is alive somewhere
+            uint32_t need = 0;
+            if (MASKS && !wm) {
+                float to0, to1;
+                unpk2(To, to0, to1);
+                need = __any_sync(0xffffffffu, to0 > 0.0f || to1 > 0.0f)
+                           ? all_k : (__reduce_or_sync(0xffffffffu, ~(dk0 & dk1)) & all_k);
+            }
+            // ---- 1. cull the batch against this warp's pixel block, queue the hits in list order
+            int nq = 0;
+            if (wm || need != 0) {
+#pragma unroll
+                for (int c = 0; c < COMP_BATCH / 32; ++c) {
+                    const int e = c * 32 + lane;
+                    bool hit = false;
+                    if (e < cnt) {
+                        const float4 A = sr[e].a;
+                        const float4 B = sr[e].b;
+                        const int eo = MASKS ? (__float_as_int(B.w) & 63) : 0;
+                        const bool wanted = wm || (MASKS && eo > 0 && ((need >> ((uint32_t)(eo - 1) & 31u)) & 1u));
+                        hit = wanted && !block_culled_fast(A.x, A.y, A.z, A.w, B.x, B.w, bx0, bx1, by0, by1);
+                    }
+                    const uint32_t m = __ballot_sync(0xffffffffu, hit);
+                    if (hit) queue[nq + __popc(m & lt)] = (uint8_t)e;
+                    nq += __popc(m);
                 }
-                bool hit = false;
-                if (e < cnt) {
-                    const float4 A = sr[e].a;
-                    const float4 B = sr[e].b;
-                    const int eo = MASKS ? (__float_as_int(B.w) & 63) : 0;
-                    const bool wanted = wm || (MASKS && eo > 0 && ((need >> ((uint32_t)(eo - 1) & 31u)) & 1u));
-                    hit = wanted && !block_culled_fast(A.x, A.y, A.z, A.w, B.x, B.w, bx0, bx1, by0, by1);
-                }
-                uint32_t mm = __ballot_sync(0xffffffffu, hit);
-
-                // power of one Gaussian at the lane's two pixels (A.7 operation order per half)
-                auto power_of = [&](const float4& A, const float4& B) -> f32x2 {
-                    const float dx = sub(A.x, pfx);
-                    const float t1 = mul(A.z, dx);     // conic.x * dx
-                    const float nt2 = mul(-A.w, dx);   // -(conic.y * dx)
-                    const f32x2 dy = add2(bc2(A.y), npfy);
-                    const f32x2 w = mul2(dy, mul2(bc2(B.x), dy));
-                    const f32x2 sq = fma2(bc2(dx), bc2(t1), w);
-                    const f32x2 nbxy = mul2(bc2(nt2), dy);
-                    return fma2(sq, bc2(-0.5f), nbxy);
-                };
-                // opacity * exp(power) on both halves, before the min(0.99, .)
-                auto raw_alpha = [&](f32x2 pw, float op, float& a0, float& a1) {
-                    if (FAST) {
-                        float q0, q1;
-                        unpk2(mul2(pw, bc2(1.44269502162933349609375f)), q0, q1);
-                        unpk2(mul2(pk2(ex2_approx(q0), ex2_approx(q1)), bc2(op)), a0, a1);
-                    } else {
-                        float e0, e1;
-                        exp2_exact_nz(pw, e0, e1);
-                        unpk2(mul2(pk2(e0, e1), bc2(op)), a0, a1);
-                    }
-                };
-                // C += c * am * Told for the four accumulated channels
-                auto accumulate = [&](const float4& Cc, float depth, f32x2 am, f32x2 Told) {
-                    if (FAST) {
-                        const f32x2 w = mul2(am, Told);
-                        C0 = fma2(bc2(Cc.x), w, C0);
-                        C1 = fma2(bc2(Cc.y), w, C1);
-                        C2 = fma2(bc2(Cc.z), w, C2);
-                        D = fma2(bc2(depth), w, D);
-                    } else {
-                        C0 = fma2(mul2(bc2(Cc.x), am), Told, C0);
-                        C1 = fma2(mul2(bc2(Cc.y), am), Told, C1);
-                        C2 = fma2(mul2(bc2(Cc.z), am), Told, C2);
-                        D = fma2(mul2(bc2(depth), am), Told, D);
-                    }
-                };
-                // the object-only chains of one object hit (composite2_kernel's arithmetic): av = alpha where the half
-                // blends at all (A.7's three skips, independent of the main chain), else 0
-                auto object_chains = [&](int obj, float av0, float av1) {
-                    const f32x2 om = fma2(pk2(av0, av1), MONE, ONE);
-                    {   // objects-only render (visible masks, sem-seg)
-                        const f32x2 tT = mul2(To, om);
-                        float n0, n1, o0, o1;
-                        unpk2(tT, n0, n1);
-                        unpk2(To, o0, o1);
-                        const bool d0 = n0 < 0.0001f, d1 = n1 < 0.0001f;  // also true for a finished (negative) chain
-                        const f32x2 am = pk2(d0 ? 0.0f : av0, d1 ? 0.0f : av1);
-                        const f32x2 Told = To;
-                        To = pk2(d0 ? -fabsf(o0) : n0, d1 ? -fabsf(o1) : n1);
-                        const float4 ec = sm_eff[obj - 1];
-                        // a finished chain has Told < 0 and am == 0: the product is -0, the sum unchanged
-                        S0 = fma2(mul2(bc2(ec.x), am), Told, S0);
-                        S1 = fma2(mul2(bc2(ec.y), am), Told, S1);
-                        S2 = fma2(mul2(bc2(ec.z), am), Told, S2);
-                    }
-                    const uint32_t kbit = 1u << ((uint32_t)(obj - 1) & 31u);
-                    const float2 tk = my_tk[(obj - 1) * 128];
-                    const f32x2 tT = mul2(pk2(tk.x, tk.y), om);
-                    float n0, n1;
-                    unpk2(tT, n0, n1);
-                    const bool d0 = n0 < 0.0001f, d1 = n1 < 0.0001f;
-                    if (d0) dk0 |= kbit;
-                    if (d1) dk1 |= kbit;
-                    my_tk[(obj - 1) * 128] = make_float2(d0 ? -fabsf(tk.x) : n0, d1 ? -fabsf(tk.y) : n1);
-                };
+                if (lane == 0) queue[nq] = 0xFF;  // completes an odd number of hits
+                __syncwarp();
+            }
+            // ---- 2. walk the hits two at a time
+            int i_obj = wm ? nq : 0;  // where the objects-only loop takes over
+            if (wm) {
 #pragma unroll 1
-                while (mm) {
-                    const GeomRec* r1 = sr + (c0 + __ffs(mm) - 1);
-                    mm &= mm - 1;
-                    // without a second hit the pair is completed by a record that never blends (opacity 0)
-                    const GeomRec* r2 = mm ? sr + (c0 + __ffs(mm) - 1) : &sm.dummy;
-                    mm &= mm - 1;
+                for (int i = 0; i < nq; i += 2) {
+                    const uint32_t pr = *reinterpret_cast<const uint16_t*>(queue + i);
+                    const uint32_t e1 = pr & 255u, e2 = pr >> 8;
+                    const GeomRec* r1 = sr + e1;
+                    const GeomRec* r2 = e2 == 255u ? &sm.dummy : sr + e2;  // a record that never blends (opacity 0)
                     const float4 A1 = r1->a, B1 = r1->b, A2 = r2->a, B2 = r2->b;
-                    const float4 Cc1 = r1->c, Cc2 = r2->c;  // loaded with the rest: a late load makes ptxas shuffle the alphas
+                    const float4 Cc1 = r1->c, Cc2 = r2->c;
                     const f32x2 p1 = power_of(A1, B1), p2 = power_of(A2, B2);
                     const int fl = (__float_as_int(B1.w) | __float_as_int(B2.w)) & PG_REC_FLAGS;  // warp-uniform
                     float a10, a11, a20, a21, q10, q11, q20, q21;
@@ -254,81 +296,82 @@ __global__ void __launch_bounds__(COMP2_THREADS, MINB) composite3_kernel(const C
                         if (o1) object_chains(o1, valid_alpha(q10, B1.w, a10, THR_ALIVE), valid_alpha(q11, B1.w, a11, THR_ALIVE));
                         if (o2) object_chains(o2, valid_alpha(q20, B2.w, a20, THR_ALIVE), valid_alpha(q21, B2.w, a21, THR_ALIVE));
                     }
-                    // ---- main chain (RGB + depth), both hits
-                    // T only decreases: if T after both hits is >= 1e-4 at every pixel of the warp, no chain terminates
-                    // at either hit (one min, one compare, one vote for the pair).  Otherwise — at most once per pixel —
-                    // the chains that terminate are marked dead from the terminating hit on (a chain that terminates
-                    // at a hit does not blend it) and the pair's alphas are formed again; that evaluation passes.
-                    f32x2 T1, T2;
-                    float av10, av11, av20, av21;
-                    if (BRANCHY) {
-                    av10 = valid_alpha(q10, B1.w, a10, thr0), av11 = valid_alpha(q11, B1.w, a11, thr1);
-                    av20 = valid_alpha(q20, B2.w, a20, thr0), av21 = valid_alpha(q21, B2.w, a21, thr1);
-                    T1 = mul2(T, fma2(pk2(av10, av11), MONE, ONE));
-                    T2 = mul2(T1, fma2(pk2(av20, av21), MONE, ONE));
-                    {
-                        float t20, t21;
-                        unpk2(T2, t20, t21);
-                        if (__builtin_expect(__any_sync(0xffffffffu, fminf(t20, t21) < 0.0001f), 0)) {
-                            float t10, t11;
-                            unpk2(T1, t10, t11);
-                            // hit 1: a chain with T1 < 1e-4 terminates there (no blend, dead for hit 2 as well)
-                            const bool d10 = t10 < 0.0001f, d11 = t11 < 0.0001f;
-                            av10 = d10 ? 0.0f : av10; av20 = d10 ? 0.0f : av20; thr0 = d10 ? THR_DEAD : thr0;
-                            av11 = d11 ? 0.0f : av11; av21 = d11 ? 0.0f : av21; thr1 = d11 ? THR_DEAD : thr1;
-                            T1 = mul2(T, fma2(pk2(av10, av11), MONE, ONE));
-                            // hit 2: chains still alive whose T would drop below 1e-4 terminate there
-                            unpk2(mul2(T1, fma2(pk2(av20, av21), MONE, ONE)), t20, t21);
-                            const bool d20 = t20 < 0.0001f, d21 = t21 < 0.0001f;
-                            av20 = d20 ? 0.0f : av20; thr0 = d20 ? THR_DEAD : thr0;
-                            av21 = d21 ? 0.0f : av21; thr1 = d21 ? THR_DEAD : thr1;
-                            T2 = mul2(T1, fma2(pk2(av20, av21), MONE, ONE));
-                        }
-                    }
-                    } else {
-                        // branch-free: every hit tests its own termination (a dead chain has alpha 0, so tT == T >= 1e-4)
-                        float n0, n1, o0, o1;
-                        av10 = valid_alpha(q10, B1.w, a10, thr0), av11 = valid_alpha(q11, B1.w, a11, thr1);
-                        unpk2(mul2(T, fma2(pk2(av10, av11), MONE, ONE)), n0, n1);
-                        unpk2(T, o0, o1);
-                        const bool d10 = n0 < 0.0001f, d11 = n1 < 0.0001f;
-                        av10 = d10 ? 0.0f : av10; thr0 = d10 ? THR_DEAD : thr0;
-                        av11 = d11 ? 0.0f : av11; thr1 = d11 ? THR_DEAD : thr1;
-                        T1 = pk2(d10 ? o0 : n0, d11 ? o1 : n1);
-                        av20 = valid_alpha(q20, B2.w, a20, thr0), av21 = valid_alpha(q21, B2.w, a21, thr1);
-                        unpk2(mul2(T1, fma2(pk2(av20, av21), MONE, ONE)), n0, n1);
-                        unpk2(T1, o0, o1);
-                        const bool d20 = n0 < 0.0001f, d21 = n1 < 0.0001f;
-                        av20 = d20 ? 0.0f : av20; thr0 = d20 ? THR_DEAD : thr0;
-                        av21 = d21 ? 0.0f : av21; thr1 = d21 ? THR_DEAD : thr1;
-                        T2 = pk2(d20 ? o0 : n0, d21 ? o1 : n1);
-                    }
+                    // main chain (RGB + depth): every hit tests its own termination — a chain that would drop below 1e-4
+                    // does not blend the hit and is dead from then on (a dead chain has alpha 0, so tT == T >= 1e-4)
+                    float n0, n1, o0, o1;
+                    float av10 = valid_alpha(q10, B1.w, a10, thr0), av11 = valid_alpha(q11, B1.w, a11, thr1);
+                    unpk2(mul2(T, fma2(pk2(av10, av11), MONE, ONE)), n0, n1);
+                    unpk2(T, o0, o1);
+                    const bool d10 = n0 < 0.0001f, d11 = n1 < 0.0001f;
+                    av10 = d10 ? 0.0f : av10; thr0 = d10 ? THR_DEAD : thr0;
+                    av11 = d11 ? 0.0f : av11; thr1 = d11 ? THR_DEAD : thr1;
+                    const f32x2 T1 = pk2(d10 ? o0 : n0, d11 ? o1 : n1);
+                    float av20 = valid_alpha(q20, B2.w, a20, thr0), av21 = valid_alpha(q21, B2.w, a21, thr1);
+                    unpk2(mul2(T1, fma2(pk2(av20, av21), MONE, ONE)), n0, n1);
+                    unpk2(T1, o0, o1);
+                    const bool d20 = n0 < 0.0001f, d21 = n1 < 0.0001f;
+                    av20 = d20 ? 0.0f : av20; thr0 = d20 ? THR_DEAD : thr0;
+                    av21 = d21 ? 0.0f : av21; thr1 = d21 ? THR_DEAD : thr1;
+                    const f32x2 T2 = pk2(d20 ? o0 : n0, d21 ? o1 : n1);
                     accumulate(Cc1, B1.z, pk2(av10, av11), T);
                     accumulate(Cc2, B2.z, pk2(av20, av21), T1);
                     T = T2;
                     if (NCONTRIB) {
-                        const uint32_t pos1 = sm.pos[s][r1 - sr], pos2 = r2 != &sm.dummy ? sm.pos[s][r2 - sr] : 0u;
+                        const uint32_t pos1 = sm.pos[s][e1], pos2 = e2 == 255u ? 0u : sm.pos[s][e2];
                         if (av10 > 0.0f) last0 = pos1;
                         if (av11 > 0.0f) last1 = pos1;
                         if (av20 > 0.0f) last0 = pos2;
                         if (av21 > 0.0f) last1 = pos2;
                     }
+                    // every 4th pair: once all main chains of the warp are dead the rest of the batch is no-ops
+                    // (object entries still have to reach their chains, so only without masks)
+                    if ((i & 6) == 6 && !__any_sync(0xffffffffu, thr0 == THR_ALIVE || thr1 == THR_ALIVE)) {
+                        i_obj = i + 2;  // the rest of the batch can only matter to the objects-only chains
+                        break;
+                    }
                 }
-                if (wm && !__any_sync(0xffffffffu, thr0 == THR_ALIVE || thr1 == THR_ALIVE)) {
-                    wm = false;
-                    if (!MASKS) break;
+                if (!__any_sync(0xffffffffu, thr0 == THR_ALIVE || thr1 == THR_ALIVE)) {
+                    w_main_done = true;
+                    if (lane == 0) atomicAdd(&sm.warps_main_done, 1);
                 }
             }
-            if (!w_main_done && !wm) {
-                w_main_done = true;
-                if (lane == 0) atomicAdd(&sm.warps_main_done, 1);
+            if (MASKS && i_obj < nq) {
+                // every main chain of the warp has terminated: only the objects-only chains run, on object entries
+                // (a batch culled while a main chain was alive still has environment entries queued: skipped)
+#pragma unroll 1
+                for (int i = i_obj; i < nq; i += 2) {
+                    const uint32_t pr = *reinterpret_cast<const uint16_t*>(queue + i);
+                    const uint32_t e1 = pr & 255u, e2 = pr >> 8;
+                    const GeomRec* r1 = sr + e1;
+                    const GeomRec* r2 = e2 == 255u ? &sm.dummy : sr + e2;
+                    const float4 B1 = r1->b, B2 = r2->b;
+                    const int fl = (__float_as_int(B1.w) | __float_as_int(B2.w)) & PG_REC_FLAGS;
+                    if (!(fl & 63)) continue;
+                    const float4 A1 = r1->a, A2 = r2->a;
+                    const f32x2 p1 = power_of(A1, B1), p2 = power_of(A2, B2);
+                    float a10, a11, a20, a21, q10, q11, q20, q21;
+                    raw_alpha(p1, B1.y, a10, a11);
+                    raw_alpha(p2, B2.y, a20, a21);
+                    unpk2(p1, q10, q11);
+                    unpk2(p2, q20, q21);
+                    if (fl & PG_REC_GENERAL) {
+                        a10 = fminf(0.99f, a10); a11 = fminf(0.99f, a11);
+                        a20 = fminf(0.99f, a20); a21 = fminf(0.99f, a21);
+                    }
+                    const int o1 = __float_as_int(B1.w) & 63, o2 = __float_as_int(B2.w) & 63;
+                    if (o1) object_chains(o1, valid_alpha(q10, B1.w, a10, THR_ALIVE), valid_alpha(q11, B1.w, a11, THR_ALIVE));
+                    if (o2) object_chains(o2, valid_alpha(q20, B2.w, a20, THR_ALIVE), valid_alpha(q21, B2.w, a21, THR_ALIVE));
+                }
             }
-            float o0, o1;
-            unpk2(To, o0, o1);
-            const bool pix_done = thr0 != THR_ALIVE && thr1 != THR_ALIVE && (!MASKS || (o0 < 0.0f && o1 < 0.0f && (dk0 & dk1 & all_k) == all_k));
-            if (__all_sync(0xffffffffu, pix_done)) {
-                w_done = true;
-                if (lane == 0) atomicAdd(&sm.warps_done, 1);
+            // ---- report progress to the producer
+            if (w_main_done) {
+                float o0, o1;
+                unpk2(To, o0, o1);
+                const bool pix_done = !MASKS || (o0 < 0.0f && o1 < 0.0f && (dk0 & dk1 & all_k) == all_k);
+                if (__all_sync(0xffffffffu, pix_done)) {
+                    w_done = true;
+                    if (lane == 0) atomicAdd(&sm.warps_done, 1);
+                }
             }
         }
         __syncwarp();
@@ -389,24 +432,23 @@ __global__ void __launch_bounds__(COMP2_THREADS, MINB) composite3_kernel(const C
     }
 }
 
-template <bool MASKS, bool NCONTRIB, bool FAST, int STAGES, int MINB, bool BRANCHY = false>
+template <bool MASKS, bool NCONTRIB, bool FAST, int STAGES, int MINB>
 static int launch_three(const CompArgs& a, dim3 grid, cudaStream_t stream) {
-    const int smem = (int)sizeof(CompSmemT<STAGES>) +
+    const int smem = (int)((sizeof(CompSmemT<STAGES>) + 15) / 16 * 16) + COMP2_CW * QSTRIDE +
                      (MASKS ? (int)(PG_MAX_OBJECTS * sizeof(float4)) + a.num_objects * 256 * (int)sizeof(float) : 0);
-    PG_CUDA_CHECK(ensure_dynamic_smem(composite3_kernel<MASKS, NCONTRIB, FAST, STAGES, MINB, BRANCHY>, smem, true));
-    composite3_kernel<MASKS, NCONTRIB, FAST, STAGES, MINB, BRANCHY><<<grid, COMP2_THREADS, smem, stream>>>(a);
+    PG_CUDA_CHECK(ensure_dynamic_smem(composite3_kernel<MASKS, NCONTRIB, FAST, STAGES, MINB>, smem, true));
+    composite3_kernel<MASKS, NCONTRIB, FAST, STAGES, MINB><<<grid, COMP2_THREADS, smem, stream>>>(a);
     return PG_OK;
 }
 
-// masks: fused K+3 passes; fast: PG_NUMERICS_FAST; variant (tuning): 31 = 5 CTAs / SM
+// masks: fused K+3 passes; fast: PG_NUMERICS_FAST
 int launch_composite3(const CompArgs& a, dim3 grid, bool masks, bool fast, int variant, cudaStream_t stream) {
+    (void)variant;
     if (!masks) {
         const bool nc = a.out_n_contrib != nullptr;
         if (fast) return nc ? launch_three<false, true, true, 4, 4>(a, grid, stream) : launch_three<false, false, true, 4, 4>(a, grid, stream);
         return nc ? launch_three<false, true, false, 4, 4>(a, grid, stream) : launch_three<false, false, false, 4, 4>(a, grid, stream);
     }
-    if (variant == 31) return fast ? launch_three<true, false, true, 4, 5>(a, grid, stream) : launch_three<true, false, false, 4, 5>(a, grid, stream);
-    if (variant == 32) return fast ? launch_three<true, false, true, 4, 4, true>(a, grid, stream) : launch_three<true, false, false, 4, 4, true>(a, grid, stream);
     return fast ? launch_three<true, false, true, 4, 4>(a, grid, stream) : launch_three<true, false, false, 4, 4>(a, grid, stream);
 }
 
