@@ -1,9 +1,9 @@
 // binning.cu — tile binning after the depth sort (re-designed):
-//   emit_kernel      : fused scan of the stored pairs per Gaussian (decoupled look-back over chunks of
-//                      512 Gaussians, in DEPTH order) + key duplication, one thread per rectangle ROW:
-//                      writes (tile id, Gaussian index) pairs.  12 B read per Gaussian, 8 B written per pair.
-//                      also accumulates the digit histograms of both tile-sort passes (shared-memory
-//                      reductions: per pair for the low digit, per run for the high digit).
+//   emit_kernel      : key duplication in DEPTH order as a pure writer (output offsets come from the scan of the
+//                      per-Gaussian pair counts preprocess made: sort.cu scan_counts_kernel), one lane per
+//                      rectangle ROW: writes (tile id, Gaussian index) pairs.  48 B read per visible Gaussian,
+//                      8 B written per pair.  Also accumulates the digit histograms of both tile-sort passes
+//                      (shared-memory reductions: per pair for the low digit, per run for the high digit).
 //   tile_scan_kernel : exclusive digit bases of both tile-sort passes.
 //   tile_order_kernel: normalises the tile ranges the last sort pass reduced (identifyTileRanges happens
 //                      inside that pass) and orders the tiles by descending list length for compositing.
@@ -13,41 +13,35 @@
 
 namespace pg {
 
-constexpr uint32_t E_FLAG_AGG = 1u << 30;
-constexpr uint32_t E_FLAG_INCL = 2u << 30;
-constexpr uint32_t E_VAL_MASK = (1u << 30) - 1;
-
-#ifndef PG_EMIT_THREADS
-#define PG_EMIT_THREADS 256
-#endif
-constexpr int EMIT_THREADS = PG_EMIT_THREADS;
+constexpr int EMIT_THREADS = 256;
 constexpr int EMIT_WARPS = EMIT_THREADS / 32;
-constexpr int EMIT_EPT = EMIT_CHUNK / EMIT_THREADS;  // entries per thread (blocked = depth order)
-constexpr int EMIT_RPT = 14;                         // rows per thread in the row scan
-constexpr int EMIT_ROWCAP = EMIT_THREADS * EMIT_RPT; // tile rows of one window (3584)
-constexpr uint32_t EMIT_OK = 0x80000000u;            // s_g bit 31: the row test may cull (CullGauss::ok)
 
-struct EmitSmem {
-    // per entry of the chunk (depth order)
-    float4 cga[EMIT_CHUNK];            // CullGauss: gx, gy, qb, thr2qa
-    float4 cgb[EMIT_CHUNK];            //            det_lo, inv_qa, umax, k
-    ushort4 rect[EMIT_CHUNK];
-    uint32_t g[EMIT_CHUNK];            // Gaussian index | EMIT_OK
-    uint32_t rowbase[EMIT_CHUNK + 1];  // exclusive scan of the rectangles' row counts
-    // per tile row of the current window
-    uint32_t rowinfo[EMIT_ROWCAP];     // ta | tb << 11 | entry << 22   (run [ta, tb) of this row; gx <= 2047)
-    uint32_t rowoff[EMIT_ROWCAP + 1];  // exclusive scan of the rows' stored pairs (window-relative)
-    uint32_t scan[EMIT_WARPS];
-    uint32_t chunk, base;
-    uint32_t hist[2][RADIX];           // digit histograms of this chunk's stored pairs (both tile-sort passes)
-    uint8_t widx[EMIT_WARPS][32];      // write phase: rank among a warp's non-empty rows -> lane
+struct EmitWarpSmem {  // count_scan_kernel: one warp's 32 depth-ordered Gaussians
+    float4 cga[32];            // CullGauss: gx, gy, qb, thr2qa
+    float4 cgb[32];            //            det_lo, inv_qa, umax, k
+    ushort4 rect[32];
+    uint32_t g[32];            // Gaussian index | EMIT_OK
+    uint32_t rowbase[33];      // exclusive scan of the rectangles' row counts
 };
-static_assert(EMIT_CHUNK <= 1024 && EMIT_CHUNK % EMIT_THREADS == 0, "entry id is packed into 10 bits");
+struct EmitWriteSmem {  // emit_kernel: one group of 32 depth-ordered Gaussians
+    ushort4 rect[32];
+    uint32_t g[32];            // Gaussian index
+    uint32_t ovf[32];          // where the rows beyond RUN_FIX of a tall rectangle live in runs_ovf
+    uint32_t rowbase[33];      // exclusive scan of the rectangles' row counts
+};
+struct EmitSmem {
+    EmitWriteSmem w[EMIT_WARPS];   // the CTA's groups
+    uint32_t rounds[EMIT_WARPS + 1];  // exclusive scan of the groups' round counts
+    uint32_t gbase[EMIT_WARPS];    // output offset of each group
+    uint32_t next;                 // round ticket
+    uint8_t widx[EMIT_WARPS][32];  // per warp, write phase: rank among the non-empty rows of a round -> lane
+    uint32_t hist[2][RADIX];       // digit histograms of this CTA's stored pairs (both tile-sort passes)
+};
+constexpr uint32_t EMIT_OK = 0x80000000u;  // g bit 31: the row test may cull (CullGauss::ok)
 
 // One stored pair.  flag: the tile cannot receive a contribution (KEEP_ALL lists only).
 __device__ __forceinline__ void emit_pair(bool valid, uint32_t dst, uint32_t tile, uint32_t g, bool flag,
-                                          uint32_t n_env, uint32_t* __restrict__ tkeys,
-                                          uint32_t* __restrict__ tvals, uint32_t* __restrict__ tile_obj_count,
+                                          uint32_t* __restrict__ tkeys, uint32_t* __restrict__ tvals,
                                           uint32_t* __restrict__ hist_lo, uint32_t mask_lo) {
     if (valid) {
         // low digit of the tile sort: the tiles of a run are consecutive, so the lanes of a warp hit distinct
@@ -55,31 +49,255 @@ __device__ __forceinline__ void emit_pair(bool valid, uint32_t dst, uint32_t til
         atomicAdd(&hist_lo[tile & mask_lo], 1u);
         tkeys[dst] = tile;
         tvals[dst] = flag ? (g | PG_CULL_FLAG) : g;
-        if (g >= n_env && !flag) atomicAdd(&tile_obj_count[tile], 1u);
     }
 }
 
-// CTA-wide exclusive scan of one value per thread (EMIT_THREADS threads); returns the exclusive prefix, *total = sum.
-__device__ __forceinline__ uint32_t cta_excl_scan(uint32_t v, uint32_t* s_scan, uint32_t* total) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t x = v;
+// (0) of count_kernel: lane = one of the warp's 32 consecutive depth-ordered Gaussians.  Stages the row
+// test's constants, the rectangle and the index in the warp's shared memory, scans the rectangles' row counts
+// (rowbase[0..32]) and returns the warp's total number of tile rows.
+__device__ __forceinline__ uint32_t emit_gather(EmitWarpSmem& ws, const uint32_t* __restrict__ perm,
+                                                const GeomRec* __restrict__ recs, ushort4* __restrict__ srect,
+                                                uint32_t p, uint32_t n_vis, int gx, int gy, int lane) {
+    uint32_t g = 0, rows = 0;
+    ushort4 r = make_ushort4(0, 0, 0, 0);
+    if (p < n_vis) {
+        g = perm[p];
+        // ONE gather per Gaussian: the 48-byte record carries everything the binning needs (the tile rectangle
+        // follows from the pixel centre and the integer radius in c.w exactly as preprocess derived it)
+        const float4 ra = recs[g].a, rb = recs[g].b;
+        const int radius = __float_as_int(recs[g].c.w);
+        r = tile_rect(ra.x, ra.y, radius, gx, gy);
+        srect[p] = r;  // in depth order for the emit kernel (coalesced)
+        const CullGauss cg = cull_setup(ra.x, ra.y, ra.z, ra.w, rb.x, rb.w);
+        ws.cga[lane] = make_float4(cg.gx, cg.gy, cg.qb, cg.thr2qa);
+        ws.cgb[lane] = make_float4(cg.det_lo, cg.inv_qa, cg.umax, cg.k);
+        if (cg.ok) g |= EMIT_OK;
+        rows = (r.z > r.x) ? (uint32_t)(r.w - r.y) : 0u;
+    }
+    ws.g[lane] = g;
+    ws.rect[lane] = r;
+    uint32_t x = rows;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-        uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+        const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
         if (lane >= o) x += y;
     }
-    __syncthreads();  // previous users of s_scan are done
-    if (lane == 31) s_scan[warp] = x;
-    __syncthreads();
-    uint32_t wb = 0, tot = 0;
+    ws.rowbase[lane] = x - rows;
+    if (lane == 31) ws.rowbase[32] = x;
+    __syncwarp();
+    return __shfl_sync(0xffffffffu, x, 31);
+}
+
+// (1) of count_kernel: tile row number t of the warp's 32 rectangles (t < total rows): which Gaussian q
+// (largest q with rowbase[q] <= t), which tile row ty, and its run [ta, tb) of tiles that can contribute.
+// Returns the number of pairs stored for the row.
+template <bool KEEP_ALL>
+__device__ __forceinline__ uint32_t emit_row(const EmitWarpSmem& ws, uint32_t t, int W, int H, int& q, int& ty,
+                                             int& ta, int& tb, int& x0, uint32_t& gi) {
+    q = 0;
 #pragma unroll
-    for (int w = 0; w < EMIT_WARPS; ++w) {
-        const uint32_t c = s_scan[w];
-        if (w < warp) wb += c;
-        tot += c;
+    for (int step = 16; step > 0; step >>= 1)
+        if (ws.rowbase[q + step] <= t) q += step;
+    const ushort4 rr = ws.rect[q];
+    ty = (int)rr.y + (int)(t - ws.rowbase[q]);
+    const float4 ca = ws.cga[q], cb = ws.cgb[q];
+    CullGauss cg;
+    cg.gx = ca.x; cg.gy = ca.y; cg.qb = ca.z; cg.thr2qa = ca.w;
+    cg.det_lo = cb.x; cg.inv_qa = cb.y; cg.umax = cb.z; cg.k = cb.w;
+    cg.qa = 0.0f; cg.qc = 0.0f;  // not used by the row test
+    const uint32_t gq = ws.g[q];
+    cg.ok = (gq & EMIT_OK) != 0;
+    gi = gq & ~EMIT_OK;
+    const int c = cull_row_run(cg, ty, rr.x, rr.z, W, H, &ta, &tb);
+    x0 = KEEP_ALL ? (int)rr.x : ta;
+    return KEEP_ALL ? (uint32_t)(rr.z - rr.x) : (uint32_t)c;
+}
+
+// count_kernel: the tile-row runs of every visible Gaussian, computed ONCE, row-parallel, in DEPTH order, and kept
+// for the emit kernel.  A CTA owns 8 GROUPS of 32 consecutive sorted positions; their rounds (32 tile rows each) are
+// taken by whichever warp is free; no dependency between CTAs (no look-back).  This is the only kernel of the
+// binning stage that gathers: one 48-byte record per Gaussian; everything it leaves behind is in depth order, so
+// the emit kernel reads coalesced:
+//   srect[p]           = tile rectangle of sorted position p;
+//   runs_fix[p][i]     = ta | tb << 11 of row i < RUN_FIX of sorted position p (run [ta, tb) of tiles that can
+//                        contribute; gx <= 2047);
+//   runs_ovf[b + i - RUN_FIX] for the rows beyond RUN_FIX of tall rectangles, b = ovf_base[p] allocated with one
+//                        global atomic per tall rectangle (no order needed; capacity = pair capacity);
+//   rnd_off[group][k]  = stored pairs of the group's rounds before round k (rounds per group <= gy);
+//   grp_loc[group]     = stored pairs of the CTA's groups before this one;
+//   cta_pairs[cta]     = stored pairs of the CTA  -> pair_scan_kernel -> cta_base[cta].
+template <bool KEEP_ALL>
+__global__ void __launch_bounds__(EMIT_THREADS)
+count_kernel(const uint32_t* __restrict__ perm, ushort4* __restrict__ srect,
+             const GeomRec* __restrict__ recs, uint32_t P, int W, int H, int gx, int gy,
+             uint32_t* __restrict__ runs_fix, uint32_t* __restrict__ runs_ovf, uint32_t* __restrict__ ovf_base,
+             uint32_t R_cap, uint32_t* __restrict__ rnd_off, uint32_t* __restrict__ grp_loc,
+             uint32_t* __restrict__ cta_pairs, Counters* __restrict__ counters) {
+    __shared__ EmitWarpSmem sw[EMIT_WARPS];
+    __shared__ uint32_t s_ovf[EMIT_WARPS][32];
+    __shared__ uint32_t s_rounds[EMIT_WARPS + 1];  // exclusive scan of the groups' round counts
+    __shared__ uint32_t s_tall[EMIT_WARPS], s_tall_base, s_gtot[EMIT_WARPS];
+    __shared__ uint32_t s_next;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t n_vis = min(counters->num_visible, P);
+    const uint32_t num_groups = (n_vis + 31u) / 32u;
+    const uint32_t grp0 = blockIdx.x * EMIT_WARPS;
+    if (grp0 >= num_groups) return;  // CTA-uniform
+    // ---- (0) warp w stages group grp0 + w
+    uint32_t my_rows = 0, tall = 0, tall_before = 0;  // tall: rows beyond RUN_FIX of this lane's rectangle
+    const uint32_t p = (grp0 + warp) * 32u + lane;
+    {
+        EmitWarpSmem& ws = sw[warp];
+        my_rows = emit_gather(ws, perm, recs, srect, p, n_vis, gx, gy, lane);
+        const uint32_t rows = ws.rowbase[lane + 1] - ws.rowbase[lane];
+        tall = rows > RUN_FIX ? rows - RUN_FIX : 0u;
+        uint32_t x = tall;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        tall_before = x - tall;
+        if (lane == 31) s_tall[warp] = x;
     }
-    *total = tot;
-    return wb + x - v;
+    if (lane == 0) s_rounds[warp + 1] = (my_rows + 31u) / 32u;
+    if (tid == 0) { s_rounds[0] = 0; s_next = 0; }
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t t_all = 0;
+        for (int w = 0; w < EMIT_WARPS; ++w) {
+            s_rounds[w + 1] += s_rounds[w];
+            const uint32_t c = s_tall[w];
+            s_tall[w] = t_all;
+            t_all += c;
+        }
+        // tall rectangles take space for their rows beyond RUN_FIX: ONE allocation per CTA (an atomic per rectangle
+        // on one word serialises in L2)
+        s_tall_base = t_all ? atomicAdd(&counters->run_ovf, t_all) : 0u;
+    }
+    __syncthreads();
+    {
+        const uint32_t b = s_tall_base + s_tall[warp] + tall_before;
+        s_ovf[warp][lane] = b;
+        if (p < n_vis) ovf_base[p] = b;
+    }
+    __syncthreads();
+    // ---- (1) the CTA's rounds (32 tile rows of one group each) are taken by whichever warp is free: a group of the
+    // nearest Gaussians has ~60 rounds, most groups have ~5
+    const uint32_t total_rounds = s_rounds[EMIT_WARPS];
+    for (;;) {
+        uint32_t u = 0;
+        if (lane == 0) u = atomicAdd(&s_next, 1u);
+        u = __shfl_sync(0xffffffffu, u, 0);
+        if (u >= total_rounds) break;
+        int w = 0;
+#pragma unroll
+        for (int i = 1; i < EMIT_WARPS; ++i) w += (s_rounds[i] <= u) ? 1 : 0;
+        const uint32_t k = u - s_rounds[w];
+        const EmitWarpSmem& ws = sw[w];
+        const uint32_t total_rows = ws.rowbase[32];
+        const uint32_t t = k * 32u + lane;
+        uint32_t len = 0, gi;
+        int q = 0, ty, ta = 0, tb = 0, x0;
+        if (t < total_rows) {
+            len = emit_row<KEEP_ALL>(ws, t, W, H, q, ty, ta, tb, x0, gi);
+            const uint32_t i = t - ws.rowbase[q];
+            const uint32_t run = (uint32_t)ta | ((uint32_t)tb << 11);
+            if (i < RUN_FIX) runs_fix[((size_t)(grp0 + w) * 32u + q) * RUN_FIX + i] = run;
+            else {
+                const uint32_t slot = s_ovf[w][q] + (i - RUN_FIX);
+                if (slot < R_cap) runs_ovf[slot] = run;  // beyond the table: an overflow frame (pair_scan_kernel flags it)
+            }
+        }
+        const uint32_t L = __reduce_add_sync(0xffffffffu, len);
+        if (lane == 0) rnd_off[(size_t)(grp0 + w) * gy + k] = L;  // pairs of this round; scanned in place below
+    }
+    __syncthreads();
+    // ---- (2) warp w: exclusive scan of its group's per-round pair counts -> where each round's pairs start
+    uint32_t carry = 0;
+    if (grp0 + warp < num_groups) {
+        const uint32_t nr = s_rounds[warp + 1] - s_rounds[warp];
+        uint32_t* ro = rnd_off + (size_t)(grp0 + warp) * gy;
+        for (uint32_t k0 = 0; k0 < nr; k0 += 32) {
+            const uint32_t k = k0 + lane;
+            const uint32_t v = k < nr ? ro[k] : 0u;
+            uint32_t x = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+                if (lane >= o) x += y;
+            }
+            if (k < nr) ro[k] = carry + x - v;
+            carry += __shfl_sync(0xffffffffu, x, 31);
+        }
+    }
+    if (lane == 0) s_gtot[warp] = carry;  // < 32 * 65536 tiles
+    __syncthreads();
+    // ---- (3) the groups' offsets inside the CTA, the CTA's pair total (-> pair_scan_kernel -> cta_base)
+    if (tid < EMIT_WARPS) {
+        uint32_t before = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < EMIT_WARPS; ++w) {
+            const uint32_t c = s_gtot[w];
+            if (w < tid) before += c;
+            total += c;
+        }
+        if (grp0 + tid < num_groups) grp_loc[grp0 + tid] = before;
+        if (tid == 0) cta_pairs[blockIdx.x] = total;  // < 256 * 65536 tiles
+    }
+}
+
+// pair_scan_kernel: exclusive scan of the per-CTA pair counts of count_kernel (one CTA; at most P / 256 values, 1024 per
+// sweep), and the frame's pair count: sort_n, overflow, sticky status.  cta_base saturates at 2^32 - 1 (nothing is
+// ever written at or beyond the pair capacity <= 2^30).
+__global__ void __launch_bounds__(1024)
+pair_scan_kernel(const uint32_t* __restrict__ cta_pairs, uint32_t* __restrict__ cta_base, uint32_t P, uint32_t R_cap,
+                 Counters* __restrict__ counters, Sticky* __restrict__ sticky) {
+    __shared__ unsigned long long s_warp[32];
+    __shared__ unsigned long long s_carry;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t n_vis = min(counters->num_visible, P);
+    const uint32_t n = (n_vis + EMIT_THREADS - 1) / EMIT_THREADS;
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (uint32_t i0 = 0; i0 < n; i0 += 1024) {
+        const uint32_t i = i0 + tid;
+        const unsigned long long v = i < n ? cta_pairs[i] : 0ull;
+        unsigned long long x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) s_warp[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            const unsigned long long w = s_warp[lane];
+            unsigned long long wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned long long y = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= o) wi += y;
+            }
+            s_warp[lane] = wi - w;
+        }
+        __syncthreads();
+        const unsigned long long excl = s_carry + s_warp[warp] + x - v;
+        if (i < n) cta_base[i] = (uint32_t)min(excl, 0xFFFFFFFFull);
+        __syncthreads();
+        if (tid == 1023) s_carry = excl + v;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        const unsigned long long R = s_carry;
+        const unsigned long long ovf = counters->run_ovf;  // rows of tall rectangles beyond RUN_FIX: same capacity
+        counters->sort_n = (uint32_t)min(R, (unsigned long long)R_cap);
+        if (R > R_cap || ovf > R_cap) {
+            counters->overflow = 1;
+            atomicAdd(&sticky->overflow_frames, 1u);
+        }
+        atomicMax(&sticky->max_pairs_needed, (uint32_t)min(max(R, ovf), 1ull << 30));
+    }
 }
 
 // KEEP_ALL = false (default): only (tile, Gaussian) pairs that can contribute are stored — per tile a
@@ -87,259 +305,160 @@ __device__ __forceinline__ uint32_t cta_excl_scan(uint32_t v, uint32_t* s_scan, 
 // KEEP_ALL = true : every tile of every rectangle is stored exactly as the reference's duplicateWithKeys
 //            does (pairs that cannot contribute carry PG_CULL_FLAG): pg_export_binning / n_contrib parity.
 //
-// The unit of work is the TILE ROW of a rectangle, not the Gaussian: rectangles span 1..gy rows, and a
-// thread that walks a tall one alone stalls its warp.  Per chunk of EMIT_CHUNK depth-ordered entries:
-//   (0) gather rect + record, derive the row test's constants (tile_cull.h) once per entry;
-//   (1) scan the row counts -> every (entry, row) gets a slot in a flat row list (windows of
-//       EMIT_ROWCAP rows; one window is the common case and its runs stay cached in shared memory);
-//   (2) one thread per row: closed-form run [ta, tb) of tiles that can contribute; scan of run lengths;
-//   (3) decoupled look-back over chunks -> output offset of the chunk;
-//   (4) every warp writes the runs of its 32 rows pair-parallel (slot j of the concatenated runs -> lane
+// A pure writer: count_kernel computed every tile row's run, pair_scan_kernel the frame-wide offsets, so every WARP knows
+// where its output starts and works on its own — no look-back, no row test, no CTA-wide barrier between set-up and
+// the final histogram flush.  Per warp, 32 consecutive depth-ordered Gaussians:
+//   (0) gather index, rectangle and offsets; scan the rectangles' row counts;
+//   (1) the unit of work is the TILE ROW of a rectangle (rectangles span 1..gy rows): rows are numbered across
+//       the 32 rectangles and taken 32 at a time, lane = row, its run [ta, tb) read back from the run tables;
+//   (2) the runs of a group of 32 rows are written pair-parallel (slot j of the concatenated runs -> lane
 //       j % 32): coalesced stores, no lane walks a long run alone.
-// Output order = entry order (depth), rows top to bottom, tiles left to right = the reference's order.
+// Output order = depth order, rows top to bottom, tiles left to right = the reference's order.
 template <bool KEEP_ALL>
 __global__ void __launch_bounds__(EMIT_THREADS)
-emit_kernel(const uint32_t* __restrict__ sorted_dkey, const uint32_t* __restrict__ perm,
-            const ushort4* __restrict__ rects, const GeomRec* __restrict__ recs, uint32_t P, uint32_t gx,
-            int W, int H, uint32_t* __restrict__ tkeys,
-            uint32_t* __restrict__ tvals, uint32_t R_cap, uint32_t* __restrict__ status,
-            uint32_t n_env, uint32_t* __restrict__ tile_obj_count, Counters* __restrict__ counters,
-            Sticky* __restrict__ sticky, int bits_lo, uint32_t* __restrict__ hist /*[2][RADIX]*/) {
-    extern __shared__ __align__(16) unsigned char emit_smem_raw[];
-    EmitSmem& sm = *reinterpret_cast<EmitSmem*>(emit_smem_raw);
-
+emit_kernel(const uint32_t* __restrict__ perm, const uint32_t* __restrict__ cta_base, const uint32_t* __restrict__ grp_loc,
+            const uint32_t* __restrict__ rnd_off,
+            const uint32_t* __restrict__ runs_fix, const uint32_t* __restrict__ runs_ovf,
+            const uint32_t* __restrict__ ovf_base, const ushort4* __restrict__ srect, uint32_t P, uint32_t gx, int gy,
+            uint32_t* __restrict__ tkeys, uint32_t* __restrict__ tvals, uint32_t R_cap,
+            const Counters* __restrict__ counters, int bits_lo, uint32_t* __restrict__ hist /*[2][RADIX]*/) {
+    __shared__ EmitSmem sm;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t mask_lo = (1u << bits_lo) - 1u;
-    if (tid == 0) sm.chunk = atomicAdd(&counters->tile_counter[4], 1u);
     for (int i = tid; i < 2 * RADIX; i += EMIT_THREADS) (&sm.hist[0][0])[i] = 0;
-    __syncthreads();
-    const uint32_t chunk = sm.chunk;
-    // Culled Gaussians carry the largest depth key and sort behind every visible one: only the first
-    // ceil(num_visible / EMIT_CHUNK) chunks hold rectangles (num_visible is final: preprocess has finished).
+    // only the first num_visible sorted positions exist (the depth sort moved the visible Gaussians only)
     const uint32_t n_vis = min(counters->num_visible, P);
-    const uint32_t num_chunks = max((n_vis + EMIT_CHUNK - 1) / EMIT_CHUNK, 1u);
-    if (chunk >= num_chunks) return;
-
-    // ---- (0) gather: thread owns EMIT_EPT consecutive sorted positions (blocked, the scan order)
-    uint32_t my_rows = 0;
-    unsigned long long local_full = 0;
-#pragma unroll
-    for (int j = 0; j < EMIT_EPT; ++j) {
-        const int q = tid * EMIT_EPT + j;
-        const uint32_t spos = chunk * EMIT_CHUNK + q;
-        uint32_t g = 0;
+    const uint32_t num_groups = (n_vis + 31u) / 32u;
+    const uint32_t grp0 = blockIdx.x * EMIT_WARPS;
+    if (grp0 >= num_groups) return;  // CTA-uniform; nothing to flush
+    // ---- (0) warp w stages group grp0 + w: index, rectangle (in depth order: count_kernel left it there), tall-rectangle
+    // slot — all coalesced
+    {
+        EmitWriteSmem& ws = sm.w[warp];
+        const uint32_t p = (grp0 + warp) * 32u + lane;
+        uint32_t g = 0, rows = 0;
         ushort4 r = make_ushort4(0, 0, 0, 0);
-        if (spos < P && sorted_dkey[spos] != 0xFFFFFFFFu) {
-            g = perm[spos];
-            r = rects[g];
-            const float4 ra = recs[g].a, rb = recs[g].b;
-            const CullGauss cg = cull_setup(ra.x, ra.y, ra.z, ra.w, rb.x, rb.w);
-            sm.cga[q] = make_float4(cg.gx, cg.gy, cg.qb, cg.thr2qa);
-            sm.cgb[q] = make_float4(cg.det_lo, cg.inv_qa, cg.umax, cg.k);
-            if (cg.ok) g |= EMIT_OK;
+        if (p < n_vis) {
+            g = perm[p];
+            r = srect[p];
+            rows = (r.z > r.x) ? (uint32_t)(r.w - r.y) : 0u;
         }
-        sm.g[q] = g;
-        sm.rect[q] = r;
-        const uint32_t nr = (r.z > r.x) ? (uint32_t)(r.w - r.y) : 0u;
-        my_rows += nr;
-        local_full += (unsigned long long)nr * (uint32_t)(r.z - r.x);
-    }
-    // the reference's R = sum of all rectangle areas (what pg_status.num_rendered reports)
+        ws.g[lane] = g;
+        ws.rect[lane] = r;
+        ws.ovf[lane] = rows > RUN_FIX ? ovf_base[p] : 0u;
+        uint32_t xs = rows;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) local_full += __shfl_xor_sync(0xffffffffu, local_full, o);
-    if (lane == 0 && local_full) atomicAdd(&counters->rendered_full, local_full);
-
-    // ---- (1) row slots
-    uint32_t total_rows;
-    {
-        uint32_t rb = cta_excl_scan(my_rows, sm.scan, &total_rows);
-#pragma unroll
-        for (int j = 0; j < EMIT_EPT; ++j) {
-            const int q = tid * EMIT_EPT + j;
-            const ushort4 r = sm.rect[q];
-            sm.rowbase[q] = rb;
-            rb += (r.z > r.x) ? (uint32_t)(r.w - r.y) : 0u;
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, xs, o);
+            if (lane >= o) xs += y;
         }
-        if (tid == EMIT_THREADS - 1) sm.rowbase[EMIT_CHUNK] = rb;
+        ws.rowbase[lane] = xs - rows;
+        if (lane == 31) {
+            ws.rowbase[32] = xs;
+            sm.rounds[warp + 1] = (xs + 31u) / 32u;
+            const uint64_t b64 = grp0 + warp < num_groups ? (uint64_t)cta_base[blockIdx.x] + grp_loc[grp0 + warp] : 0ull;
+            sm.gbase[warp] = (uint32_t)min(b64, (uint64_t)0xFFFFFFFFu);
+        }
     }
+    if (tid == 0) { sm.rounds[0] = 0; sm.next = 0; }
     __syncthreads();
-    const uint32_t nwin = (total_rows + EMIT_ROWCAP - 1) / EMIT_ROWCAP;
-
-    // rows [w0, w0 + tw) -> sm.rowinfo / sm.rowoff; returns the window's stored pairs
-    auto compute_window = [&](uint32_t w0, uint32_t tw) -> uint32_t {
-        // (a) expansion: every entry writes its id into the slots of its rows that fall into the window
-#pragma unroll
-        for (int j = 0; j < EMIT_EPT; ++j) {
-            const int q = tid * EMIT_EPT + j;
-            const uint32_t b = sm.rowbase[q], e = sm.rowbase[q + 1];
-            const uint32_t lo = max(b, w0), hi = min(e, w0 + tw);
-            for (uint32_t t = lo; t < hi; ++t) sm.rowinfo[t - w0] = (uint32_t)q;
-        }
-        __syncthreads();
-        // (b) one thread per row (adjacent lanes = adjacent rows)
-        for (uint32_t t = tid; t < tw; t += EMIT_THREADS) {
-            const uint32_t q = sm.rowinfo[t];
-            const ushort4 r = sm.rect[q];
-            const int ty = (int)r.y + (int)(w0 + t - sm.rowbase[q]);
-            const float4 ca = sm.cga[q], cb = sm.cgb[q];
-            CullGauss cg;
-            cg.gx = ca.x; cg.gy = ca.y; cg.qb = ca.z; cg.thr2qa = ca.w;
-            cg.det_lo = cb.x; cg.inv_qa = cb.y; cg.umax = cb.z; cg.k = cb.w;
-            cg.qa = 0.0f; cg.qc = 0.0f;  // not used by the row test
-            cg.ok = (sm.g[q] & EMIT_OK) != 0;
-            int ta, tb;
-            const int c = cull_row_run(cg, ty, r.x, r.z, W, H, &ta, &tb);
-            sm.rowinfo[t] = (uint32_t)ta | ((uint32_t)tb << 11) | (q << 22);
-            sm.rowoff[t] = KEEP_ALL ? (uint32_t)(r.z - r.x) : (uint32_t)c;
-        }
-        __syncthreads();
-        // (c) exclusive scan of the run lengths, EMIT_RPT consecutive rows per thread
-        uint32_t len[EMIT_RPT], sum = 0;
-#pragma unroll
-        for (int i = 0; i < EMIT_RPT; ++i) {
-            const uint32_t t = tid * EMIT_RPT + i;
-            len[i] = t < tw ? sm.rowoff[t] : 0u;
-            sum += len[i];
-        }
-        uint32_t win_total;
-        uint32_t o = cta_excl_scan(sum, sm.scan, &win_total);
-#pragma unroll
-        for (int i = 0; i < EMIT_RPT; ++i) {
-            const uint32_t t = tid * EMIT_RPT + i;
-            if (t < tw) sm.rowoff[t] = o;
-            o += len[i];
-        }
-        if (tid == 0) sm.rowoff[tw] = win_total;
-        __syncthreads();
-        return win_total;
-    };
-
-    // ---- (2) sweep 1: count
-    uint32_t total = 0;
-    {
-        uint64_t t64 = 0;
-        for (uint32_t w = 0; w < nwin; ++w) {
-            const uint32_t w0 = w * EMIT_ROWCAP;
-            t64 += compute_window(w0, min((uint32_t)EMIT_ROWCAP, total_rows - w0));
-        }
-        total = (uint32_t)min(t64, (uint64_t)E_VAL_MASK);
-    }
-    // ---- (3) chunk-level decoupled look-back (single value): warp 0 inspects 32 predecessors per step
-    if (warp == 0) {
-        volatile uint32_t* st = status + chunk;
-        uint32_t prev = 0;
-        const uint32_t tot_c = total;
-        if (chunk == 0) {
-            if (lane == 0) *st = tot_c | E_FLAG_INCL;
-        } else {
-            if (lane == 0) *st = tot_c | E_FLAG_AGG;
-            int t = (int)chunk - 1;  // lane l looks at chunk t - l
-            while (true) {
-                const int mine = t - lane;
-                const uint32_t sv = mine >= 0 ? *(volatile uint32_t*)(status + mine) : (2u << 30);
-                const uint32_t f = sv >> 30;
-                const uint32_t not_ready = __ballot_sync(0xffffffffu, f == 0);
-                const uint32_t incl = __ballot_sync(0xffffffffu, f == 2);
-                // usable prefix of the window: lanes below the first not-ready one, up to the first inclusive one
-                const int first_nr = not_ready ? __ffs(not_ready) - 1 : 32;
-                const int first_in = incl ? __ffs(incl) - 1 : 32;
-                const int take = min(first_nr, first_in + 1);  // lanes [0, take)
-                uint32_t v = lane < take ? (sv & E_VAL_MASK) : 0u;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                prev = min(prev + v, E_VAL_MASK);
-                if (first_in < first_nr) break;
-                t -= take;
-            }
-            if (lane == 0) *st = min(prev + tot_c, E_VAL_MASK) | E_FLAG_INCL;
-        }
-        if (lane == 0) {
-            sm.base = prev;
-            if (chunk == num_chunks - 1) {
-                uint64_t R = (uint64_t)prev + total;
-                counters->sort_n = (uint32_t)min(R, (uint64_t)R_cap);
-                if (R > R_cap) {
-                    counters->overflow = 1;
-                    atomicAdd(&sticky->overflow_frames, 1u);
-                }
-                atomicMax(&sticky->max_pairs_needed, (uint32_t)min(R, (uint64_t)E_VAL_MASK + 1u));
-            }
-        }
-    }
+    if (tid == 0)
+        for (int w = 0; w < EMIT_WARPS; ++w) sm.rounds[w + 1] += sm.rounds[w];
     __syncthreads();
-    // ---- (4) sweep 2: write
-    uint32_t off = sm.base;
-    for (uint32_t w = 0; w < nwin; ++w) {
-        const uint32_t w0 = w * EMIT_ROWCAP;
-        const uint32_t tw = min((uint32_t)EMIT_ROWCAP, total_rows - w0);
-        uint32_t win_total;
-        if (nwin > 1) win_total = compute_window(w0, tw);  // a single window is still cached
-        else win_total = sm.rowoff[tw];
-        for (uint32_t t0 = 0; t0 < tw; t0 += EMIT_THREADS) {
-            const uint32_t t = t0 + tid;
-            uint32_t info = 0, o0 = 0, len = 0, g = 0;
-            int ty = 0, x0 = 0;
-            if (t < tw) {
-                info = sm.rowinfo[t];
-                o0 = sm.rowoff[t];
-                len = sm.rowoff[t + 1] - o0;
-                const uint32_t q = info >> 22;
-                const ushort4 r = sm.rect[q];
-                g = sm.g[q] & ~EMIT_OK;
-                ty = (int)r.y + (int)(w0 + t - sm.rowbase[q]);
-                x0 = KEEP_ALL ? (int)r.x : (int)(info & 2047u);
-            }
-            const int ta = (int)(info & 2047u), tb = (int)((info >> 11) & 2047u);
-            const uint32_t dst0 = off + o0;                    // may wrap only beyond R_cap (checked below)
-            const uint32_t room = dst0 < R_cap ? R_cap - dst0 : 0u;
-            const uint32_t tile0 = (uint32_t)ty * gx + (uint32_t)x0;
-            // high digit of the tile sort: once per run (a run crosses a digit boundary at most every
-            // 2^bits_lo tiles); only pairs that are really stored count
-            for (uint32_t tcur = tile0, left = min(len, room); left > 0;) {
-                const uint32_t n1 = min(left, (((tcur >> bits_lo) + 1u) << bits_lo) - tcur);
-                atomicAdd(&sm.hist[1][(tcur >> bits_lo) & 255u], n1);
-                tcur += n1;
-                left -= n1;
-            }
-            // The warp writes the pairs of its 32 rows PAIR-parallel: slot j of the group's concatenated output
-            // goes to lane j % 32, so stores are fully coalesced and no lane walks a long run alone.  Row of a
-            // slot: non-empty rows have distinct start offsets s; per batch of 32 slots the heads falling into
-            // it form a bit mask (one warp reduction), a popcount gives every slot the rank of its row among
-            // the non-empty rows, and widx maps the rank back to the lane that holds the row.
-            const uint32_t NE = __ballot_sync(0xffffffffu, len > 0);
-            if (NE == 0) continue;  // warp-uniform
-            const uint32_t gbase = __shfl_sync(0xffffffffu, o0, 0);  // NE != 0: the warp's first row exists
-            const uint32_t L = __reduce_add_sync(0xffffffffu, len);
-            const uint32_t srow = o0 - gbase;                        // start slot of this lane's row
-            const uint32_t tms = tile0 - srow;                       // tile of slot j in this row = tms + j
-            const int xms = x0 - (int)srow;
-            if (len > 0) sm.widx[warp][__popc(NE & ((1u << lane) - 1u))] = (uint8_t)lane;
-            __syncwarp();
-            const uint32_t gdst = off + gbase;
-            const uint32_t groom = gdst < R_cap ? R_cap - gdst : 0u;
-            uint32_t base_rank = 0;  // non-empty rows that start before the current batch
-            for (uint32_t jb = 0; jb < L; jb += 32) {
-                const uint32_t rel = srow - jb;  // wraps for rows that started earlier
-                const uint32_t hm = __reduce_or_sync(0xffffffffu, (len > 0 && rel < 32u) ? (1u << rel) : 0u);
-                const uint32_t j = jb + lane;
-                const uint32_t rank = base_rank + __popc(hm & (0xFFFFFFFFu >> (31 - lane))) - 1u;
-                const int src = sm.widx[warp][rank & 31u];
-                const uint32_t p_tms = __shfl_sync(0xffffffffu, tms, src);
-                const uint32_t p_g = __shfl_sync(0xffffffffu, g, src);
-                bool flag = false;
-                if (KEEP_ALL) {
-                    const int x = __shfl_sync(0xffffffffu, xms, src) + (int)j;
-                    const int p_ta = __shfl_sync(0xffffffffu, ta, src), p_tb = __shfl_sync(0xffffffffu, tb, src);
-                    flag = !(x >= p_ta && x < p_tb);
-                }
-                emit_pair(j < L && j < groom, gdst + j, p_tms + j, p_g, flag, n_env, tkeys, tvals, tile_obj_count,
-                          sm.hist[0], mask_lo);
-                base_rank += __popc(hm);
-            }
-            __syncwarp();  // widx is rewritten by the next group
+    // ---- the CTA's rounds (32 tile rows of one group each; count_kernel left every round's output offset) are taken
+    // by whichever warp is free: a group of the nearest Gaussians has ~60 rounds of up to 32 x gx pairs, most groups
+    // have ~5 rounds of a few dozen pairs, and a warp that owned a whole group would keep its CTA waiting
+    const uint32_t total_rounds = sm.rounds[EMIT_WARPS];
+    uint8_t* const widx = sm.widx[warp];
+    for (;;) {
+        uint32_t u = 0;
+        if (lane == 0) u = atomicAdd(&sm.next, 1u);
+        u = __shfl_sync(0xffffffffu, u, 0);
+        if (u >= total_rounds) break;
+        int w = 0;
+#pragma unroll
+        for (int i = 1; i < EMIT_WARPS; ++i) w += (sm.rounds[i] <= u) ? 1 : 0;
+        const uint32_t k = u - sm.rounds[w];
+        const EmitWriteSmem& ws = sm.w[w];
+        const uint32_t total_rows = ws.rowbase[32];
+        uint32_t off;
+        {
+            const uint64_t o64 = (uint64_t)sm.gbase[w] + rnd_off[(size_t)(grp0 + w) * gy + k];
+            off = (uint32_t)min(o64, (uint64_t)0xFFFFFFFFu);  // saturated offsets only occur beyond R_cap
         }
-        off = (uint32_t)min((uint64_t)off + win_total, (uint64_t)0xFFFFFFFFu);
-        if (nwin > 1) __syncthreads();  // the next window overwrites rowinfo / rowoff
+        // ---- (1) lane = row t: which Gaussian (largest q with rowbase[q] <= t), which tile row, its run
+        const uint32_t t = k * 32u + lane;
+        uint32_t len = 0, gi = 0;
+        int ta = 0, tb = 0, ty = 0, x0 = 0;
+        if (t < total_rows) {
+            int q = 0;
+#pragma unroll
+            for (int step = 16; step > 0; step >>= 1)
+                if (ws.rowbase[q + step] <= t) q += step;
+            const ushort4 rr = ws.rect[q];
+            const uint32_t i = t - ws.rowbase[q];
+            uint32_t run;
+            if (i < RUN_FIX) run = runs_fix[((size_t)(grp0 + w) * 32u + q) * RUN_FIX + i];
+            else {
+                const uint32_t slot = ws.ovf[q] + (i - RUN_FIX);
+                run = slot < R_cap ? runs_ovf[slot] : 0u;  // beyond the table: an overflow frame
+            }
+            ty = (int)rr.y + (int)i;
+            gi = ws.g[q];
+            ta = (int)(run & 2047u);
+            tb = (int)(run >> 11);
+            x0 = KEEP_ALL ? (int)rr.x : ta;
+            len = KEEP_ALL ? (uint32_t)(rr.z - rr.x) : (uint32_t)(tb - ta);
+        }
+        // exclusive scan of the run lengths of this round
+        uint32_t o0 = len;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, o0, o);
+            if (lane >= o) o0 += y;
+        }
+        const uint32_t L = __shfl_sync(0xffffffffu, o0, 31);
+        o0 -= len;
+        if (L == 0) continue;  // warp-uniform
+        const uint32_t tile0 = (uint32_t)ty * gx + (uint32_t)x0;
+        const uint32_t dst0 = off + o0;
+        const uint32_t room = dst0 < R_cap ? R_cap - dst0 : 0u;
+        // high digit of the tile sort: once per run (a run crosses a digit boundary at most every
+        // 2^bits_lo tiles); only pairs that are really stored count
+        for (uint32_t tcur = tile0, left = min(len, room); left > 0;) {
+            const uint32_t n1 = min(left, (((tcur >> bits_lo) + 1u) << bits_lo) - tcur);
+            atomicAdd(&sm.hist[1][(tcur >> bits_lo) & 255u], n1);
+            tcur += n1;
+            left -= n1;
+        }
+        // ---- (2) pair-parallel write.  Row of a slot: non-empty rows have distinct start offsets; per batch of
+        // 32 slots the heads falling into it form a bit mask (one warp reduction), a popcount gives every slot
+        // the rank of its row among the non-empty rows, and widx maps the rank back to the lane holding the row.
+        const uint32_t NE = __ballot_sync(0xffffffffu, len > 0);
+        const uint32_t tms = tile0 - o0;  // tile of slot j in this row = tms + j
+        const int xms = x0 - (int)o0;
+        if (len > 0) widx[__popc(NE & ((1u << lane) - 1u))] = (uint8_t)lane;
+        __syncwarp();
+        const uint32_t groom = off < R_cap ? R_cap - off : 0u;
+        uint32_t base_rank = 0;  // non-empty rows that start before the current batch
+        for (uint32_t jb = 0; jb < L; jb += 32) {
+            const uint32_t rel = o0 - jb;  // wraps for rows that started earlier
+            const uint32_t hm = __reduce_or_sync(0xffffffffu, (len > 0 && rel < 32u) ? (1u << rel) : 0u);
+            const uint32_t j = jb + lane;
+            const uint32_t rank = base_rank + __popc(hm & (0xFFFFFFFFu >> (31 - lane))) - 1u;
+            const int src = widx[rank & 31u];
+            const uint32_t p_tms = __shfl_sync(0xffffffffu, tms, src);
+            const uint32_t p_g = __shfl_sync(0xffffffffu, gi, src);
+            bool flag = false;
+            if (KEEP_ALL) {
+                const int xx = __shfl_sync(0xffffffffu, xms, src) + (int)j;
+                const int p_ta = __shfl_sync(0xffffffffu, ta, src), p_tb = __shfl_sync(0xffffffffu, tb, src);
+                flag = !(xx >= p_ta && xx < p_tb);
+            }
+            emit_pair(j < L && j < groom, off + j, p_tms + j, p_g, flag, tkeys, tvals, sm.hist[0], mask_lo);
+            base_rank += __popc(hm);
+        }
+        __syncwarp();  // widx is rewritten by the warp's next round
     }
     __syncthreads();
     for (int i = tid; i < 2 * RADIX; i += EMIT_THREADS) {
@@ -443,21 +562,38 @@ __global__ void export_keys_kernel(const uint2* __restrict__ ranges, uint32_t ti
     }
 }
 
-int launch_emit(bool keep_all, const uint32_t* sorted_dkey, const uint32_t* perm, const ushort4* rects, const GeomRec* recs,
-                uint32_t P, uint32_t gx, int W, int H, uint32_t* tkeys, uint32_t* tvals, uint32_t R_cap, uint32_t* status,
-                uint32_t n_env, uint32_t* tile_obj_count, Counters* counters, Sticky* sticky, int bits_lo,
+int launch_count(bool keep_all, const uint32_t* perm, ushort4* srect, const GeomRec* recs, uint32_t P, int W, int H,
+                 uint32_t* runs_fix, uint32_t* runs_ovf, uint32_t* ovf_base, uint32_t R_cap, uint32_t* rnd_off,
+                 uint32_t* grp_loc, uint32_t* cta_pairs, uint32_t* cta_base, Counters* counters, Sticky* sticky,
+                 cudaStream_t stream) {
+    if (P == 0) return PG_OK;
+    const uint32_t blocks = (P + EMIT_THREADS - 1) / EMIT_THREADS;  // sized for P; CTAs beyond num_visible exit at once
+    const int gx = (W + PG_TILE - 1) / PG_TILE, gy = (H + PG_TILE - 1) / PG_TILE;
+    if (keep_all)
+        count_kernel<true><<<blocks, EMIT_THREADS, 0, stream>>>(perm, srect, recs, P, W, H, gx, gy, runs_fix, runs_ovf, ovf_base,
+                                                                 R_cap, rnd_off, grp_loc, cta_pairs, counters);
+    else
+        count_kernel<false><<<blocks, EMIT_THREADS, 0, stream>>>(perm, srect, recs, P, W, H, gx, gy, runs_fix, runs_ovf, ovf_base,
+                                                                  R_cap, rnd_off, grp_loc, cta_pairs, counters);
+    PG_CUDA_CHECK(cudaGetLastError());
+    pair_scan_kernel<<<1, 1024, 0, stream>>>(cta_pairs, cta_base, P, R_cap, counters, sticky);
+    count_launch(2);
+    PG_CUDA_CHECK(cudaGetLastError());
+    return PG_OK;
+}
+
+int launch_emit(bool keep_all, const uint32_t* perm, const uint32_t* cta_base, const uint32_t* grp_loc, const uint32_t* rnd_off,
+                const uint32_t* runs_fix, const uint32_t* runs_ovf, const uint32_t* ovf_base, const ushort4* srect, uint32_t P,
+                uint32_t gx, int gy, uint32_t* tkeys, uint32_t* tvals, uint32_t R_cap, Counters* counters, int bits_lo,
                 uint32_t* hist_tile, cudaStream_t stream) {
-    uint32_t chunks = (P + EMIT_CHUNK - 1) / EMIT_CHUNK;
-    if (chunks == 0) return PG_OK;
-    if (keep_all) {
-        PG_CUDA_CHECK(ensure_dynamic_smem(emit_kernel<true>, (int)sizeof(EmitSmem)));
-        emit_kernel<true><<<chunks, EMIT_THREADS, sizeof(EmitSmem), stream>>>(sorted_dkey, perm, rects, recs, P, gx, W, H, tkeys, tvals, R_cap, status,
-                                                      n_env, tile_obj_count, counters, sticky, bits_lo, hist_tile);
-    } else {
-        PG_CUDA_CHECK(ensure_dynamic_smem(emit_kernel<false>, (int)sizeof(EmitSmem)));
-        emit_kernel<false><<<chunks, EMIT_THREADS, sizeof(EmitSmem), stream>>>(sorted_dkey, perm, rects, recs, P, gx, W, H, tkeys, tvals, R_cap, status,
-                                                       n_env, tile_obj_count, counters, sticky, bits_lo, hist_tile);
-    }
+    if (P == 0) return PG_OK;
+    const uint32_t blocks = (P + EMIT_THREADS - 1) / EMIT_THREADS;  // sized for P; CTAs beyond num_visible exit at once
+    if (keep_all)
+        emit_kernel<true><<<blocks, EMIT_THREADS, 0, stream>>>(perm, cta_base, grp_loc, rnd_off, runs_fix, runs_ovf, ovf_base, srect, P,
+                                                                gx, gy, tkeys, tvals, R_cap, counters, bits_lo, hist_tile);
+    else
+        emit_kernel<false><<<blocks, EMIT_THREADS, 0, stream>>>(perm, cta_base, grp_loc, rnd_off, runs_fix, runs_ovf, ovf_base, srect, P,
+                                                                 gx, gy, tkeys, tvals, R_cap, counters, bits_lo, hist_tile);
     count_launch(1);
     PG_CUDA_CHECK(cudaGetLastError());
     return PG_OK;

@@ -3,10 +3,13 @@
 //
 //   memset(workspace head)                      clear counters, histograms, look-back status
 //   preprocess_kernel                           A.1-A.5, writes GeomRec / depth key / tile rect / radii
-//   hist_kernel + scan_rows_kernel              digit histograms of the depth keys (4 x 8 bit)
-//   onesweep_pass_kernel x4                     P Gaussians by depth (stable; values = index)
-//   emit_kernel                                 tile-row culling + scan + (tile, index) pairs in depth order
-//                                               + digit histograms of the tile sort
+//   compact_hist_kernel + scan_rows_kernel      (depth key, index) of the visible Gaussians in index order + the digit
+//                                               histograms of those keys (4 x 8 bit)
+//   onesweep_pass_kernel x4                     visible Gaussians by depth (stable)
+//   count_kernel + pair_scan_kernel             tile-row runs of every visible Gaussian (row-parallel, kept for emit), pairs per
+//                                               Gaussian -> output offsets, pair count, overflow
+//   emit_kernel                                 (tile, index) pairs in depth order (pure writer) + digit histograms of the
+//                                               tile sort
 //   tile_scan_kernel                            digit bases of the tile sort
 //   onesweep_pass_kernel x2                     stored pairs by tile id (stable)  => reference order; the last
 //                                               pass also reduces the tile ranges (identifyTileRanges)
@@ -51,18 +54,22 @@ struct CompArgs;
 struct PoseDev;
 
 int launch_preprocess(const pg_raster_settings* s, const pg_gaussians* g, const pg_object_table* objs,
-                      int32_t* radii, GeomRec* recs, ushort4* rect, uint32_t* dkey, Counters* counters,
-                      cudaStream_t stream);
+                      int32_t* radii, GeomRec* recs, uint32_t* dkey, Counters* counters, cudaStream_t stream);
 int launch_mark_visible(int P, const float* means, const float* view, uint8_t* present, cudaStream_t stream);
-int launch_hist(const uint32_t* keys, uint32_t n, int npass, uint32_t* hist, cudaStream_t stream);
+int launch_compact_hist(const uint32_t* keys_in, uint32_t n, uint32_t* keys_out, uint32_t* vals_out, uint32_t* hist,
+                        uint32_t* status, uint32_t* ticket, cudaStream_t stream);
 int launch_onesweep_pass(bool iota, bool write_keys, const uint32_t* keys_in, uint32_t* keys_out,
                          const uint32_t* vals_in, uint32_t* vals_out, const uint32_t* n_ptr,
                          uint32_t n_imm, uint32_t max_tiles, int begin_bit, int num_bits,
                          const uint32_t* bin_base, uint32_t* status, uint32_t* ticket, uint2* ranges_raw,
-                         cudaStream_t stream);
-int launch_emit(bool keep_all, const uint32_t* sorted_dkey, const uint32_t* perm, const ushort4* rects, const GeomRec* recs,
-                uint32_t P, uint32_t gx, int W, int H, uint32_t* tkeys, uint32_t* tvals, uint32_t R_cap, uint32_t* status,
-                uint32_t n_env, uint32_t* tile_obj_count, Counters* counters, Sticky* sticky, int bits_lo,
+                         uint32_t n_env, uint32_t* tile_obj_count, cudaStream_t stream);
+int launch_count(bool keep_all, const uint32_t* perm, ushort4* srect, const GeomRec* recs, uint32_t P, int W, int H,
+                 uint32_t* runs_fix, uint32_t* runs_ovf, uint32_t* ovf_base, uint32_t R_cap, uint32_t* rnd_off,
+                 uint32_t* grp_loc, uint32_t* cta_pairs, uint32_t* cta_base, Counters* counters, Sticky* sticky,
+                 cudaStream_t stream);
+int launch_emit(bool keep_all, const uint32_t* perm, const uint32_t* cta_base, const uint32_t* grp_loc, const uint32_t* rnd_off,
+                const uint32_t* runs_fix, const uint32_t* runs_ovf, const uint32_t* ovf_base, const ushort4* srect, uint32_t P,
+                uint32_t gx, int gy, uint32_t* tkeys, uint32_t* tvals, uint32_t R_cap, Counters* counters, int bits_lo,
                 uint32_t* hist_tile, cudaStream_t stream);
 int launch_tile_scan(const uint32_t* hist_tile, uint32_t* bins, Counters* counters, cudaStream_t stream);
 int launch_tile_order(uint2* ranges, uint32_t tiles, uint32_t* order, cudaStream_t stream);
@@ -169,39 +176,43 @@ static int run_binning(const pg_raster_settings* s, const pg_gaussians* g, const
     prof_mark(0, stream);
     PG_CUDA_CHECK(cudaMemsetAsync(at<char>(ws, L.zero_begin), 0, L.zero_end - L.zero_begin, stream));
     prof_mark(1, stream);
-    int rc = launch_preprocess(s, g, objs, radii, at<GeomRec>(ws, L.recs), at<ushort4>(ws, L.rect),
-                               at<uint32_t>(ws, L.dkey_a), counters, stream);
+    int rc = launch_preprocess(s, g, objs, radii, at<GeomRec>(ws, L.recs), at<uint32_t>(ws, L.dkey_a), counters, stream);
     if (rc) return rc;
     if (opts && opts->scene_read_event)  // nothing after this point reads the caller's scene arrays
         PG_CUDA_CHECK(cudaEventRecord((cudaEvent_t)opts->scene_read_event, stream));
     prof_mark(2, stream);
     if (s->debug & 1) PG_CUDA_CHECK(cudaStreamSynchronize(stream));
-    // depth sort: a -> b -> a -> b -> a
+    // depth sort of the VISIBLE Gaussians: compaction a -> b (+ digit histograms), then b -> a -> b -> a -> b
     uint32_t* hist = at<uint32_t>(ws, L.hist_depth);
-    rc = launch_hist(at<uint32_t>(ws, L.dkey_a), (uint32_t)P, 4, hist, stream);
+    uint32_t* ka = at<uint32_t>(ws, L.dkey_b); uint32_t* kb = at<uint32_t>(ws, L.dkey_a);
+    uint32_t* va = at<uint32_t>(ws, L.dval_b); uint32_t* vb = at<uint32_t>(ws, L.dval_a);
+    rc = launch_compact_hist(at<uint32_t>(ws, L.dkey_a), (uint32_t)P, ka, va, hist, at<uint32_t>(ws, L.status_compact),
+                             &counters->tile_counter[7], stream);
     if (rc) return rc;
-    uint32_t* ka = at<uint32_t>(ws, L.dkey_a); uint32_t* kb = at<uint32_t>(ws, L.dkey_b);
-    uint32_t* va = at<uint32_t>(ws, L.dval_a); uint32_t* vb = at<uint32_t>(ws, L.dval_b);
     uint32_t* st = at<uint32_t>(ws, L.status_depth);
     for (int p = 0; p < 4; ++p) {
-        rc = launch_onesweep_pass(p == 0, true, ka, kb, va, vb, nullptr, (uint32_t)P, L.tilesP, 8 * p, 8,
+        rc = launch_onesweep_pass(false, true, ka, kb, va, vb, &counters->num_visible, 0, L.tilesP, 8 * p, 8,
                                   hist + p * RADIX, st + (size_t)p * L.tilesP * RADIX,
-                                  &counters->tile_counter[p], nullptr, stream);
+                                  &counters->tile_counter[p], nullptr, 0, nullptr, stream);
         if (rc) return rc;
         uint32_t* t = ka; ka = kb; kb = t;
         t = va; va = vb; vb = t;
     }
     prof_mark(3, stream);
     if (s->debug & 1) PG_CUDA_CHECK(cudaStreamSynchronize(stream));
-    // after 4 passes the sorted keys/permutation are back in (dkey_a, dval_a) == (ka, va)
+    // after 4 passes the sorted keys / permutation are back in (dkey_b, dval_b) == (ka, va)
     const uint32_t n_env = (objs && objs->num_objects > 0) ? (uint32_t)objs->first[0] : (uint32_t)P;
     const int bits = tile_bits(L.tiles);
     const int bits_lo = (bits + 1) / 2, bits_hi = bits - bits_lo;
-    rc = launch_emit(keep_all, ka, va, at<ushort4>(ws, L.rect), at<GeomRec>(ws, L.recs), (uint32_t)P, gx, W, H,
-                     at<uint32_t>(ws, L.tkey_a),
-                     at<uint32_t>(ws, L.tval_a), (uint32_t)R_cap, at<uint32_t>(ws, L.status_emit),
-                     n_env, at<uint32_t>(ws, L.tile_obj_count), counters, at<Sticky>(ws, L.sticky), bits_lo,
-                     at<uint32_t>(ws, L.hist_tile), stream);
+    rc = launch_count(keep_all, va, at<ushort4>(ws, L.srect), at<GeomRec>(ws, L.recs), (uint32_t)P, W, H,
+                      at<uint32_t>(ws, L.runs_fix), at<uint32_t>(ws, L.runs_ovf), at<uint32_t>(ws, L.ovf_base), (uint32_t)R_cap,
+                      at<uint32_t>(ws, L.rnd_off), at<uint32_t>(ws, L.grp_loc), at<uint32_t>(ws, L.cta_pairs),
+                      at<uint32_t>(ws, L.cta_base), counters, at<Sticky>(ws, L.sticky), stream);
+    if (rc) return rc;
+    rc = launch_emit(keep_all, va, at<uint32_t>(ws, L.cta_base), at<uint32_t>(ws, L.grp_loc), at<uint32_t>(ws, L.rnd_off),
+                     at<uint32_t>(ws, L.runs_fix), at<uint32_t>(ws, L.runs_ovf), at<uint32_t>(ws, L.ovf_base),
+                     at<ushort4>(ws, L.srect), (uint32_t)P, gx, (int)((H + PG_TILE - 1) / PG_TILE), at<uint32_t>(ws, L.tkey_a),
+                     at<uint32_t>(ws, L.tval_a), (uint32_t)R_cap, counters, bits_lo, at<uint32_t>(ws, L.hist_tile), stream);
     if (rc) return rc;
     prof_mark(4, stream);
     rc = launch_tile_scan(at<uint32_t>(ws, L.hist_tile), at<uint32_t>(ws, L.bins_tile), counters, stream);
@@ -215,13 +226,14 @@ static int run_binning(const pg_raster_settings* s, const pg_gaussians* g, const
     uint2* ranges_raw = at<uint2>(ws, L.ranges);
     rc = launch_onesweep_pass(false, two, at<uint32_t>(ws, L.tkey_a), at<uint32_t>(ws, L.tkey_b),
                               at<uint32_t>(ws, L.tval_a), at<uint32_t>(ws, L.tval_b), &counters->sort_n, 0,
-                              L.tilesR, 0, bits_lo, bins, stt, &counters->tile_counter[5], two ? nullptr : ranges_raw, stream);
+                              L.tilesR, 0, bits_lo, bins, stt, &counters->tile_counter[5], two ? nullptr : ranges_raw, n_env,
+                              two ? nullptr : at<uint32_t>(ws, L.tile_obj_count), stream);
     if (rc) return rc;
     if (two) {
         rc = launch_onesweep_pass(false, false, at<uint32_t>(ws, L.tkey_b), at<uint32_t>(ws, L.tkey_a),
                                   at<uint32_t>(ws, L.tval_b), at<uint32_t>(ws, L.tval_a), &counters->sort_n, 0,
                                   L.tilesR, bits_lo, bits_hi, bins + RADIX, stt + (size_t)L.tilesR * RADIX,
-                                  &counters->tile_counter[6], ranges_raw, stream);
+                                  &counters->tile_counter[6], ranges_raw, n_env, at<uint32_t>(ws, L.tile_obj_count), stream);
         if (rc) return rc;
     }
     rc = launch_tile_order(at<uint2>(ws, L.ranges), L.tiles, at<uint32_t>(ws, L.tile_order), stream);

@@ -74,12 +74,24 @@ __device__ __forceinline__ bool block_culled(float gx, float gy, float qa, float
 #define PG_REC_GENERAL 0x40
 #define PG_REC_FLAGS 0x7F
 
+// Tile rectangle of a Gaussian: [min, max) tile columns / rows touched by the square of side 2 radius + 1
+// around the pixel centre, clamped to the grid.  Used by preprocess (radii, pair counts) and by the binning stage,
+// which re-derives the rectangle from the record instead of gathering it from a second array.
+__device__ __forceinline__ ushort4 tile_rect(float pixx, float pixy, int radius, int gx, int gy) {
+    const float fr = (float)radius;
+    int rminx = (int)div(sub(pixx, fr), 16.0f), rminy = (int)div(sub(pixy, fr), 16.0f);
+    int rmaxx = (int)div(add(add(pixx, fr), 15.0f), 16.0f), rmaxy = (int)div(add(add(pixy, fr), 15.0f), 16.0f);
+    rminx = min(gx, max(0, rminx)); rminy = min(gy, max(0, rminy));
+    rmaxx = min(gx, max(0, rmaxx)); rmaxy = min(gy, max(0, rmaxy));
+    return make_ushort4((unsigned short)rminx, (unsigned short)rminy, (unsigned short)rmaxx, (unsigned short)rmaxy);
+}
+
 // ---- per-Gaussian record staged into shared memory by the compositing kernel (48 B) ----------
 struct __align__(16) GeomRec {
     float4 a;  // x, y, conic.x, conic.y
     float4 b;  // conic.z, opacity, depth, cut (power below which alpha < 1/255; mantissa bits 0-5 = object id,
                // bit 6 = PG_REC_GENERAL)
-    float4 c;  // r, g, b, object id (as int bits; 0 = environment, k+1 = object k)
+    float4 c;  // r, g, b, radius in pixels (as int bits: with the pixel centre it gives the tile rectangle, tile_rect())
 };
 
 // ---- status block at the head of the workspace ------------------------------------------------
@@ -88,7 +100,9 @@ struct Counters {
     uint32_t overflow;
     uint32_t num_visible;
     uint32_t sort_n;         // pairs stored = min(pairs kept by the binning stage, pair capacity): what the tile sort processes
-    uint32_t tile_counter[8];  // dynamic CTA-tile tickets: [0..3] depth-sort passes, [4] emit, [5..6] tile-sort passes
+    uint32_t tile_counter[8];  // dynamic CTA-tile tickets: [0..3] depth-sort passes, [5..6] tile-sort passes,
+                               // [7] depth-key compaction
+    uint32_t run_ovf;          // rows beyond RUN_FIX of tall rectangles, allocated in runs_ovf by count_kernel
     unsigned long long stats[8];  // debug&2: pairs evaluated, pairs reaching exp, pairs blended (all chains), pixel slots walked,
                                   // warp-hits: environment, object while a main chain lives, object afterwards; cull passes afterwards
     unsigned long long rendered_full;  // sum of all tile-rectangle areas = the reference's num_rendered
@@ -109,10 +123,8 @@ constexpr int SORT_THREADS = 256;
 constexpr int SORT_IPT = PG_SORT_IPT;
 constexpr int SORT_TILE = SORT_THREADS * SORT_IPT;  // 4096 items per CTA-tile
 constexpr int RADIX = 256;
-#ifndef PG_EMIT_CHUNK
-#define PG_EMIT_CHUNK 512
-#endif
-constexpr int EMIT_CHUNK = PG_EMIT_CHUNK;  // Gaussians per emit CTA (2 per thread)
+constexpr int SCAN_TILE = 2048;  // items per CTA of the depth-key compaction
+constexpr int RUN_FIX = 8;       // tile rows per rectangle with a fixed slot in the run table (taller ones spill)
 
 struct Layout {
     // all offsets in bytes from the workspace base; every region 256-B aligned
@@ -124,17 +136,23 @@ struct Layout {
     size_t ranges;       // uint2[tiles] (cleared: tiles without pairs keep (0,0))
     size_t tile_obj_count; // u32[tiles] pairs whose Gaussian belongs to an object
     size_t status_depth; // u32[4][tilesP][256]
-    size_t status_emit;  // u32[chunks]
+    size_t status_compact; // u32[tilesC] look-back of the depth-key compaction
     size_t status_tile;  // u32[2][tilesR][256]
     size_t zero_end;
     size_t bins_tile;    // u32[2][256] exclusive bases of the two tile-sort passes
     size_t tile_order;   // u32[tiles] tile ids by descending list length (compositing launch order)
     size_t recs;         // GeomRec[P]
-    size_t rect;         // ushort4[P]
+    size_t srect;        // ushort4[P] tile rectangles of the visible Gaussians in depth order (count_kernel -> emit_kernel)
+    size_t ovf_base;     // u32[P] where the rows beyond RUN_FIX of a tall rectangle live in runs_ovf
+    size_t grp_loc;      // u32[ceil(P / 32)] pairs of the count_kernel CTA's groups (32 sorted positions) before each group
+    size_t cta_pairs, cta_base;  // u32[ceil(P / 256)] pairs per count_kernel CTA and their exclusive scan
+    size_t rnd_off;      // u32[ceil(P / 32)][gy] pairs of a group's rounds (32 tile rows) before each round
+    size_t runs_fix;     // u32[P][RUN_FIX] ta | tb << 11 of the first RUN_FIX tile rows of every visible rectangle (depth order)
+    size_t runs_ovf;     // u32[R_cap] the rows beyond RUN_FIX (more rows than the pair capacity count as an overflow)
     size_t dkey_a, dkey_b, dval_a, dval_b;  // u32[P] depth-sort ping-pong
     size_t tkey_a, tkey_b, tval_a, tval_b;  // u32[R_cap] tile-sort ping-pong
     size_t total;
-    uint32_t tiles, tilesP, tilesR, chunks;
+    uint32_t tiles, tilesP, tilesR, tilesC;
 };
 
 inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
@@ -147,8 +165,8 @@ inline Layout make_layout(int P, int W, int H, uint64_t R_cap) {
     if (L.tilesP == 0) L.tilesP = 1;
     L.tilesR = (uint32_t)((R_cap + SORT_TILE - 1) / SORT_TILE);
     if (L.tilesR == 0) L.tilesR = 1;
-    L.chunks = (uint32_t)((P + EMIT_CHUNK - 1) / EMIT_CHUNK);
-    if (L.chunks == 0) L.chunks = 1;
+    L.tilesC = (uint32_t)((P + SCAN_TILE - 1) / SCAN_TILE);
+    if (L.tilesC == 0) L.tilesC = 1;
     size_t o = 0;
     L.sticky = o; o = align_up(o + sizeof(Sticky));
     L.counters = o; o = align_up(o + sizeof(Counters));
@@ -158,13 +176,20 @@ inline Layout make_layout(int P, int W, int H, uint64_t R_cap) {
     L.ranges = o; o = align_up(o + (size_t)L.tiles * 8);
     L.tile_obj_count = o; o = align_up(o + (size_t)L.tiles * 4);
     L.status_depth = o; o = align_up(o + (size_t)4 * L.tilesP * RADIX * 4);
-    L.status_emit = o; o = align_up(o + (size_t)L.chunks * 4);
+    L.status_compact = o; o = align_up(o + (size_t)L.tilesC * 4);
     L.status_tile = o; o = align_up(o + (size_t)2 * L.tilesR * RADIX * 4);
     L.zero_end = o;
     L.bins_tile = o; o = align_up(o + 2 * RADIX * 4);
     L.tile_order = o; o = align_up(o + (size_t)L.tiles * 4);
     L.recs = o; o = align_up(o + (size_t)P * sizeof(GeomRec));
-    L.rect = o; o = align_up(o + (size_t)P * 8);
+    L.srect = o; o = align_up(o + (size_t)P * 8);
+    L.ovf_base = o; o = align_up(o + (size_t)P * 4);
+    L.grp_loc = o; o = align_up(o + ((size_t)P / 32 + 1) * 4);
+    L.cta_pairs = o; o = align_up(o + ((size_t)P / 256 + 1) * 4);
+    L.cta_base = o; o = align_up(o + ((size_t)P / 256 + 1) * 4);
+    L.rnd_off = o; o = align_up(o + ((size_t)P / 32 + 1) * (size_t)gy * 4);
+    L.runs_fix = o; o = align_up(o + (size_t)P * RUN_FIX * 4);
+    L.runs_ovf = o; o = align_up(o + (size_t)R_cap * 4);
     L.dkey_a = o; o = align_up(o + (size_t)P * 4);
     L.dkey_b = o; o = align_up(o + (size_t)P * 4);
     L.dval_a = o; o = align_up(o + (size_t)P * 4);
@@ -186,6 +211,36 @@ inline int tile_bits(uint32_t tiles) {
 
 void set_error(const char* fmt, ...);
 void count_launch(int n);
+
+#if defined(__CUDACC__)
+// Decoupled look-back by ONE WARP, 32 predecessors per step: lane l inspects tile (t - l); the usable prefix of the
+// window ends at the first tile that has published nothing yet or at the first inclusive prefix.  Returns the
+// exclusive prefix of `tile` (all lanes).  Status word: value | flag << SHIFT (0 = nothing, 1 = aggregate, 2 = inclusive).
+template <typename T, int SHIFT>
+__device__ __forceinline__ T warp_lookback(const volatile T* status, uint32_t tile, int lane) {
+    const T kVal = (T(1) << SHIFT) - 1;
+    T prev = 0;
+    int t = (int)tile - 1;
+    while (true) {
+        const int mine = t - lane;
+        const T sv = mine >= 0 ? status[mine] : (T(2) << SHIFT);
+        const uint32_t f = (uint32_t)(sv >> SHIFT);
+        const uint32_t not_ready = __ballot_sync(0xffffffffu, f == 0);
+        const uint32_t incl = __ballot_sync(0xffffffffu, f == 2);
+        const int first_nr = not_ready ? __ffs(not_ready) - 1 : 32;
+        const int first_in = incl ? __ffs(incl) - 1 : 32;
+        const int take = min(first_nr, first_in + 1);  // lanes [0, take)
+        T v = lane < take ? (sv & kVal) : T(0);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        prev += v;
+        if (first_in < first_nr) break;
+        t -= take;
+    }
+    return prev;
+}
+
+#endif
 
 // cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute of a kernel: what has been granted is
 // remembered per (kernel, device) — keyed by the function's address, because kernels with the same signature

@@ -17,22 +17,82 @@ constexpr uint32_t FLAG_AGG = 1u << 30;
 constexpr uint32_t FLAG_INCL = 2u << 30;
 constexpr uint32_t VAL_MASK = (1u << 30) - 1;
 
-// ---- digit histograms of up to 4 passes in one read of the keys --------------------------------
-__global__ void __launch_bounds__(256) hist_kernel(const uint32_t* __restrict__ keys, uint32_t n,
-                                                    int npass, uint32_t* __restrict__ hist /*[npass][256]*/) {
+// ---- depth keys of the VISIBLE Gaussians, compacted in index order, + their digit histograms -----------------
+// preprocess leaves 0xFFFFFFFF in the depth key of every culled Gaussian (41 % of the bench scene).  One pass over
+// the P keys drops them — order preserved, so the stable sort that follows still breaks depth ties by Gaussian
+// index as the reference's does — writes (key, index) pairs and accumulates the 4 x 256 digit histograms of what
+// is kept.  The four onesweep passes then move num_visible items instead of P.
+// CTA-tile = 256 threads x 8 keys, warp-blocked (rank order == memory order); single-value decoupled look-back.
+constexpr int SCAN_IPT = SCAN_TILE / 256;
+
+__global__ void __launch_bounds__(256) compact_hist_kernel(const uint32_t* __restrict__ keys_in, uint32_t n,
+                                                            uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
+                                                            uint32_t* __restrict__ hist /*[4][256]*/,
+                                                            uint32_t* __restrict__ status, uint32_t* __restrict__ ticket) {
     __shared__ uint32_t s_h[4][RADIX];
-    for (int i = threadIdx.x; i < 4 * RADIX; i += blockDim.x) (&s_h[0][0])[i] = 0;
+    __shared__ uint32_t s_warp[8];
+    __shared__ uint32_t s_tile, s_base;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+    for (int i = tid; i < 4 * RADIX; i += 256) (&s_h[0][0])[i] = 0;
     __syncthreads();
-    const uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        uint32_t k = keys[i];
+    const uint32_t tile = s_tile;
+    const uint32_t wbase = tile * SCAN_TILE + warp * (32 * SCAN_IPT) + lane;
+    uint32_t keys[SCAN_IPT], before[SCAN_IPT];  // before: kept items of this warp ahead of item i of this lane
+    uint32_t wcount = 0;
+    const uint32_t lt = (1u << lane) - 1u;
 #pragma unroll
-        for (int p = 0; p < 4; ++p)
-            if (p < npass) atomicAdd(&s_h[p][(k >> (8 * p)) & 255], 1u);
+    for (int i = 0; i < SCAN_IPT; ++i) {
+        const uint32_t idx = wbase + i * 32;
+        keys[i] = idx < n ? keys_in[idx] : 0xFFFFFFFFu;
+    }
+#pragma unroll
+    for (int i = 0; i < SCAN_IPT; ++i) {
+        const bool keep = keys[i] != 0xFFFFFFFFu;
+        const uint32_t m = __ballot_sync(0xffffffffu, keep);
+        before[i] = wcount + __popc(m & lt);
+        wcount += __popc(m);
+        if (keep) {
+#pragma unroll
+            for (int p = 0; p < 4; ++p) atomicAdd(&s_h[p][(keys[i] >> (8 * p)) & 255u], 1u);
+        }
+    }
+    if (lane == 0) s_warp[warp] = wcount;
+    __syncthreads();
+    if (warp == 0) {
+        // warp 0: exclusive scan of the 8 warp counts, then the look-back over the tiles with earlier tickets
+        const uint32_t c = lane < 8 ? s_warp[lane] : 0u;
+        uint32_t x = c;
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        const uint32_t total = __shfl_sync(0xffffffffu, x, 7);
+        __syncwarp();
+        if (lane < 8) s_warp[lane] = x - c;
+        volatile uint32_t* st = status;
+        uint32_t excl = 0;
+        if (tile == 0) {
+            if (lane == 0) st[0] = total | FLAG_INCL;
+        } else {
+            if (lane == 0) st[tile] = total | FLAG_AGG;
+            excl = warp_lookback<uint32_t, 30>(st, tile, lane);
+            if (lane == 0) st[tile] = ((excl + total) & VAL_MASK) | FLAG_INCL;
+        }
+        if (lane == 0) s_base = excl;
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < npass * RADIX; i += blockDim.x) {
-        uint32_t c = (&s_h[0][0])[i];
+    const uint32_t base = s_base + s_warp[warp];
+#pragma unroll
+    for (int i = 0; i < SCAN_IPT; ++i) {
+        if (keys[i] != 0xFFFFFFFFu) {
+            keys_out[base + before[i]] = keys[i];
+            vals_out[base + before[i]] = wbase + i * 32;
+        }
+    }
+    for (int i = tid; i < 4 * RADIX; i += 256) {
+        const uint32_t c = (&s_h[0][0])[i];
         if (c) atomicAdd(&hist[i], c);
     }
 }
@@ -61,7 +121,8 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, uint32_t* __restrict_
                      const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ vals_out,
                      const uint32_t* __restrict__ n_ptr, uint32_t n_imm, int begin_bit, int num_bits,
                      const uint32_t* __restrict__ bin_base, uint32_t* __restrict__ status,
-                     uint32_t* __restrict__ ticket, uint2* __restrict__ ranges_raw) {
+                     uint32_t* __restrict__ ticket, uint2* __restrict__ ranges_raw, uint32_t n_env,
+                     uint32_t* __restrict__ tile_obj_count) {
     constexpr int WARPS = SORT_THREADS / 32;
     // s_warp_pos[w][d]: first the number of digit-d items of warp w (early counts), then the running
     // position inside the CTA-tile's digit-sorted staging buffer where warp w's next digit-d item goes
@@ -195,29 +256,51 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, uint32_t* __restrict_
     }
     __syncthreads();
     // ---- coalesced store: staging position j of digit d goes to (global start of d) + (j - CTA start of d)
-    for (uint32_t j = tid; j < tile_n; j += SORT_THREADS) {
-        uint32_t k = s_keys[j];
-        uint32_t d = (k >> begin_bit) & mask;
-        uint32_t dst = s_gbase[d] + j;
-        if (WRITE_KEYS) keys_out[dst] = k;
-        vals_out[dst] = s_vals[j];
+    for (uint32_t j0 = 0; j0 < tile_n; j0 += SORT_THREADS) {
+        const uint32_t j = j0 + tid;
+        const bool valid = j < tile_n;
+        uint32_t k = 0, v = 0, dst = 0;
+        if (valid) {
+            k = s_keys[j];
+            v = s_vals[j];
+            const uint32_t d = (k >> begin_bit) & mask;
+            dst = s_gbase[d] + j;
+            if (WRITE_KEYS) keys_out[dst] = k;
+            vals_out[dst] = v;
+        }
         // Last pass of the tile sort (keys are whole tile ids): identifyTileRanges happens here.  Where the id
         // changes inside this CTA-tile's staging buffer, a run of that id starts / ends at a known output
         // position; the tile's range is the union over CTA-tiles: max of the ends, min of the starts (kept
         // bit-inverted, so that the per-frame clear to zero is the identity of both reductions).
         if (ranges_raw) {
-            if (j == 0 || s_keys[j - 1] != k) atomicMax(&ranges_raw[k].x, ~dst);
-            if (j + 1 == tile_n || s_keys[j + 1] != k) atomicMax(&ranges_raw[k].y, dst + 1u);
+            const bool head = valid && (j == 0 || s_keys[j - 1] != k);
+            if (head) atomicMax(&ranges_raw[k].x, ~dst);
+            if (valid && (j + 1 == tile_n || s_keys[j + 1] != k)) atomicMax(&ranges_raw[k].y, dst + 1u);
+            // un-culled OBJECT pairs per tile (the compositing producer stops scanning a list once it has seen them
+            // all): counted per run of equal ids inside the warp's 32 staging positions — one atomic per run that
+            // holds objects instead of one per object pair (3.8 M atomics on ~1500 hot words cost the emit kernel
+            // 0.1 ms when it did this)
+            if (tile_obj_count) {
+                const bool is_obj = valid && !(v & PG_CULL_FLAG) && v >= n_env;
+                const uint32_t heads = __ballot_sync(0xffffffffu, head || (valid && lane == 0));
+                const uint32_t objm = __ballot_sync(0xffffffffu, is_obj);
+                if (valid && (heads >> lane & 1u)) {
+                    const uint32_t later = heads & ~((2u << lane) - 1u);      // heads after this lane
+                    const uint32_t seg = (later ? ((1u << (__ffs(later) - 1)) - 1u) : 0xFFFFFFFFu) & ~((1u << lane) - 1u);
+                    const uint32_t c = __popc(objm & seg);
+                    if (c) atomicAdd(&tile_obj_count[k], c);
+                }
+            }
         }
     }
 }
 
-int launch_hist(const uint32_t* keys, uint32_t n, int npass, uint32_t* hist, cudaStream_t stream) {
+int launch_compact_hist(const uint32_t* keys_in, uint32_t n, uint32_t* keys_out, uint32_t* vals_out, uint32_t* hist,
+                        uint32_t* status, uint32_t* ticket, cudaStream_t stream) {
     if (n == 0) return PG_OK;
-    int blocks = (int)min((uint32_t)(PG_SM_COUNT * 8), (n + 255u) / 256u);
-    hist_kernel<<<blocks, 256, 0, stream>>>(keys, n, npass, hist);
+    compact_hist_kernel<<<(n + SCAN_TILE - 1) / SCAN_TILE, 256, 0, stream>>>(keys_in, n, keys_out, vals_out, hist, status, ticket);
     PG_CUDA_CHECK(cudaGetLastError());
-    scan_rows_kernel<<<npass, 256, 0, stream>>>(hist);
+    scan_rows_kernel<<<4, 256, 0, stream>>>(hist);
     count_launch(2);
     PG_CUDA_CHECK(cudaGetLastError());
     return PG_OK;
@@ -228,17 +311,17 @@ int launch_onesweep_pass(bool iota, bool write_keys, const uint32_t* keys_in, ui
                          const uint32_t* vals_in, uint32_t* vals_out, const uint32_t* n_ptr,
                          uint32_t n_imm, uint32_t max_tiles, int begin_bit, int num_bits,
                          const uint32_t* bin_base, uint32_t* status, uint32_t* ticket, uint2* ranges_raw,
-                         cudaStream_t stream) {
+                         uint32_t n_env, uint32_t* tile_obj_count, cudaStream_t stream) {
     if (max_tiles == 0) return PG_OK;
     dim3 grid(max_tiles), block(SORT_THREADS);
     if (iota && write_keys)
-        onesweep_pass_kernel<true, true><<<grid, block, 0, stream>>>(keys_in, keys_out, vals_in, vals_out, n_ptr, n_imm, begin_bit, num_bits, bin_base, status, ticket, ranges_raw);
+        onesweep_pass_kernel<true, true><<<grid, block, 0, stream>>>(keys_in, keys_out, vals_in, vals_out, n_ptr, n_imm, begin_bit, num_bits, bin_base, status, ticket, ranges_raw, n_env, tile_obj_count);
     else if (!iota && write_keys)
-        onesweep_pass_kernel<false, true><<<grid, block, 0, stream>>>(keys_in, keys_out, vals_in, vals_out, n_ptr, n_imm, begin_bit, num_bits, bin_base, status, ticket, ranges_raw);
+        onesweep_pass_kernel<false, true><<<grid, block, 0, stream>>>(keys_in, keys_out, vals_in, vals_out, n_ptr, n_imm, begin_bit, num_bits, bin_base, status, ticket, ranges_raw, n_env, tile_obj_count);
     else if (!iota && !write_keys)
-        onesweep_pass_kernel<false, false><<<grid, block, 0, stream>>>(keys_in, keys_out, vals_in, vals_out, n_ptr, n_imm, begin_bit, num_bits, bin_base, status, ticket, ranges_raw);
+        onesweep_pass_kernel<false, false><<<grid, block, 0, stream>>>(keys_in, keys_out, vals_in, vals_out, n_ptr, n_imm, begin_bit, num_bits, bin_base, status, ticket, ranges_raw, n_env, tile_obj_count);
     else
-        onesweep_pass_kernel<true, false><<<grid, block, 0, stream>>>(keys_in, keys_out, vals_in, vals_out, n_ptr, n_imm, begin_bit, num_bits, bin_base, status, ticket, ranges_raw);
+        onesweep_pass_kernel<true, false><<<grid, block, 0, stream>>>(keys_in, keys_out, vals_in, vals_out, n_ptr, n_imm, begin_bit, num_bits, bin_base, status, ticket, ranges_raw, n_env, tile_obj_count);
     PG_CUDA_CHECK(cudaGetLastError());
     count_launch(1);
     return PG_OK;
