@@ -87,8 +87,10 @@ STAGE_NAMES = ["clear", "preprocess", "depth_sort", "emit", "tile_scan", "tile_s
 _LIB = None
 
 # Process-wide default of pg_launch_opts.numerics for calls that do not name one (set_numerics() / PG_NUMERICS).
+# "fast" by default: the reference's own CUDA expf is MUFU-based too, so neither mode is bit-identical to it, and both
+# stay inside its tolerances; "exact" makes the images bit-reproducible on the CPU oracle (what the parity tests pin).
 _NUMERICS = {"exact": NUMERICS_EXACT, "fast": NUMERICS_FAST}
-_default_numerics = _NUMERICS.get(os.environ.get("PG_NUMERICS", "exact").lower(), NUMERICS_EXACT)
+_default_numerics = _NUMERICS.get(os.environ.get("PG_NUMERICS", "fast").lower(), NUMERICS_FAST)
 
 
 def set_numerics(mode: str) -> None:

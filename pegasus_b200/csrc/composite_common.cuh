@@ -77,7 +77,7 @@ struct CompArgs {
     uint32_t* out_n_contrib;
     // masks
     uint32_t n_env;                 // Gaussian indices >= n_env belong to objects
-    const uint32_t* tile_obj_count; // [tiles] number of un-culled object pairs per tile
+    const uint32_t* tile_obj_count; // [tiles][OBJ_SPREAD] partial counts of the un-culled object pairs per tile
     int num_objects, num_colors;
     float eff_color[PG_MAX_OBJECTS][3];  // colour the rasterizer produces for object k's flat SH
     float set_color[PG_MAX_COLORS][3];   // colour set the masks are tested against
@@ -180,7 +180,13 @@ template <bool MASKS, int COMP_STAGES, int NCW, int WAITNS>
 __device__ __forceinline__ void composite_producer(const CompArgs& a, CompSmemT<COMP_STAGES>& sm, const int tile,
                                                    const uint2 range, const int n, const int lane, const uint32_t lt) {
     // =========================== PRODUCER ===========================
-    int obj_left = MASKS ? (int)a.tile_obj_count[tile] : 0;  // un-culled object entries not yet compacted
+    int obj_left = 0;  // un-culled object entries not yet compacted
+    if (MASKS) {
+        const uint4* oc = reinterpret_cast<const uint4*>(a.tile_obj_count + (size_t)tile * OBJ_SPREAD);
+        static_assert(OBJ_SPREAD == 8, "two 16-byte loads");
+        const uint4 c0 = oc[0], c1 = oc[1];
+        obj_left = (int)(c0.x + c0.y + c0.z + c0.w + c1.x + c1.y + c1.z + c1.w);
+    }
     // id chunks are fetched by TMA from a 16-byte aligned base; entries outside [range.x, range.y) are ignored
     const uint32_t a0 = range.x & ~3u;
     const int span = (int)(range.y - a0);

@@ -124,6 +124,7 @@ constexpr int SORT_IPT = PG_SORT_IPT;
 constexpr int SORT_TILE = SORT_THREADS * SORT_IPT;  // 4096 items per CTA-tile
 constexpr int RADIX = 256;
 constexpr int SCAN_TILE = 2048;  // items per CTA of the depth-key compaction
+constexpr int OBJ_SPREAD = 8;    // partial per-tile object counters (hot words serialise in L2)
 constexpr int RUN_FIX = 8;       // tile rows per rectangle with a fixed slot in the run table (taller ones spill)
 
 struct Layout {
@@ -134,7 +135,8 @@ struct Layout {
     size_t hist_depth;   // u32[4][256]  depth-sort digit histograms -> exclusive bases
     size_t hist_tile;    // u32[2][256] digit histograms of the two tile-sort passes
     size_t ranges;       // uint2[tiles] (cleared: tiles without pairs keep (0,0))
-    size_t tile_obj_count; // u32[tiles] pairs whose Gaussian belongs to an object
+    size_t tile_obj_count; // u32[tiles][OBJ_SPREAD] un-culled pairs whose Gaussian belongs to an object (partial counts:
+                           // the last sort pass spreads its atomics over OBJ_SPREAD words per tile)
     size_t status_depth; // u32[4][tilesP][256]
     size_t status_compact; // u32[tilesC] look-back of the depth-key compaction
     size_t status_tile;  // u32[2][tilesR][256]
@@ -174,7 +176,7 @@ inline Layout make_layout(int P, int W, int H, uint64_t R_cap) {
     L.hist_depth = o; o = align_up(o + 4 * RADIX * 4);
     L.hist_tile = o; o = align_up(o + 2 * RADIX * 4);
     L.ranges = o; o = align_up(o + (size_t)L.tiles * 8);
-    L.tile_obj_count = o; o = align_up(o + (size_t)L.tiles * 4);
+    L.tile_obj_count = o; o = align_up(o + (size_t)L.tiles * OBJ_SPREAD * 4);
     L.status_depth = o; o = align_up(o + (size_t)4 * L.tilesP * RADIX * 4);
     L.status_compact = o; o = align_up(o + (size_t)L.tilesC * 4);
     L.status_tile = o; o = align_up(o + (size_t)2 * L.tilesR * RADIX * 4);

@@ -288,7 +288,7 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, uint32_t* __restrict_
                     const uint32_t later = heads & ~((2u << lane) - 1u);      // heads after this lane
                     const uint32_t seg = (later ? ((1u << (__ffs(later) - 1)) - 1u) : 0xFFFFFFFFu) & ~((1u << lane) - 1u);
                     const uint32_t c = __popc(objm & seg);
-                    if (c) atomicAdd(&tile_obj_count[k], c);
+                    if (c) atomicAdd(&tile_obj_count[k * OBJ_SPREAD + ((tile + warp) & (OBJ_SPREAD - 1))], c);
                 }
             }
         }

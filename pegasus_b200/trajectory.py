@@ -153,3 +153,25 @@ def pose_deltas(trajectory: Mapping, object_id, timestep: int) -> Tuple[np.ndarr
     R1, t1 = _step(trajectory, object_id, timestep)
     R0, t0 = _step(trajectory, object_id, timestep - 1)
     return R1 @ R0.T, t1 - t0
+
+
+def replay_recorded_drop(t: np.ndarray, q: np.ndarray, num_objects: int, num_frames: int, stride: int = 1,
+                         stagger: int = 20, ring: float = 0.28) -> Dict[str, Dict[str, Dict[str, list]]]:
+    """A K-object trajectory dict in the reference's JSON layout (`[body][step]{t, q}`, q as x,y,z,w —
+    src/engine/physical_simulation.py / src/gs/pegasus_setup.py:160-196) made from ONE recorded body: object k
+    replays the recording (every `stride`-th step) starting `k * stagger` steps later and shifted to a ring of radius
+    `ring` metres, so K objects drop and tumble one after the other.  The recording is the reference's own
+    src/engine/simulation_steps.json, body 1 (committed excerpt: tests/golden/simulation_body1.npz)."""
+    t = np.asarray(t, dtype=np.float64)
+    q = np.asarray(q, dtype=np.float64)
+    n = t.shape[0]
+    traj: Dict[str, Dict[str, Dict[str, list]]] = {}
+    for k in range(num_objects):
+        ang = 2.0 * np.pi * k / max(num_objects, 1)
+        shift = np.array([ring * np.cos(ang), ring * np.sin(ang), 0.0]) - np.array([t[-1, 0], t[-1, 1], 0.0])
+        body = {}
+        for f in range(num_frames):
+            i = min(max(f * stride - k * stagger, 0), n - 1)
+            body[str(f)] = {"t": list(t[i] + shift), "q": list(q[i])}
+        traj[str(k + 1)] = body
+    return traj
