@@ -55,6 +55,11 @@ def parse_args():
     ap.add_argument("--gpu-baseline-frames", type=int, default=10)
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--ref-seconds", type=float, default=150.0, help="cap of the --impl reference run")
+    ap.add_argument("--numerics", default="fast", choices=["fast", "exact"],
+                    help="compositing numerics of the timed legs (the product default is fast)")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the sub-records (exact numerics, pose / pack stages, passes/s, dynamic C3, 4K stress C4)")
+    ap.add_argument("--extra-frames", type=int, default=30, help="timed frames of the dynamic / 4K sub-records")
     return ap.parse_args()
 
 
@@ -80,14 +85,17 @@ def build_clouds(spec):
 
 
 def object_poses(spec, n_frames):
-    """Absolute poses per frame: list over frames of [(R, t)] * K."""
-    from pegasus_b200 import synth
-    from pegasus_b200.sh_rotation import quat_xyzw_to_rotation
+    """Absolute poses per frame: list over frames of [(R, t)] * K.  Dynamic workload (configs[2]): the reference's own
+    PyBullet recording (src/engine/simulation_steps.json, body 1; committed excerpt tests/golden/simulation_body1.npz)
+    replayed for K objects with per-object time / space offsets through the product's pose schedule
+    (pegasus_b200.trajectory: dynamic_object_pose / update_object_pose of src/gs/pegasus_setup.py:160-196)."""
+    from pegasus_b200 import synth, trajectory
     K = spec["objects"]
     if not spec["dynamic"]:
         return [synth.static_poses(K, seed=4000)]
-    traj = synth.drop_trajectory(K, n_frames, seed=4000)
-    return [[(quat_xyzw_to_rotation(traj[f, k, 3:]), traj[f, k, :3]) for k in range(K)] for f in range(n_frames)]
+    g = np.load(os.path.join(ROOT, "tests", "golden", "simulation_body1.npz"))
+    traj = trajectory.replay_recorded_drop(g["t"], g["q"], num_objects=K, num_frames=n_frames)
+    return trajectory.dynamic_object_poses(traj, list(range(1, K + 1)), n_frames)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -160,13 +168,14 @@ def measured_peaks():
 N_BANDS = 17  # 1080p has 68 tile rows -> 4 rows per band
 
 
-def cpu_reference_frames_per_s(spec, env, objs, cams, poses0, budget_s, bands_per_frame=2, max_frames=None,
+def cpu_reference_frames_per_s(spec, env, objs, cams, poses0, budget_s, bands_per_frame=None, max_frames=None,
                                first_view=0):
-    """Times the reference's K+3 passes (oracle: C + OpenMP restatement) on a bounded sample.
-    Per sampled frame: the fixed part (scene merges, activations, per-Gaussian stage of all K+3
-    passes over the full scene) runs once and is timed whole; binning + compositing + mask tests are
-    timed on `bands_per_frame` bands of tile rows (offset rotates with the frame) and scaled to the
-    frame.  Returns (frames/s, description, frames sampled, seconds spent)."""
+    """Times the reference's K+3 passes (oracle: C + OpenMP restatement) frame by frame until `max_frames` frames or
+    `budget_s` seconds.  bands_per_frame=None (default): every frame is rendered WHOLE (all tile rows of all K+3
+    passes) and its time is what was measured.  bands_per_frame=n: a bounded sample — the fixed part (scene merges,
+    activations, per-Gaussian stage of all K+3 passes over the full scene) is timed whole, binning + compositing +
+    mask tests on n bands of tile rows (offset rotates with the frame) and scaled to the frame.
+    Returns (frames/s, description, frames done, seconds spent, seconds per frame as measured or estimated)."""
     import oracle
     W, H = spec["width"], spec["height"]
     colors = oracle.generate_colors(max(spec["objects"], 1))
@@ -183,24 +192,31 @@ def cpu_reference_frames_per_s(spec, env, objs, cams, poses0, budget_s, bands_pe
     while True:
         c = cams[(first_view + frames) % len(cams)]
         ocam = oracle.camera(c["R"], c["T"], c["FoVx"], c["FoVy"], W, H)
-        nb = min(bands_per_frame, len(bands))
-        pick = [bands[(frames * 5 + j * (len(bands) // nb)) % len(bands)] for j in range(nb)]
+        if bands_per_frame is None:
+            pick = bands
+        else:
+            nb = min(bands_per_frame, len(bands))
+            pick = [bands[(frames * 5 + j * (len(bands) // nb)) % len(bands)] for j in range(nb)]
         t0 = time.perf_counter()
         t_fixed, t_bands = oracle.frame_reference_split(ocam, env, posed, colors, bg, pick)
-        spent += time.perf_counter() - t0
+        dt = time.perf_counter() - t0
+        spent += dt
         rows_done = sum(b[1] - b[0] for b in pick)
-        est.append(t_fixed + sum(t_bands) * rows / rows_done)
+        # a whole frame costs what the call took; a sample is scaled from its bands
+        est.append(dt if bands_per_frame is None else t_fixed + sum(t_bands) * rows / rows_done)
         frames += 1
         if max_frames is not None and frames >= max_frames:
             break
-        if spent >= budget_s:
+        if spent + est[-1] > budget_s:   # the next frame would not fit
             break
     fps = len(est) / sum(est)
-    desc = (f"{frames} frames; per frame the reference's K+3={spec['objects'] + 3} passes: merges + activations + "
-            f"per-Gaussian stage over the full {spec['env_n'] + spec['objects'] * spec['obj_n']}-Gaussian scene timed "
-            f"whole, binning + compositing + mask tests timed on {bands_per_frame} bands of {per}/{rows} tile rows "
-            f"({W}x{H}) and scaled by rows/rows_sampled; band offsets rotate with the frame, views follow the orbit")
-    return fps, desc, frames, spent
+    what = (f"{frames} WHOLE frames" if bands_per_frame is None else
+            f"{frames} frames, binning + compositing + mask tests timed on {bands_per_frame} bands of {per}/{rows} tile rows "
+            f"and scaled by rows/rows_sampled (band offsets rotate with the frame)")
+    desc = (f"{what}; per frame the reference's K+3={spec['objects'] + 3} passes: merges + activations + per-Gaussian stage "
+            f"+ binning + compositing + mask tests over the full {spec['env_n'] + spec['objects'] * spec['obj_n']}-Gaussian "
+            f"scene ({W}x{H}), views follow the orbit")
+    return fps, desc, frames, spent, est
 
 
 def use_host_cores(oracle):
@@ -234,7 +250,9 @@ _REAL_STDOUT = [None]
 
 def run_reference(args):
     """--impl reference: the reference's algorithm for the path on the host cores (oracle port: the
-    reference's own rasterizer is CUDA-only and absent from the tree, so there is no oracle/_ref)."""
+    reference's own rasterizer is CUDA-only and absent from the tree, so there is no oracle/_ref).
+    Every step is one WHOLE frame (all K+3 passes over the full scene, all tile rows); the run stops after
+    --steps frames or when the next frame would exceed --ref-seconds, and reports the steps it really did."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -244,22 +262,25 @@ def run_reference(args):
     env, objs, cams = build_clouds(spec)
     poses0 = object_poses(spec, 1)[0]
     cores = oracle.num_threads()
-    # warm-up bands are run and discarded
-    n_warm = min(args.warmup, 1)
+    t_all = time.perf_counter()
+    n_warm = min(max(args.warmup, 0), 1)   # one whole frame (~10 s) warms caches and the OpenMP pool
     if n_warm > 0:
-        cpu_reference_frames_per_s(spec, env, objs, cams, poses0, 0.0, bands_per_frame=1, max_frames=n_warm)
-    fps, desc, steps, secs = cpu_reference_frames_per_s(spec, env, objs, cams, poses0, args.ref_seconds,
-                                                        bands_per_frame=2, max_frames=args.steps, first_view=n_warm)
+        cpu_reference_frames_per_s(spec, env, objs, cams, poses0, 0.0, max_frames=n_warm)
+    budget = max(args.ref_seconds - (time.perf_counter() - t_all), 0.0)
+    fps, desc, steps, secs, per_frame = cpu_reference_frames_per_s(spec, env, objs, cams, poses0, budget,
+                                                                   max_frames=max(args.steps, 1), first_view=n_warm)
     line = {
         "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-        "warmup": n_warm, "ms_per_step": 1e3 / fps, "higher_is_better": True,
+        "warmup": n_warm, "ms_per_step": 1e3 * secs / steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {k: spec[k] for k in ("workload", "env_n", "objects", "obj_n", "views", "width", "height")},
         "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-        "note": "each step is one frame estimated from a bounded sample (see cpu_baseline.sample); "
-                "%.1f s of CPU time were spent on %d steps" % (secs, steps),
+        "steps_requested": args.steps, "warmup_requested": args.warmup,
+        "note": "every step is one whole frame, timed as run (no extrapolation); %d of the %d requested steps and %d of "
+                "the %d requested warm-up steps fit into --ref-seconds %.0f (%.1f s of CPU time on %d threads)"
+                % (steps, args.steps, n_warm, args.warmup, args.ref_seconds, secs, cores),
     }
     emit_line(line)
 
@@ -267,78 +288,91 @@ def run_reference(args):
 # ----------------------------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------------------------
-def run_ours(args):
+FP32_LANES_MEASURED = 116.4  # FMA lane-ops / clk / SM that packed FP32 (FFMA2) sustains on B200: tools/microbench/ffma2.cu,
+                             # profiles/r1z_microbench_ffma2.txt (128 nominal lanes; scalar FFMA with register operands: 79)
+
+
+class Workload:
+    """One composed scene + its views + pose packets, resident on this rank's GPU."""
+
+    def __init__(self, spec, args, dev, rank, world, n_frames, env=None):
+        import colorsys
+        import torch
+        from pegasus_b200 import Camera, ComposedScene, dist as pgd, synth
+        from pegasus_b200.sh_rotation import generate_pose_packets
+        self.spec, self.dev, self.rank, self.world = spec, dev, rank, world
+        Wd, Hd = spec["width"], spec["height"]
+        self.env = env if env is not None else synth.make_env(spec["env_n"], seed=1000)
+        self.objs = {i + 1: synth.make_object(spec["obj_n"], seed=2000 + i) for i in range(spec["objects"])}
+        self.cams_h = synth.orbit_cameras(spec["views"], Wd, Hd, seed=3000)
+        # semantic colours: generate_colors(n) of src/utility/graphic_utils.py:40-60 (BGR order)
+        ncol = max(spec["objects"], 1)
+        self.colors = np.asarray([colorsys.hls_to_rgb(i / ncol, 0.6, 0.7)[::-1] for i in range(ncol)], dtype=np.float32)
+        self.scene = ComposedScene(self.env, self.objs, self.colors, device=dev, sh_mode="rotate")
+        self.cams = [Camera(c["R"], c["T"], c["FoVx"], c["FoVy"], Wd, Hd, device=dev) for c in self.cams_h]
+        self.bg = torch.zeros(3, device=dev)
+        K = self.K = spec["objects"]
+        # pose packets: built on rank 0, NCCL-broadcast, consumed straight from the receive buffer
+        self.n_pose_frames = n_frames * world if spec["dynamic"] else 1
+        self.packets = torch.zeros((self.n_pose_frames, max(K, 1), 103), dtype=torch.float32, device=dev)
+        self.packets_host = torch.zeros((self.n_pose_frames, max(K, 1), 103), dtype=torch.float32).pin_memory()
+        if rank == 0 and K:
+            for f, poses in enumerate(object_poses(spec, self.n_pose_frames)):
+                self.packets_host[f] = torch.from_numpy(generate_pose_packets(poses, self.scene.pivots, rotate_sh=True))
+            self.packets.copy_(self.packets_host)
+        pgd.broadcast_pose_packets(self.packets, src=0)
+        if world > 1:
+            self.packets_host.copy_(self.packets)  # every rank keeps the host copy for its e2e leg
+        if K:
+            self.scene.apply_pose_packets(self.packets[0])
+
+    # frames of this rank: global frame g = i * world + rank
+    def view_of(self, i):
+        return self.cams[(i * self.world + self.rank) % len(self.cams)]
+
+    def pose_of(self, i):
+        return self.packets[(i * self.world + self.rank) % self.n_pose_frames]
+
+
+def measure(wl, K_steps, W_steps, numerics, want_stats=True, want_e2e=True):
+    """Device-resident frames/s (frames in flight), per-stage times with one frame in flight, end-to-end frames/s
+    through DatasetGenerator — of one Workload.  Returns a dict."""
     import torch
-    from pegasus_b200 import Camera, ComposedScene, _lib, dist as pgd
-    from pegasus_b200.rasterizer import _PAIR_CAPACITY_HINT, workspace_for
-    from pegasus_b200.sh_rotation import generate_pose_packets
-
-    if not torch.cuda.is_available():
-        raise RuntimeError("bench.py needs a CUDA device (there is no CPU path); use --impl reference for the CPU arm")
-    rank, world, local = pgd.init_from_env()
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
+    from pegasus_b200 import DatasetGenerator, _lib, dist as pgd
+    from pegasus_b200.rasterizer import _PAIR_CAPACITY_HINT
     L = _lib.load()
-    spec = workload_spec(args)
-    K_steps, W_steps = args.steps, max(args.warmup, 0)
-    Wd, Hd = spec["width"], spec["height"]
+    spec, scene, dev, rank, world, bg = wl.spec, wl.scene, wl.dev, wl.rank, wl.world, wl.bg
+    Wd, Hd, Kobj = spec["width"], spec["height"], wl.K
+    dynamic = spec["dynamic"] and Kobj > 0
+    res = {}
 
-    env, objs, cams_h = build_clouds(spec)
-    # semantic colours: generate_colors(n) of src/utility/graphic_utils.py:40-60 (BGR order)
-    import colorsys
-    ncol = max(spec["objects"], 1)
-    colors = np.asarray([colorsys.hls_to_rgb(i / ncol, 0.6, 0.7)[::-1] for i in range(ncol)], dtype=np.float32)
-    scene = ComposedScene(env, objs, colors, device=dev, sh_mode="rotate")
-    cams = [Camera(c["R"], c["T"], c["FoVx"], c["FoVy"], Wd, Hd, device=dev) for c in cams_h]
-    bg = torch.zeros(3, device=dev)
-    Kobj = spec["objects"]
-
-    # ---- pose packets: built on rank 0, NCCL-broadcast, consumed straight from the receive buffer
-    n_pose_frames = (W_steps + K_steps) * world if spec["dynamic"] else 1
-    packets = torch.zeros((n_pose_frames, max(Kobj, 1), 103), dtype=torch.float32, device=dev)
-    packets_host = torch.zeros((n_pose_frames, max(Kobj, 1), 103), dtype=torch.float32).pin_memory()
-    if rank == 0 and Kobj:
-        for f, poses in enumerate(object_poses(spec, n_pose_frames)):
-            packets_host[f] = torch.from_numpy(generate_pose_packets(poses, scene.pivots, rotate_sh=True))
-        packets.copy_(packets_host)
-    pgd.broadcast_pose_packets(packets, src=0)
-    if world > 1:
-        packets_host.copy_(packets)  # every rank keeps the host copy for its e2e leg
-    if Kobj:
-        scene.apply_pose_packets(packets[0])
-
-    # frames of this rank: global frame g = i*world + rank
-    def view_of(i):
-        return cams[(i * world + rank) % len(cams)]
-
-    def pose_of(i):
-        return packets[(i * world + rank) % n_pose_frames]
-
-    # ---- calibration (setup, untimed): pair capacity = 1.05 x max R over the views this rank renders
+    # ---- calibration (setup, untimed): pair capacity = 1.05 x max stored pairs over the views this rank renders
     out = scene.alloc_outputs(Wd, Hd, masks=True)
     max_R = 0
-    n_cal = min(len(cams), W_steps + K_steps)
+    n_cal = min(len(wl.cams), W_steps + K_steps)
     for i in range(n_cal):
-        if spec["dynamic"] and Kobj:
-            scene.apply_pose_packets(pose_of(i))
-        o = scene.render(view_of(i), bg, masks=True, out=out, sync_check=True)
+        if dynamic:
+            scene.apply_pose_packets(wl.pose_of(i))
+        o = scene.render(wl.view_of(i), bg, masks=True, out=out, sync_check=True, numerics=numerics)
         max_R = max(max_R, o["num_stored"])
     cap = int(max_R * 1.05) + 4096
     _PAIR_CAPACITY_HINT[(Wd, Hd)] = cap
-    # compositing statistics per view (untimed): pairs evaluated / exp'd / blended
+    res["pair_capacity"] = cap
+    # compositing statistics per view (untimed, exact-arithmetic counting kernel): pairs evaluated / exp'd / blended
     stats = []
-    for i in range(min(n_cal, 8)):
-        if spec["dynamic"] and Kobj:
-            scene.apply_pose_packets(pose_of(i))
-        scene.render(view_of(i), bg, masks=True, out=out, sync_check=True, pair_capacity=cap, debug=2)
+    for i in range(min(n_cal, 8) if want_stats else 1):
+        if dynamic:
+            scene.apply_pose_packets(wl.pose_of(i))
+        scene.render(wl.view_of(i), bg, masks=True, out=out, sync_check=True, pair_capacity=cap, debug=2)
         st = scene.read_stats()
         st.update(num_rendered=out["num_rendered"], num_visible=out["num_visible"], num_stored=out["num_stored"])
         stats.append(st)
+    res["stats"] = stats
 
-    def frame(i, sync_check=False):
-        if spec["dynamic"] and Kobj:
-            scene.apply_pose_packets(pose_of(i))
-        scene.render(view_of(i), bg, masks=True, out=out, sync_check=sync_check, pair_capacity=cap)
+    def frame(i, nm=numerics, masks=True, o=out):
+        if dynamic:
+            scene.apply_pose_packets(wl.pose_of(i))
+        scene.render(wl.view_of(i), bg, masks=masks, out=o, sync_check=False, pair_capacity=cap, numerics=nm)
 
     # ---- device-resident timing: NSLOT frames in flight (one CUDA stream + workspace + output set per
     # slot), the way a dataset generator renders a sequence: frame i+1's per-Gaussian / binning stages
@@ -358,20 +392,21 @@ def run_ours(args):
     def frame_on_slot(i):
         sl = i % NSLOT
         with torch.cuda.stream(streams[sl]):
-            if spec["dynamic"] and Kobj:
+            if dynamic:
                 # the pose kernel rewrites rows the PREVIOUS frame's per-Gaussian stage reads (other stream);
                 # that frame's later stages never touch the scene arrays again
                 if frames_issued[0] > 0:
                     streams[sl].wait_event(read_ev[(i - 1) % NSLOT])
-                scene.apply_pose_packets(pose_of(i))
-            scene.render(view_of(i), bg, masks=True, out=slot_out[sl], sync_check=False, pair_capacity=cap, slot=sl,
-                         scene_read_event=read_ev[sl] if (spec["dynamic"] and Kobj) else None,
-                         composite_stream=comp_streams[sl])
+                scene.apply_pose_packets(wl.pose_of(i))
+            scene.render(wl.view_of(i), bg, masks=True, out=slot_out[sl], sync_check=False, pair_capacity=cap, slot=sl,
+                         scene_read_event=read_ev[sl] if dynamic else None, composite_stream=comp_streams[sl],
+                         numerics=numerics)
             frames_issued[0] += 1
 
     for sl in range(NSLOT):  # size every slot's workspace before timing
         with torch.cuda.stream(streams[sl]):
-            scene.render(view_of(0), bg, masks=True, out=slot_out[sl], sync_check=True, pair_capacity=cap, slot=sl)
+            scene.render(wl.view_of(0), bg, masks=True, out=slot_out[sl], sync_check=True, pair_capacity=cap, slot=sl,
+                         numerics=numerics)
     torch.cuda.synchronize()
     for i in range(W_steps):
         frame_on_slot(i)
@@ -379,7 +414,7 @@ def run_ours(args):
     overflow0 = [scene.read_status(slot=sl)["overflow_frames"] for sl in range(NSLOT)]
     pgd.barrier()
     launches0 = int(L.pg_launch_count())
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(dev.index)
     sampler.start()
     time.sleep(0.25)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -398,79 +433,121 @@ def run_ours(args):
     torch.cuda.synchronize()
     pgd.barrier()
     ms = ev0.elapsed_time(ev1)
-    launches = int(L.pg_launch_count()) - launches0
-    clocks = sampler.stop()
+    res["gpu_launches"] = int(L.pg_launch_count()) - launches0
+    res["clocks"] = sampler.stop()
     for sl in range(NSLOT):  # sticky counter: covers every frame rendered on the slot since `overflow0` was taken
         if scene.read_status(slot=sl)["overflow_frames"] != overflow0[sl]:
             raise RuntimeError("pair capacity overflowed inside the timed region; the measurement is invalid")
-    # per-stage kernel durations: the same frames once more with ONE frame in flight (with several in
-    # flight a pair of CUDA events around one kernel also covers other frames' kernels)
-    K_seq = min(K_steps, 50)
-    _lib.check(L.pg_profile_enable(K_seq), "pg_profile_enable")
-    seq0, seq1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    seq0.record(main)
-    for i in range(W_steps, W_steps + K_seq):
-        frame(i)
-    seq1.record(main)
-    torch.cuda.synchronize()
-    seq_ms_per_step = seq0.elapsed_time(seq1) / K_seq
-    stage_ms = np.zeros((K_seq, _lib.NUM_STAGES), dtype=np.float32)
-    buf = (C.c_float * _lib.NUM_STAGES)()
-    for f in range(int(L.pg_profile_frames())):
-        _lib.check(L.pg_profile_read(f, buf), "pg_profile_read")
-        stage_ms[f] = np.frombuffer(buf, dtype=np.float32)
-    L.pg_profile_enable(0)
     ms_max = pgd.max_over_ranks(ms, device=dev)
-    value = world * K_steps / (ms_max / 1e3)
+    res.update(value=world * K_steps / (ms_max / 1e3), ms_per_step=ms_max / K_steps, nslot=NSLOT, split=bool(SPLIT))
+
+    # ---- per-stage kernel durations: the same frames once more with ONE frame in flight (with several in
+    # flight a pair of CUDA events around one kernel also covers other frames' kernels)
+    def staged_pass(nm, masks=True, n=None):
+        n = n or min(K_steps, 50)
+        o = out if masks else scene.alloc_outputs(Wd, Hd, masks=False)
+        _lib.check(L.pg_profile_enable(n), "pg_profile_enable")
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record(main)
+        for i in range(W_steps, W_steps + n):
+            frame(i, nm, masks, o)
+        s1.record(main)
+        torch.cuda.synchronize()
+        stage_ms = np.zeros((n, _lib.NUM_STAGES), dtype=np.float32)
+        buf = (C.c_float * _lib.NUM_STAGES)()
+        for f in range(int(L.pg_profile_frames())):
+            _lib.check(L.pg_profile_read(f, buf), "pg_profile_read")
+            stage_ms[f] = np.frombuffer(buf, dtype=np.float32)
+        L.pg_profile_enable(0)
+        return s0.elapsed_time(s1) / n, stage_ms.mean(axis=0)
+
+    res["seq_ms_per_step"], res["stage_ms"] = staged_pass(numerics)
+    res["staged_pass"] = staged_pass
 
     # ---- end-to-end timing through the public API (pegasus_b200.DatasetGenerator, the generate_dataset loop
     # of pegasus.py:247-390): per frame the camera + pose packets are copied from pinned host memory, the pose
-    # kernel and the fused frame run, the products are packed (u8 RGB, u16 depth mm, u8 masks) and copied back to
+    # kernel and the fused frame run, the products are packed (u8 RGB, u16 depth mm, bit masks) and copied back to
     # pinned host memory; NSLOT frames in flight, one stream per slot.  No PNG encoding (host-side, not this path).
-    from pegasus_b200 import DatasetGenerator
-    gen = DatasetGenerator(scene, Wd, Hd, bg=bg, frames_in_flight=NSLOT, overlap_compositing=SPLIT)
-    gen.pair_capacity = cap  # calibrated above; the slots' workspaces are already sized
-    nc = colors.shape[0]
+    if want_e2e:
+        gen = DatasetGenerator(scene, Wd, Hd, bg=bg, frames_in_flight=NSLOT, overlap_compositing=SPLIT, numerics=numerics)
+        gen.pair_capacity = cap  # calibrated above; the slots' workspaces are already sized
 
-    def e2e_inputs(first_local, count):
-        """Global frame list [first_local*world, (first_local+count)*world): cameras + per-frame host pose packets."""
-        gl = range(first_local * world, (first_local + count) * world)
-        cam_list = [cams[g % len(cams)] for g in gl]
-        pk = torch.stack([packets_host[g % n_pose_frames] for g in gl]) if Kobj else None
-        return cam_list, pk
+        def e2e_inputs(first_local, count):
+            """Global frame list [first_local*world, (first_local+count)*world): cameras + per-frame host pose packets."""
+            gl = range(first_local * world, (first_local + count) * world)
+            cam_list = [wl.cams[g % len(wl.cams)] for g in gl]
+            pk = torch.stack([wl.packets_host[g % wl.n_pose_frames] for g in gl]) if Kobj else None
+            return cam_list, pk
 
-    h2d = 35 * 4 + (Kobj * 103 * 4 if Kobj else 0)
-    d2h = gen.d2h_bytes_per_frame
-    checksum = [0]
+        checksum = [0]
 
-    def on_frame(f, prods):
-        if f == 0:
-            checksum[0] = int(prods["rgb"].astype(np.int64).sum()) + int(prods["visible"].astype(np.int64).sum())
+        def on_frame(f, prods):
+            if f == 0:
+                checksum[0] = int(prods["rgb"].astype(np.int64).sum()) + int(prods["visible"].astype(np.int64).sum())
 
-    if W_steps:
-        cl, pk = e2e_inputs(0, W_steps)
-        gen.generate(cl, pose_packets=pk, rank=rank, world=world)
-    cl, pk = e2e_inputs(W_steps, K_steps)
-    torch.cuda.synchronize()
-    pgd.barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(main)
-    t_wall = time.perf_counter()
-    st = gen.generate(cl, pose_packets=pk, rank=rank, world=world)  # returns when every frame's products are on the host
-    t_wall = time.perf_counter() - t_wall
-    e1.record(main)
-    torch.cuda.synchronize()
-    pgd.barrier()
-    assert st["frames"] == K_steps
-    e2e_ms = pgd.max_over_ranks(max(e0.elapsed_time(e1), t_wall * 1e3), device=dev)
-    e2e_value = world * K_steps / (e2e_ms / 1e3)
-    gen.generate(cl[:world], pose_packets=None if pk is None else pk[:world], rank=rank, world=world, on_frame=on_frame)
-    checksum = checksum[0]
+        if W_steps:
+            cl, pk = e2e_inputs(0, W_steps)
+            gen.generate(cl, pose_packets=pk, rank=rank, world=world)
+        cl, pk = e2e_inputs(W_steps, K_steps)
+        torch.cuda.synchronize()
+        pgd.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(main)
+        t_wall = time.perf_counter()
+        st = gen.generate(cl, pose_packets=pk, rank=rank, world=world)  # returns when every frame's products are on the host
+        t_wall = time.perf_counter() - t_wall
+        e1.record(main)
+        torch.cuda.synchronize()
+        pgd.barrier()
+        assert st["frames"] == K_steps
+        e2e_ms = pgd.max_over_ranks(max(e0.elapsed_time(e1), t_wall * 1e3), device=dev)
+        gen.generate(cl[:world], pose_packets=None if pk is None else pk[:world], rank=rank, world=world, on_frame=on_frame)
+        res["e2e"] = {"value": world * K_steps / (e2e_ms / 1e3), "unit": UNIT,
+                      "h2d_bytes_per_step": 35 * 4 + (Kobj * 103 * 4 if Kobj else 0),
+                      "d2h_bytes_per_step": gen.d2h_bytes_per_frame, "ms_per_step": e2e_ms / K_steps,
+                      "checksum": checksum[0]}
+        res["gen"] = gen
+    return res
+
+
+def time_launches(fn, n, stream):
+    """Mean milliseconds of n back-to-back calls of fn() on `stream` (CUDA events, after 3 warm-up calls)."""
+    import torch
+    for _ in range(3):
+        fn()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(stream)
+    for _ in range(n):
+        fn()
+    b.record(stream)
+    b.synchronize()
+    return a.elapsed_time(b) / n
+
+
+def run_ours(args):
+    import torch
+    from pegasus_b200 import _lib, dist as pgd
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (there is no CPU path); use --impl reference for the CPU arm")
+    rank, world, local = pgd.init_from_env()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    L = _lib.load()
+    _lib.set_numerics(args.numerics)
+    spec = workload_spec(args)
+    K_steps, W_steps = args.steps, max(args.warmup, 0)
+    Wd, Hd = spec["width"], spec["height"]
+    wl = Workload(spec, args, dev, rank, world, W_steps + K_steps)
+    scene, Kobj = wl.scene, wl.K
+    m = measure(wl, K_steps, W_steps, args.numerics)
+    NSLOT, SPLIT, cap, stats = m["nslot"], m["split"], m["pair_capacity"], m["stats"]
+    main = torch.cuda.current_stream(dev)
 
     # ---- roofline per stage (rank 0's numbers)
     hbm_peak, sm_max_mhz, peak_src = measured_peaks()
     P = scene.P
-    mean_stage = stage_ms.mean(axis=0)
+    mean_stage = m["stage_ms"]
     mR = float(np.mean([s["num_rendered"] for s in stats]))
     mV = float(np.mean([s["num_visible"] for s in stats]))
     mS = float(np.mean([s["num_stored"] for s in stats]))  # pairs that can contribute: stored + sorted
@@ -478,14 +555,18 @@ def run_ours(args):
     tiles = ((Wd + 15) // 16) * ((Hd + 15) // 16)
     alg_bytes = {
         "preprocess": 284.0 * mV + 16.0 * (P - mV),
-        "depth_sort": (4.0 + 4 * 16.0) * P,
-        "emit": 4.0 * P + 76.0 * mV + 8.0 * mS,
+        # compaction: 4 B read per Gaussian, 8 B written per visible one; 4 passes x (8 read + 8 written) per visible one
+        "depth_sort": 4.0 * P + 8.0 * mV + 4 * 16.0 * mV,
+        # count: 4 B index + 48 B record read, 8 B rectangle + <= 32 B runs written per visible Gaussian;
+        # emit: 4 + 8 + 32 B read per visible Gaussian, 8 B written per pair
+        "emit": (52.0 + 40.0 + 44.0) * mV + 8.0 * mS,
         "tile_scan": 4.0 * tiles + 8.0 * tiles,
         "tile_sort": (16.0 + 12.0) * mS,
     }
     # FP32 work of compositing: 11 flop to evaluate a pair, +27 when it reaches exp(), +14 when blended
     comp_flop = 11.0 * ev_ + 27.0 * ex_ + 14.0 * bl_
-    fp32_peak = 148 * 128 * 2 * sm_max_mhz * 1e6 / 1e12  # TFLOP/s, derived from clocks.max.sm
+    fp32_nominal = 148 * 128 * 2 * sm_max_mhz * 1e6 / 1e12  # TFLOP/s, from clocks.max.sm
+    fp32_peak = 148 * FP32_LANES_MEASURED * 2 * sm_max_mhz * 1e6 / 1e12  # what packed FP32 sustains (microbenchmark)
     stages = []
     for j, name in enumerate(_lib.STAGE_NAMES):
         t = float(mean_stage[j])
@@ -496,7 +577,7 @@ def run_ours(args):
         elif name == "composite" and t > 0:
             tf = comp_flop / (t * 1e-3) / 1e12
             e.update(bound="fp32", achieved=tf, peak=fp32_peak, unit="TFLOP/s", frac=tf / fp32_peak,
-                     pair_evals_per_s=ev_ / (t * 1e-3))
+                     frac_of_nominal=tf / fp32_nominal, pair_evals_per_s=ev_ / (t * 1e-3))
         stages.append(e)
     dom = max(stages, key=lambda e: e["ms"])
     traffic = None
@@ -506,25 +587,67 @@ def run_ours(args):
             traffic = json.load(open(tp)).get(dom["stage"])
         except Exception:
             traffic = None
-    roofline = {"kernel": {"composite": "composite2_kernel<MASKS> (2 pixels per thread, packed FP32)", "tile_sort": "onesweep_pass_kernel (tile id)",
-                           "depth_sort": "onesweep_pass_kernel (depth)", "preprocess": "preprocess_kernel",
-                           "emit": "emit_kernel"}.get(dom["stage"], dom["stage"]),
+    roofline = {"kernel": {"composite": "composite3_kernel<MASKS> (2 pixels per thread, packed FP32, %s numerics)" % args.numerics,
+                           "tile_sort": "onesweep_pass_kernel (tile id)", "depth_sort": "onesweep_pass_kernel (depth)",
+                           "preprocess": "preprocess_kernel", "emit": "count_kernel + emit_kernel"}.get(dom["stage"], dom["stage"]),
                 "bound": dom.get("bound"), "achieved": dom.get("achieved"), "peak": dom.get("peak"),
                 "unit": dom.get("unit"), "frac": dom.get("frac"), "traffic": traffic,
                 "peak_source": peak_src if dom.get("bound") == "hbm" else
-                "derived: 148 SM x 128 FP32 lanes x 2 flop x clocks.max.sm (no FP32 figure in MEASURED_PEAKS.json)",
+                "measured: 148 SM x %.1f FMA lanes/clk/SM (packed-FP32 microbenchmark, profiles/r1z_microbench_ffma2.txt; 128 "
+                "nominal -> %.1f TFLOP/s, frac_of_nominal beside it) x 2 flop x clocks.max.sm" % (FP32_LANES_MEASURED, fp32_nominal),
                 "ms_per_launch": dom["ms"], "share_of_step": dom["share"],
                 "timing": "CUDA events around each stage on the launching stream, averaged over a pass of the "
                           "same frames with one frame in flight (%.3f ms/frame); the timed region keeps %d frames "
-                          "in flight, where stages of different frames overlap" % (seq_ms_per_step, NSLOT)}
+                          "in flight, where stages of different frames overlap" % (m["seq_ms_per_step"], NSLOT)}
+
+    extras = {}
+    if rank == 0 and world == 1 and not args.no_extras:
+        # ---- the other numerics mode on the same frames (one frame in flight)
+        other = "exact" if args.numerics == "fast" else "fast"
+        seq_o, st_o = m["staged_pass"](other)
+        extras["numerics_" + other] = {"sequential_ms_per_step": seq_o, "composite_ms": float(st_o[_lib.STAGE_NAMES.index("composite")]),
+                                       "what": "exact: every float op an individually rounded IEEE op, exp as an FMA polynomial, images "
+                                               "bit-identical to the CPU oracle; fast: MUFU ex2 + one blend weight per Gaussian"}
+        # ---- passes/s of the plain 3-tuple API's work (RGB + depth + radii of the merged scene, no mask chains)
+        seq_p, st_p = m["staged_pass"](args.numerics, masks=False)
+        extras["single_pass"] = {"passes_per_s": 1e3 / seq_p, "ms_per_pass": seq_p,
+                                 "composite_ms": float(st_p[_lib.STAGE_NAMES.index("composite")]),
+                                 "what": "one rasterization of the merged %d-Gaussian scene (what GaussianRasterizer.forward "
+                                         "does per call), one pass in flight" % P}
+        # ---- pose and packing kernels (HBM-bound streaming kernels around the frame)
+        if Kobj:
+            n_obj = P - scene.n_env
+            t = time_launches(lambda: scene.apply_pose_packets(wl.packets[0]), 50, main)
+            gbs = 416.0 * n_obj / (t * 1e-3) / 1e9
+            stages.append({"stage": "pose", "ms": t, "share": None, "bound": "hbm", "achieved": gbs, "peak": hbm_peak,
+                           "unit": "GB/s", "frac": gbs / hbm_peak,
+                           "what": "pg_pose_apply: %d object Gaussians x 416 B (means, quaternions, 45 SH coefficients read and "
+                                   "written)" % n_obj})
+        o = scene.alloc_outputs(Wd, Hd, masks=True)
+        scene.render(wl.view_of(0), wl.bg, masks=True, out=o, sync_check=True, pair_capacity=cap)
+        nc = int(scene.color_set.shape[0])
+        rgb8 = torch.empty((Hd, Wd, 3), dtype=torch.uint8, device=dev)
+        d16 = torch.empty((Hd, Wd), dtype=torch.int16, device=dev)
+        bits = torch.empty((nc, Hd, (Wd + 7) // 8), dtype=torch.uint8, device=dev)
+        vp = lambda x: C.c_void_p(x.data_ptr())
+        t = time_launches(lambda: _lib.check(L.pg_pack_frame(Wd, Hd, vp(o["color"]), vp(o["depth"]), vp(rgb8), vp(d16),
+                                                             C.c_void_p(main.cuda_stream)), "pg_pack_frame"), 50, main)
+        gbs = (16.0 + 5.0) * Wd * Hd / (t * 1e-3) / 1e9
+        stages.append({"stage": "pack_frame", "ms": t, "share": None, "bound": "hbm", "achieved": gbs, "peak": hbm_peak,
+                       "unit": "GB/s", "frac": gbs / hbm_peak, "what": "16 B read + 5 B written per pixel"})
+        t = time_launches(lambda: _lib.check(L.pg_pack_masks(Wd, Hd, nc, vp(o["visible"]), vp(bits),
+                                                             C.c_void_p(main.cuda_stream)), "pg_pack_masks"), 50, main)
+        gbs = (1.0 + 1.0 / 8) * nc * Wd * Hd / (t * 1e-3) / 1e9
+        stages.append({"stage": "pack_masks", "ms": t, "share": None, "bound": "hbm", "achieved": gbs, "peak": hbm_peak,
+                       "unit": "GB/s", "frac": gbs / hbm_peak, "what": "per plane 1 B read + 1 bit written per pixel; x2 per frame"})
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         import oracle
         use_host_cores(oracle)
         poses0 = object_poses(spec, 1)[0]
-        fps, desc, steps, secs = cpu_reference_frames_per_s(spec, env, objs, cams_h, poses0, args.cpu_seconds,
-                                                            bands_per_frame=3, max_frames=2)
+        fps, desc, steps, secs, _ = cpu_reference_frames_per_s(spec, wl.env, wl.objs, wl.cams_h, poses0, args.cpu_seconds,
+                                                               max_frames=1)
         cpu_baseline = {"value": fps, "unit": UNIT, "cores": oracle.num_threads(), "kind": "port",
                         "sample": desc, "seconds": secs}
 
@@ -541,52 +664,113 @@ def run_ours(args):
                       depth=torch.empty((1, Hd, Wd), dtype=torch.float32, device=dev),
                       radii=torch.empty((max(n, 1),), dtype=torch.int32, device=dev)) for n in sizes]
         if Kobj:
-            scene.apply_pose_packets(packets[0])
+            scene.apply_pose_packets(wl.packets[0])
         for i in range(2):  # warm-up: buffer growth
-            baseline.reference_frame(brast, scene, cams[i % len(cams)], bg, outs=bouts)
+            baseline.reference_frame(brast, scene, wl.cams[i % len(wl.cams)], wl.bg, outs=bouts)
         nb = max(1, args.gpu_baseline_frames)
         b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
         b0.record(main)
         pairs = 0
         for i in range(nb):
-            res = baseline.reference_frame(brast, scene, cams[(W_steps + i) % len(cams)], bg, outs=bouts)
+            res = baseline.reference_frame(brast, scene, wl.cams[(W_steps + i) % len(wl.cams)], wl.bg, outs=bouts)
             pairs += res[0]["num_rendered"]
         b1.record(main)
         torch.cuda.synchronize()
         bms = b0.elapsed_time(b1) / nb
+        # one pass over the merged scene alone: the apples-to-apples kernel comparison for single_pass above
+        import math as _m
+        def one_pass(i):
+            cm = wl.cams[(W_steps + i) % len(wl.cams)]
+            brast.forward(scene.means3D, scene.shs, scene.opacity, scene.scales, scene.rotations, cm.world_view_transform,
+                          cm.full_proj_transform, cm.camera_center, wl.bg, Wd, Hd, _m.tan(cm.FoVx * 0.5), _m.tan(cm.FoVy * 0.5),
+                          out=bouts[0])
+        one_pass(0)
+        torch.cuda.synchronize()
+        b0.record(main)
+        for i in range(nb):
+            one_pass(i)
+        b1.record(main)
+        torch.cuda.synchronize()
+        pms = b0.elapsed_time(b1) / nb
         gpu_baseline = {"value": 1e3 / bms, "unit": UNIT, "ms_per_step": bms, "frames": nb, "kind": "restatement",
                         "passes_per_frame": Kobj + 3, "pairs_full_scene_pass": pairs / nb,
+                        "single_pass": {"passes_per_s": 1e3 / pms, "ms_per_pass": pms},
                         "what": "baseline/upstream_style.cu: restatement of the public CUDA forward rasterizer the "
                                 "reference pins as a submodule (source absent from the reference tree), sm_100a build, "
                                 "CUB scan/sort; K+3 rasterizer passes per frame as src/gs/render.py issues them, "
                                 "scene merges / activations / CPU mask tests NOT included"}
 
+    # ---- the other GPU configurations of BASELINE.json as sub-records (short runs, same measurement code)
+    if rank == 0 and world == 1 and not args.no_extras:
+        del m["staged_pass"]
+        m.pop("gen", None)
+        n_x = max(args.extra_frames, 6)
+        try:
+            # configs[2]: dynamic scene, 10 objects, a new pose packet (the reference's PyBullet recording) and a pose-kernel
+            # launch every frame
+            a3 = argparse.Namespace(**vars(args))
+            a3.workload, a3.objects, a3.obj_n = "dynamic", 10, 100_000
+            s3 = workload_spec(a3)
+            del wl.scene
+            torch.cuda.empty_cache()
+            w3 = Workload(s3, a3, dev, rank, world, 3 + n_x, env=wl.env)
+            m3 = measure(w3, n_x, 3, args.numerics, want_stats=False)
+            extras["dynamic_c3"] = {"workload": s3["workload"], "value": m3["value"], "unit": UNIT, "steps": n_x, "warmup": 3,
+                                    "e2e": m3["e2e"]["value"], "sequential_ms_per_step": m3["seq_ms_per_step"],
+                                    "poses": "reference recording src/engine/simulation_steps.json body 1 (tests/golden/"
+                                             "simulation_body1.npz), 10 staggered replays, one pose packet + pose kernel per frame"}
+            del w3, m3
+            torch.cuda.empty_cache()
+        except Exception as e:  # a sub-record must never take the headline down
+            extras["dynamic_c3"] = {"error": repr(e)}
+        try:
+            # configs[3]: large-environment stress, 6 M Gaussians at 3840x2160
+            a4 = argparse.Namespace(**vars(args))
+            a4.workload, a4.objects, a4.obj_n, a4.env_n, a4.width, a4.height, a4.views = "tabletop", 3, 150_000, 6_000_000, 3840, 2160, 24
+            s4 = workload_spec(a4)
+            w4 = Workload(s4, a4, dev, rank, world, 3 + n_x)
+            m4 = measure(w4, n_x, 3, args.numerics, want_stats=False)
+            names = _lib.STAGE_NAMES
+            extras["stress_4k_c4"] = {"workload": s4["workload"], "value": m4["value"], "unit": UNIT, "steps": n_x, "warmup": 3,
+                                      "e2e": m4["e2e"]["value"], "sequential_ms_per_step": m4["seq_ms_per_step"],
+                                      "stage_ms": {names[j]: float(m4["stage_ms"][j]) for j in range(len(names))}}
+            del w4, m4
+            torch.cuda.empty_cache()
+        except Exception as e:
+            extras["stress_4k_c4"] = {"error": repr(e)}
+
     if rank == 0:
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K_steps, "warmup": W_steps,
-            "ms_per_step": ms_max / K_steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "metric": METRIC, "value": m["value"], "unit": UNIT, "n_gpus": world, "steps": K_steps, "warmup": W_steps,
+            "ms_per_step": m["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": dict({k: spec[k] for k in ("workload", "env_n", "objects", "obj_n", "views", "width", "height")},
                            parallelism=f"view-parallel x{world} (scene replicated, frames round-robin, pose packets NCCL-broadcast); "
                                        f"{NSLOT} frames in flight per GPU (one workspace + "
                                        + ("a high-priority binning stream and a normal-priority compositing stream"
                                           if SPLIT else "one stream") + " per slot)",
-                           frames_in_flight=NSLOT, split_compositing_stream=bool(SPLIT),
+                           frames_in_flight=NSLOT, split_compositing_stream=bool(SPLIT), numerics=args.numerics,
                            cache="inputs larger than L2 (scene parameters 0.7 GB per frame vs 126 MB L2)",
-                           pair_capacity=cap, pairs_per_frame=mR, stored_pairs_per_frame=mS, visible_per_frame=mV),
-            "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_ms / K_steps, "checksum": checksum},
-            "gpu_launches": launches,
+                           pair_capacity=cap, pairs_per_frame=mR, stored_pairs_per_frame=mS, visible_per_frame=mV,
+                           pose_kernel_in_value=bool(spec["dynamic"]),
+                           note="tabletop poses are static: `value` times the fused frame only (the scene is posed once at "
+                                "set-up); `e2e` also runs the pose kernel, the packing kernels and the copies every frame"),
+            "clocks": m["clocks"],
+            "e2e": m["e2e"],
+            "gpu_launches": m["gpu_launches"],
             "roofline": roofline,
             "roofline_stages": stages,
-            "sequential_ms_per_step": seq_ms_per_step,
+            "sequential_ms_per_step": m["seq_ms_per_step"],
             "compositing_stats": {"pairs_evaluated": ev_, "pairs_reaching_exp": ex_, "pairs_blended": bl_,
-                                  "pixel_slots_walked": float(np.mean([s.get("pixel_slots", 0) for s in stats]))},
+                                  "pixel_slots_walked": float(np.mean([s.get("pixel_slots", 0) for s in stats])),
+                                  "warp_hits_env": float(np.mean([s.get("hits_env", 0) for s in stats])),
+                                  "warp_hits_obj_main": float(np.mean([s.get("hits_obj_main", 0) for s in stats])),
+                                  "warp_hits_obj_after": float(np.mean([s.get("hits_obj_after", 0) for s in stats]))},
             "cpu_baseline": cpu_baseline,
             "gpu_baseline": gpu_baseline,
         }
+        line.update(extras)
         emit_line(line)
     if world > 1:
         import torch.distributed as dist

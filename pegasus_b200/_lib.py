@@ -116,9 +116,11 @@ def load():
     global _LIB
     if _LIB is not None:
         return _LIB
-    path = os.environ.get("PG_LIB_PATH") or _build.OUT  # PG_LIB_PATH: a tuning build of the same sources
-    if not os.path.exists(path):
-        path = _build.build()  # raises if nvcc is unavailable or compilation fails
+    path = os.environ.get("PG_LIB_PATH")  # a tuning build of the same sources
+    if not path:
+        # (re)built when missing or when the sources it was built from have changed (content hash beside the .so);
+        # raises if nvcc is unavailable or compilation fails — there is nothing to fall back to
+        path = _build.build()
     L = C.CDLL(path)
     L.pg_version.restype = C.c_char_p
     L.pg_last_error.restype = C.c_char_p

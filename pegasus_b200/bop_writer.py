@@ -7,7 +7,10 @@ threaded `write_training_data` call of /root/reference/pegasus.py:333-365:
     <root>/<dataset>/train/<scene:06d>/{rgb,depth,mask,mask_visib,sem_mask}/<frame:06d>[_<idx:06d>].png
     <root>/<dataset>/train/<scene:06d>/scene_camera.json, scene_gt.json
 
-Differences, all on the host and none in file content:
+Differences, all on the host and none in file content — with ONE exception: out-of-range values saturate
+(`pg_pack_frame` clamps RGB * 255 to [0, 255] and depth * 1000 to [0, 65535]) where the reference's
+`.astype("uint8")` / `.astype(np.uint16)` wrap modulo 256 / 65536 (pegasus.py:340-358), which turns a pixel brighter
+than 1.0 dark; a deliberate deviation, pinned by tests/test_gpu_generate.py::test_pack_kernel_saturates.  Otherwise:
   * images arrive already packed by the GPU (`pg_pack_frame`: u8 RGB HWC, u16 depth in mm; masks
     u8 0/1 from the fused compositing pass), so no float image crosses PCIe and no numpy norm runs;
   * the per-object oriented bounding box is computed ONCE per object (ObjectMeta), not re-read from

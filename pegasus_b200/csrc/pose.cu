@@ -182,7 +182,10 @@ __global__ void pack_kernel(int W, int H, const float* __restrict__ color, const
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             float v = mul(color[c * HW + i], 255.0f);
-            // numpy's float -> uint8 cast on the host: truncation (values are in [0,255])
+            // numpy's float -> uint8 cast on the host truncates; for values in [0, 256) this is it.  DELIBERATE
+            // DEVIATION outside that range: the reference's (rgb * 255).astype("uint8") wraps modulo 256 (a pixel
+            // brighter than 1.0 — SH colours are clamped only below — comes out dark), depth beyond 65.535 m wraps
+            // modulo 65536; here both saturate.  Pinned by tests/test_gpu_generate.py.
             v = fminf(fmaxf(v, 0.0f), 255.0f);
             rgb_u8[3 * i + c] = (uint8_t)(int)v;
         }

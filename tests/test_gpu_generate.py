@@ -95,6 +95,27 @@ def test_pack_kernel_matches_reference_host_conversion():
     np.testing.assert_array_equal(o16.cpu().numpy().view(np.uint16), np.array(G["pack_depth_u16"], dtype=np.uint16))
 
 
+def test_pack_kernel_saturates():
+    """Out of range the reference's host casts wrap (uint8: modulo 256, uint16: modulo 65536); pg_pack_frame saturates
+    instead — the one deliberate difference in file content (bop_writer.py header)."""
+    import ctypes as C
+    from pegasus_b200 import _lib
+    d = torch.device("cuda", 0)
+    H, W = 2, 4
+    vals = torch.tensor([-0.2, 0.0, 0.5, 1.0, 1.004, 1.3, 2.0, 300.0], dtype=torch.float32)
+    color = vals.reshape(1, H, W).repeat(3, 1, 1).contiguous().to(d)
+    dep = torch.tensor([-1.0, 0.0, 0.0005, 1.2345, 65.535, 65.6, 100.0, 1e6], dtype=torch.float32).reshape(1, H, W).to(d)
+    o8 = torch.empty((H, W, 3), dtype=torch.uint8, device=d)
+    o16 = torch.empty((H, W), dtype=torch.int16, device=d)
+    L = _lib.load()
+    st = torch.cuda.current_stream(d)
+    _lib.check(L.pg_pack_frame(W, H, C.c_void_p(color.data_ptr()), C.c_void_p(dep.data_ptr()), C.c_void_p(o8.data_ptr()),
+                               C.c_void_p(o16.data_ptr()), C.c_void_p(st.cuda_stream)), "pg_pack_frame")
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(o8.cpu().numpy()[..., 0].reshape(-1), [0, 0, 127, 255, 255, 255, 255, 255])
+    np.testing.assert_array_equal(o16.cpu().numpy().view(np.uint16).reshape(-1), [0, 0, 0, 1234, 65535, 65535, 65535, 65535])
+
+
 @pytest.mark.parametrize("mode", ["dynamic", "static"])
 def test_pipelined_generation_equals_sequential_frames(mode, tmp_path):
     import cv2
