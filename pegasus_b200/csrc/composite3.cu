@@ -76,7 +76,8 @@ __device__ __forceinline__ bool block_culled_fast(float gx, float gy, float qa, 
 
 constexpr int QSTRIDE = COMP_BATCH + 16;  // bytes of one warp's hit queue (entry indices; 0xFF = no second hit)
 
-// Dynamic shared memory: CompSmem | hit queues [COMP2_CW][QSTRIDE] | (MASKS) eff[PG_MAX_OBJECTS] float4 {colour the
+// Dynamic shared memory: CompSmem | hit queues [COMP2_CW][QSTRIDE] | (MASKS) per-warp, per-object boxes
+// [COMP2_CW][PG_MAX_OBJECTS] float4 | (MASKS) eff[PG_MAX_OBJECTS] float4 {colour the
 // rasterizer produces for object k's flat SH, silhouette decision threshold} | Tk2[K][128] float2 — the standalone
 // transmittance of object k at the two pixels of each lane (slot = warp * 32 + lane).
 template <bool MASKS, bool NCONTRIB, bool FAST, int COMP_STAGES, int MINB>
@@ -85,7 +86,8 @@ __global__ void __launch_bounds__(COMP2_THREADS, MINB) composite3_kernel(const C
     extern __shared__ __align__(128) unsigned char smem_raw[];
     CompSmem& sm = *reinterpret_cast<CompSmem*>(smem_raw);
     constexpr int kQueueOff = (int)((sizeof(CompSmem) + 15) / 16 * 16);
-    constexpr int kEffOff = kQueueOff + COMP2_CW * QSTRIDE;
+    constexpr int kBoxOff = kQueueOff + COMP2_CW * QSTRIDE;
+    constexpr int kEffOff = kBoxOff + (MASKS ? COMP2_CW * PG_MAX_OBJECTS * (int)sizeof(float4) : 0);
     float4* sm_eff = reinterpret_cast<float4*>(smem_raw + kEffOff);
     float2* sm_tk = reinterpret_cast<float2*>(smem_raw + kEffOff + PG_MAX_OBJECTS * sizeof(float4));
 
@@ -134,12 +136,11 @@ __global__ void __launch_bounds__(COMP2_THREADS, MINB) composite3_kernel(const C
     float pfx = (float)px;
     asm volatile("" : "+f"(pfx));
     const f32x2 npfy = pk2(-(float)py0, -(float)py1);
-    const float bx0 = (float)wx0, bx1 = (float)min(wx0 + 7, a.W - 1);
-    const float by0 = (float)wy0, by1 = (float)min(wy0 + 7, a.H - 1);
     const int K = MASKS ? a.num_objects : 0;
     const uint32_t all_k = K >= 32 ? 0xFFFFFFFFu : ((1u << K) - 1u);
     float2* my_tk = sm_tk + (warp * 32 + lane);  // object k's silhouette chains at my_tk[k * 128]
     uint8_t* const queue = smem_raw + kQueueOff + warp * QSTRIDE;
+    float4* const my_box = reinterpret_cast<float4*>(smem_raw + kBoxOff) + warp * PG_MAX_OBJECTS;  // MASKS: per object
 
     // Main chain: T stays the transmittance (frozen once the chain has terminated); thr0 / thr1 say whether it is alive
     // (1/255: alive, +inf: finished — see valid_alpha).  Object chains (To, Tk): a finished chain holds -|T|.
@@ -247,9 +248,39 @@ __global__ void __launch_bounds__(COMP2_THREADS, MINB) composite3_kernel(const C
                 need = __any_sync(0xffffffffu, to0 > 0.0f || to1 > 0.0f)
                            ? all_k : (__reduce_or_sync(0xffffffffu, ~(dk0 & dk1)) & all_k);
             }
-            // ---- 1. cull the batch against this warp's pixel block, queue the hits in list order
+            // ---- 1. cull the batch against the bounding box of this warp's pixels it can still change: pixels saturate
+            // one by one, the box shrinks, and a Gaussian that only touches finished pixels is a no-op.  An environment
+            // entry can change pixels whose main chain is alive; an entry of object k also those whose objects-only
+            // render chain or whose silhouette chain k is alive (one box per object, in shared memory).
+            float ax0, ax1, ay0, ay1;
+            {
+                const bool m0 = thr0 == THR_ALIVE, m1 = thr1 == THR_ALIVE;
+                const int big = 1 << 30;
+                auto box = [&](bool l0, bool l1, float& x0, float& x1, float& y0, float& y1) {
+                    x0 = (float)__reduce_min_sync(0xffffffffu, (l0 || l1) ? px : big);
+                    x1 = (float)__reduce_max_sync(0xffffffffu, (l0 || l1) ? px : -big);
+                    y0 = (float)__reduce_min_sync(0xffffffffu, l0 ? py0 : (l1 ? py1 : big));
+                    y1 = (float)__reduce_max_sync(0xffffffffu, l1 ? py1 : (l0 ? py0 : -big));
+                };
+                box(m0, m1, ax0, ax1, ay0, ay1);
+                if (MASKS) {
+                    float to0, to1;
+                    unpk2(To, to0, to1);
+                    const bool o0 = m0 || to0 > 0.0f, o1 = m1 || to1 > 0.0f;
+                    for (int k = 0; k < K; ++k) {
+                        float x0, x1, y0, y1;
+                        box(o0 || !((dk0 >> k) & 1u), o1 || !((dk1 >> k) & 1u), x0, x1, y0, y1);
+                        if (lane == 0) my_box[k] = make_float4(x0, x1, y0, y1);
+                    }
+                    __syncwarp();
+                }
+            }
             int nq = 0;
+#ifdef PG_EXP_SKIP_OBJCULL
+            if (wm) {
+#else
             if (wm || need != 0) {
+#endif
 #pragma unroll
                 for (int c = 0; c < COMP_BATCH / 32; ++c) {
                     const int e = c * 32 + lane;
@@ -259,7 +290,9 @@ __global__ void __launch_bounds__(COMP2_THREADS, MINB) composite3_kernel(const C
                         const float4 B = sr[e].b;
                         const int eo = MASKS ? (__float_as_int(B.w) & 63) : 0;
                         const bool wanted = wm || (MASKS && eo > 0 && ((need >> ((uint32_t)(eo - 1) & 31u)) & 1u));
-                        hit = wanted && !block_culled_fast(A.x, A.y, A.z, A.w, B.x, B.w, bx0, bx1, by0, by1);
+                        float4 bb = make_float4(ax0, ax1, ay0, ay1);
+                        if (MASKS && eo > 0) bb = my_box[eo - 1];
+                        hit = wanted && !block_culled_fast(A.x, A.y, A.z, A.w, B.x, B.w, bb.x, bb.y, bb.z, bb.w);
                     }
                     const uint32_t m = __ballot_sync(0xffffffffu, hit);
                     if (hit) queue[nq + __popc(m & lt)] = (uint8_t)e;
@@ -335,7 +368,11 @@ __global__ void __launch_bounds__(COMP2_THREADS, MINB) composite3_kernel(const C
                     if (lane == 0) atomicAdd(&sm.warps_main_done, 1);
                 }
             }
+#ifdef PG_EXP_SKIP_OBJLOOP
+            if (false) {
+#else
             if (MASKS && i_obj < nq) {
+#endif
                 // every main chain of the warp has terminated: only the objects-only chains run, on object entries
                 // (a batch culled while a main chain was alive still has environment entries queued: skipped)
 #pragma unroll 1
@@ -435,7 +472,7 @@ __global__ void __launch_bounds__(COMP2_THREADS, MINB) composite3_kernel(const C
 template <bool MASKS, bool NCONTRIB, bool FAST, int STAGES, int MINB>
 static int launch_three(const CompArgs& a, dim3 grid, cudaStream_t stream) {
     const int smem = (int)((sizeof(CompSmemT<STAGES>) + 15) / 16 * 16) + COMP2_CW * QSTRIDE +
-                     (MASKS ? (int)(PG_MAX_OBJECTS * sizeof(float4)) + a.num_objects * 256 * (int)sizeof(float) : 0);
+                     (MASKS ? (int)((COMP2_CW + 1) * PG_MAX_OBJECTS * sizeof(float4)) + a.num_objects * 256 * (int)sizeof(float) : 0);
     PG_CUDA_CHECK(ensure_dynamic_smem(composite3_kernel<MASKS, NCONTRIB, FAST, STAGES, MINB>, smem, true));
     composite3_kernel<MASKS, NCONTRIB, FAST, STAGES, MINB><<<grid, COMP2_THREADS, smem, stream>>>(a);
     return PG_OK;
