@@ -276,11 +276,7 @@ __global__ void __launch_bounds__(COMP2_THREADS, MINB) composite3_kernel(const C
                 }
             }
             int nq = 0;
-#ifdef PG_EXP_SKIP_OBJCULL
-            if (wm) {
-#else
             if (wm || need != 0) {
-#endif
 #pragma unroll
                 for (int c = 0; c < COMP_BATCH / 32; ++c) {
                     const int e = c * 32 + lane;
@@ -368,11 +364,7 @@ __global__ void __launch_bounds__(COMP2_THREADS, MINB) composite3_kernel(const C
                     if (lane == 0) atomicAdd(&sm.warps_main_done, 1);
                 }
             }
-#ifdef PG_EXP_SKIP_OBJLOOP
-            if (false) {
-#else
             if (MASKS && i_obj < nq) {
-#endif
                 // every main chain of the warp has terminated: only the objects-only chains run, on object entries
                 // (a batch culled while a main chain was alive still has environment entries queued: skipped)
 #pragma unroll 1
