@@ -31,6 +31,9 @@
  *                             imgBuffer (point_list_keys, point_list, ranges).
  *   pg_pack_frame,         <- the host-side conversions in pegasus.py:340-358 (rgb*255 -> u8,
  *   pg_pack_masks             depth*1000 -> u16, masks -> 0/255 u8) done on the device before the D2H copy.
+ *   pg_png_encode          <- the PNG encoding of every product by imageio inside the writer threads
+ *                             (pegasus.py:346-358, src/tools/pegasus_working.py:407-438): the zlib stream of each
+ *                             image is produced on the device; the host only frames it as a PNG file.
  */
 #ifndef PEGASUS_B200_H
 #define PEGASUS_B200_H
@@ -250,6 +253,37 @@ int pg_pack_frame(int32_t width, int32_t height, const float* color, const float
  * they cross PCIe as one bit per pixel and are expanded by the writer thread that encodes the PNG. */
 int pg_pack_masks(int32_t width, int32_t height, int32_t n_planes, const uint8_t* masks, uint8_t* bits,
                   pg_stream_t stream);
+
+/* ---- PNG streams on the device -------------------------------------------------------------------------
+ * One call encodes n_images images of the same width x height (a frame's RGB, depth, semantic map and mask
+ * planes): per image the complete zlib stream of its PNG IDAT chunk — Sub-filtered scanlines, run-length matches,
+ * one dynamic-Huffman deflate block, Adler-32 — is written to `out`; `result[0]` receives its length in bytes,
+ * `result[1]` becomes non-zero when it did not fit `out_capacity` (the stream is then unusable: grow and encode
+ * again).  The Huffman code is NOT derived per image: `table` is a u32[PG_PNG_TABLE_WORDS] device array built on the
+ * host (pegasus_b200/png_codec.py: build_table) from the token histogram of sample images, which a call accumulates
+ * into `hist` (u32[PG_PNG_HIST_WORDS], caller-zeroed) when that pointer is not NULL.  Any table encodes any image
+ * correctly; the ratio depends on how typical the sample was.  `images` is a HOST array. */
+#define PG_PNG_RGB8 0   /* src u8 [H][W][3]                         -> 8-bit RGB */
+#define PG_PNG_GRAY16 1 /* src u16 [H][W]                           -> 16-bit grayscale (big-endian in the file) */
+#define PG_PNG_MASK8 2  /* src u8 [H][W], non-zero = set            -> 8-bit grayscale 0 / 255 */
+#define PG_PNG_TABLE_WORDS 610
+#define PG_PNG_HIST_WORDS 286
+
+typedef struct pg_png_image {
+    const void* src;       /* device */
+    int32_t kind;          /* PG_PNG_* */
+    int32_t src_pitch;     /* bytes between source rows */
+    uint8_t* out;          /* device, 16-byte aligned */
+    uint32_t out_capacity; /* bytes, a multiple of 16; pg_png_worst_case_bytes() never overflows */
+    const uint32_t* table; /* device */
+    void* scratch;         /* device, pg_png_scratch_bytes(height), 16-byte aligned */
+    uint32_t* hist;        /* device or NULL */
+    uint32_t* result;      /* device u32[2] */
+} pg_png_image;
+
+size_t pg_png_scratch_bytes(int32_t height);
+size_t pg_png_worst_case_bytes(int32_t kind, int32_t width, int32_t height);
+int pg_png_encode(int32_t n_images, const pg_png_image* images, int32_t width, int32_t height, pg_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -76,10 +76,19 @@ class LaunchOpts(C.Structure):
                 ("status_host", _f), ("numerics", C.c_int32)]
 
 
+class PngImage(C.Structure):
+    _fields_ = [("src", _f), ("kind", C.c_int32), ("src_pitch", C.c_int32), ("out", _f), ("out_capacity", C.c_uint32),
+                ("table", _f), ("scratch", _f), ("hist", _f), ("result", _f)]
+
+
+PNG_TABLE_WORDS = 610
+PNG_HIST_WORDS = 286
+
 EXPORTS = ["pg_version", "pg_last_error", "pg_workspace_bytes", "pg_workspace_init", "pg_rasterize_forward",
            "pg_render_composed", "pg_read_status", "pg_mark_visible", "pg_pose_apply",
            "pg_export_binning", "pg_pack_frame", "pg_profile_enable", "pg_profile_frames",
-           "pg_profile_read", "pg_launch_count", "pg_read_stats", "pg_pack_masks"]
+           "pg_profile_read", "pg_launch_count", "pg_read_stats", "pg_pack_masks", "pg_png_scratch_bytes",
+           "pg_png_worst_case_bytes", "pg_png_encode"]
 
 NUM_STAGES = 7
 STAGE_NAMES = ["clear", "preprocess", "depth_sort", "emit", "tile_scan", "tile_sort", "composite"]
@@ -149,6 +158,12 @@ def load():
     L.pg_profile_read.argtypes = [C.c_int32, C.POINTER(C.c_float)]
     L.pg_launch_count.restype = C.c_uint64
     L.pg_read_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.pg_png_scratch_bytes.argtypes = [C.c_int32]
+    L.pg_png_scratch_bytes.restype = C.c_size_t
+    L.pg_png_worst_case_bytes.argtypes = [C.c_int32, C.c_int32, C.c_int32]
+    L.pg_png_worst_case_bytes.restype = C.c_size_t
+    L.pg_png_encode.argtypes = [C.c_int32, C.POINTER(PngImage), C.c_int32, C.c_int32, C.c_void_p]
+    L.pg_png_encode.restype = C.c_int
     for name in ("pg_profile_enable", "pg_profile_read", "pg_read_stats"):
         getattr(L, name).restype = C.c_int
     for name in ("pg_rasterize_forward", "pg_render_composed", "pg_read_status", "pg_mark_visible",

@@ -221,6 +221,25 @@ class BOPDatasetWriter:
                 _imwrite(str(self.mask_visib_path / "{:06d}_{:06d}.png".format(frame_id, idx)),
                          (mask_visib[idx] != 0).astype(np.uint8) * 255)
 
+    def write_encoded(self, frame_id: int, streams: Dict, width: int, height: int, n_colours: int, rgb: bool = True,
+                      sem_seg: bool = True, silhouette: bool = True, visible: bool = True) -> None:
+        """The same files as `_write`, from zlib streams the GPU produced (pg_png_encode; `streams`: name -> bytes-like
+        with the names of DatasetGenerator's encoder: rgb, depth, sem_seg, silhouette<k>, visible<k>).  The host only
+        frames them: signature, IHDR, IDAT + CRC-32, IEND.  The files decode to the pixels `_write` stores."""
+        from . import png_codec as pc
+        name = "{:06d}.png".format(frame_id)
+        if rgb:
+            pc.write_png(str(self.rgb_path / name), pc.KIND_RGB8, width, height, streams["rgb"])
+            pc.write_png(str(self.depth_path / name), pc.KIND_GRAY16, width, height, streams["depth"])
+        if sem_seg:
+            pc.write_png(str(self.sem_mask_path / name), pc.KIND_RGB8, width, height, streams["sem_seg"])
+        for idx in range(n_colours):
+            sub = "{:06d}_{:06d}.png".format(frame_id, idx)
+            if silhouette:
+                pc.write_png(str(self.mask_path / sub), pc.KIND_MASK8, width, height, streams[f"silhouette{idx}"])
+            if visible:
+                pc.write_png(str(self.mask_visib_path / sub), pc.KIND_MASK8, width, height, streams[f"visible{idx}"])
+
     def close(self) -> None:
         """Join the writer threads and flush both JSON files."""
         for th in self._threads:

@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libpegasus_b200.so")
-SOURCES = ["pg_abi.cu", "preprocess.cu", "sort.cu", "binning.cu", "composite.cu", "composite3.cu", "pose.cu"]
+SOURCES = ["pg_abi.cu", "preprocess.cu", "sort.cu", "binning.cu", "composite.cu", "composite3.cu", "pose.cu", "png.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "--fmad=false", "-Xcompiler", "-fPIC,-ffp-contract=off", "-shared"]
 

@@ -80,6 +80,7 @@ int launch_pose(int K, const int32_t* first, const PoseDev* poses_dev, const pg_
 int launch_pack(int W, int H, const float* color, const float* depth, uint8_t* rgb_u8, uint16_t* depth_u16,
                 cudaStream_t stream);
 int launch_pack_masks(int W, int H, int n_planes, const uint8_t* masks, uint8_t* bits, cudaStream_t stream);
+int launch_png_encode(int n_images, const pg_png_image* images, int width, int height, cudaStream_t stream);
 int launch_composite_from_abi(const uint2* ranges, const uint32_t* tile_order, const uint32_t* point_list, const GeomRec* recs, int W,
                               int H, const float* bg, const pg_raster_outputs* ro, const pg_frame_outputs* fo,
                               const pg_object_table* objs, uint32_t n_env, const uint32_t* tile_obj_count,
@@ -416,6 +417,42 @@ int pg_pack_masks(int32_t width, int32_t height, int32_t n_planes, const uint8_t
                   pg_stream_t stream) {
     if (width <= 0 || height <= 0 || n_planes < 0 || (n_planes > 0 && (!masks || !bits))) { set_error("bad argument"); return PG_ERR_INVALID; }
     return launch_pack_masks(width, height, n_planes, masks, bits, (cudaStream_t)stream);
+}
+
+size_t pg_png_scratch_bytes(int32_t height) {
+    if (height <= 0) return 0;
+    return ((size_t)height * 4 + 15) / 16 * 16 + (size_t)height * 16;
+}
+
+size_t pg_png_worst_case_bytes(int32_t kind, int32_t width, int32_t height) {
+    if (kind < PG_PNG_RGB8 || kind > PG_PNG_MASK8 || width <= 0 || height <= 0) return 0;
+    // 2 bytes zlib header, block header, <= 15 bits per stream byte (a match token of <= 21 bits stands for >= 3
+    // bytes), end of block, padding, Adler-32; rounded up to the 16-byte granularity of out_capacity
+    const size_t bpp = kind == PG_PNG_RGB8 ? 3 : (kind == PG_PNG_GRAY16 ? 2 : 1);
+    const size_t row = bpp * (size_t)width + 1;
+    const size_t b = 2 + (32 * (size_t)(PG_PNG_TABLE_WORDS - 514) + 15 * row * (size_t)height + 15 + 7) / 8 + 4 + 8;
+    return (b + 15) / 16 * 16;
+}
+
+int pg_png_encode(int32_t n_images, const pg_png_image* images, int32_t width, int32_t height, pg_stream_t stream) {
+    if (n_images < 0 || width <= 0 || height <= 0 || (n_images > 0 && !images)) { set_error("bad argument"); return PG_ERR_INVALID; }
+    for (int i = 0; i < n_images; ++i) {
+        const pg_png_image& im = images[i];
+        if (im.kind < PG_PNG_RGB8 || im.kind > PG_PNG_MASK8 || !im.src || !im.out || !im.table || !im.scratch || !im.result) {
+            set_error("pg_png_encode: image %d: bad kind or NULL pointer", i);
+            return PG_ERR_INVALID;
+        }
+        const int bpp = im.kind == PG_PNG_RGB8 ? 3 : (im.kind == PG_PNG_GRAY16 ? 2 : 1);
+        if (im.src_pitch < bpp * width || (im.kind == PG_PNG_GRAY16 && (((uintptr_t)im.src | (uintptr_t)im.src_pitch) & 1))) {
+            set_error("pg_png_encode: image %d: src_pitch %d too small or 16-bit source misaligned", i, im.src_pitch);
+            return PG_ERR_INVALID;
+        }
+        if (((uintptr_t)im.out & 15) || ((uintptr_t)im.scratch & 15) || (im.out_capacity & 15) || im.out_capacity < 64) {
+            set_error("pg_png_encode: image %d: out / scratch must be 16-byte aligned, out_capacity a multiple of 16 >= 64", i);
+            return PG_ERR_INVALID;
+        }
+    }
+    return launch_png_encode(n_images, images, width, height, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -10,7 +10,10 @@ ONE fused frame (pg_render_composed), the packing kernels (pg_pack_frame: u8 RGB
 pg_pack_masks: the 2 x n_colours mask planes as one bit per pixel), and D2H copies of the packed products
 into a pinned host buffer set.  `frames_in_flight` frames
 are pipelined, each on its own CUDA stream + workspace slot, so frame i+1's per-Gaussian and binning
-stages overlap frame i's compositing and copies.  Host buffer sets are recycled through a free list:
+stages overlap frame i's compositing and copies.  With `png_on_gpu=True` the frame's PNG streams are produced on
+the device as well (pg_png_encode: Sub filter, run-length matches, Huffman coding with per-scene tables) and the
+D2H copy carries the compressed streams instead of the raw products: the writer thread only frames them as PNG
+files (CRC-32) — the host cost per frame drops from ~170 ms of libpng to a few ms, the D2H bytes to a third.  Host buffer sets are recycled through a free list:
 a set goes back only after the writer (thread pool, like pegasus.py:346) is done with it, which
 back-pressures rendering when PNG encoding is the bottleneck.
 
@@ -30,6 +33,8 @@ import numpy as np
 import torch
 
 from . import _lib
+from . import png_codec
+from .png_gpu import FramePngEncoder, PngTables
 from .scene import ComposedScene
 from .sh_rotation import POSE_WORDS, generate_pose_packets
 
@@ -71,7 +76,7 @@ class DatasetGenerator:
 
     def __init__(self, scene: ComposedScene, width: int, height: int, bg: Optional[torch.Tensor] = None,
                  frames_in_flight: int = 3, host_sets: Optional[int] = None, writer_threads: int = 4,
-                 overlap_compositing: bool = True, numerics=None):
+                 overlap_compositing: bool = True, numerics=None, png_on_gpu: bool = False):
         self.scene = scene
         self.dev = scene.device
         self.W, self.H = int(width), int(height)
@@ -117,6 +122,20 @@ class DatasetGenerator:
         self.d2h_bytes_per_frame = W * H * (3 + 2 + 3) + 2 * nc * H * self.Wb
         self.pair_capacity: Optional[int] = None
         self._overflow_seen: Dict[int, int] = {}  # slot -> sticky overflow_frames already reported
+        # ---- PNG streams on the device (optional): per slot one encoder over the slot's product buffers
+        self.png_on_gpu = bool(png_on_gpu)
+        self.png_tables: Optional[PngTables] = None
+        self.png_enc: List[FramePngEncoder] = []
+        self.png_fallbacks = 0  # frames whose streams outgrew the calibrated capacity (encoded again, unbounded)
+        if self.png_on_gpu:
+            self.png_tables = PngTables(dev, ["rgb", "depth", "sem", "mask"])
+            for sl in range(self.nslot):
+                o, pk = self.outs[sl], self.packs[sl]
+                imgs = [("rgb", png_codec.KIND_RGB8, "rgb", pk["rgb"]), ("depth", png_codec.KIND_GRAY16, "depth", pk["depth"]),
+                        ("sem_seg", png_codec.KIND_RGB8, "sem", o["sem_seg"])]
+                imgs += [(f"silhouette{k}", png_codec.KIND_MASK8, "mask", o["silhouette"][k]) for k in range(nc)]
+                imgs += [(f"visible{k}", png_codec.KIND_MASK8, "mask", o["visible"][k]) for k in range(nc)]
+                self.png_enc.append(FramePngEncoder(self.png_tables, W, H, imgs))
 
     # ------------------------------------------------------------------ capacity
     def calibrate(self, cams: Sequence, pose_packets: Optional[torch.Tensor] = None, margin: float = 1.05) -> int:
@@ -135,7 +154,52 @@ class DatasetGenerator:
                 sc.render(cams[0], self.bg, masks=True, out=self.outs[sl], sync_check=True,
                           pair_capacity=self.pair_capacity, slot=sl, numerics=self.numerics)
         torch.cuda.synchronize(self.dev)
+        if self.png_on_gpu:
+            self._calibrate_png(cams, pose_packets)
         return self.pair_capacity
+
+    def _pack_slot(self, sl: int, st: torch.cuda.Stream) -> None:
+        L, o = _lib.load(), self.outs[sl]
+        _lib.check(L.pg_pack_frame(self.W, self.H, C.c_void_p(o["color"].data_ptr()), C.c_void_p(o["depth"].data_ptr()),
+                                   C.c_void_p(self.packs[sl]["rgb"].data_ptr()), C.c_void_p(self.packs[sl]["depth"].data_ptr()),
+                                   C.c_void_p(st.cuda_stream)), "pg_pack_frame")
+
+    def _calibrate_png(self, cams: Sequence, pose_packets: Optional[torch.Tensor], margin: float = 1.3,
+                       samples: int = 4) -> None:
+        """Per-scene Huffman tables from the token histograms of a few sample views, then the stream capacities
+        (= D2H bytes per frame) from the largest streams those views produce.  Statistics that drift later cost
+        ratio, never correctness; a stream that outgrows its capacity is caught per frame and encoded again."""
+        sc, enc, st = self.scene, self.png_enc[0], torch.cuda.current_stream(self.dev)
+        pick = list(cams[::max(1, len(cams) // samples)])[:samples]
+
+        def render(i, cam):
+            if pose_packets is not None and self.K:
+                sc.apply_pose_packets(pose_packets[i % pose_packets.shape[0]])
+            sc.render(cam, self.bg, masks=True, out=self.outs[0], sync_check=True, pair_capacity=self.pair_capacity,
+                      numerics=self.numerics)
+            self._pack_slot(0, st)
+        for i, cam in enumerate(pick):
+            render(i, cam)
+            enc.accumulate_hist(st)
+        self.png_tables.rebuild_from_hist()
+        sizes = np.zeros(len(enc.images), dtype=np.int64)
+        for i, cam in enumerate(pick):
+            render(i, cam)
+            sizes = np.maximum(sizes, np.asarray(enc.measured_sizes(st)))
+        # masks of one frame swap sizes with the view (coverage): all planes get the largest one's room
+        names = enc.names
+        mask_max = max([int(s) for n, s in zip(names, sizes) if n.startswith(("silhouette", "visible"))] or [0])
+        caps = [int(margin * (mask_max if n.startswith(("silhouette", "visible")) else s)) + 8192 for n, s in zip(names, sizes)]
+        for e in self.png_enc:
+            e.set_capacities(caps)
+        sets = []
+        while not self._free.empty():
+            sets.append(self._free.get())
+        for h in sets:
+            h["png"] = torch.empty(self.png_enc[0].arena_bytes, dtype=torch.uint8).pin_memory()
+            h["png_result"] = torch.zeros((len(names), 2), dtype=torch.int32).pin_memory()
+            self._free.put(h)
+        self.d2h_bytes_per_frame = self.png_enc[0].arena_bytes + 8 * len(names)
 
     # ------------------------------------------------------------------ one frame, asynchronous
     def _issue(self, i: int, sl: int, cam, cam_row: torch.Tensor, pose_row: Optional[torch.Tensor], host: Dict,
@@ -156,10 +220,13 @@ class DatasetGenerator:
             sc.render(cs, self.bg, masks=True, out=o, sync_check=False, pair_capacity=self.pair_capacity, slot=sl,
                       scene_read_event=self.read_ev[sl] if dynamic else None, composite_stream=self.comp_streams[sl],
                       numerics=self.numerics, status_host=host["status"])
-            _lib.check(L.pg_pack_frame(self.W, self.H, C.c_void_p(o["color"].data_ptr()),
-                                       C.c_void_p(o["depth"].data_ptr()), C.c_void_p(self.packs[sl]["rgb"].data_ptr()),
-                                       C.c_void_p(self.packs[sl]["depth"].data_ptr()), C.c_void_p(st.cuda_stream)),
-                       "pg_pack_frame")
+            self._pack_slot(sl, st)
+            if self.png_on_gpu:
+                self.png_enc[sl].encode(st)
+                host["png"].copy_(self.png_enc[sl].arena, non_blocking=True)
+                host["png_result"].copy_(self.png_enc[sl].result, non_blocking=True)
+                self.done_ev[sl].record(st)
+                return
             for name in ("visible", "silhouette"):
                 _lib.check(L.pg_pack_masks(self.W, self.H, self.nc, C.c_void_p(o[name].data_ptr()),
                                            C.c_void_p(self.packs[sl][name].data_ptr()), C.c_void_p(st.cuda_stream)),
@@ -217,6 +284,10 @@ class DatasetGenerator:
             step = max(1, len(mine) // 16)
             self.calibrate([cams[f] for f in mine[::step]],
                            None if (per_frame is None or static) else per_frame[mine[::step]].to(self.dev))
+        if self.png_on_gpu and not self.png_tables.calibrated:  # pair capacity was set by hand
+            step = max(1, len(mine) // 16)
+            self._calibrate_png([cams[f] for f in mine[::step]],
+                                None if (per_frame is None or static) else per_frame[mine[::step]].to(self.dev))
         pool = ThreadPoolExecutor(max_workers=self.writer_threads) if (writer is not None or on_frame) else None
         want_rgb, want_sil = "rgb" in data_points, "seg_sil" in data_points
         want_vis, want_sem = "seg_vis" in data_points, "sem_seg" in data_points
@@ -247,6 +318,15 @@ class DatasetGenerator:
                                    "`margin`")
             stats["frames"] += 1
             W_ = self.W
+            png_streams = None
+            if self.png_on_gpu:
+                if int(host["png_result"][:, 1].max()) != 0:
+                    # statistics drifted past the calibrated capacity: encode this frame again without a bound while
+                    # the slot's products are still intact (rare; costs a synchronisation)
+                    self.png_fallbacks += 1
+                    png_streams = self.png_enc[sl].encode_unbounded(self.streams[sl])
+                else:
+                    png_streams = self.png_enc[sl].streams(host["png"], host["png_result"])
 
             def make_products():
                 # runs on the writer thread: the masks cross PCIe bit-packed and are expanded to the u8 0/1
@@ -269,6 +349,13 @@ class DatasetGenerator:
 
             def work():
                 try:
+                    if png_streams is not None:
+                        if writer is not None:
+                            writer.write_encoded(f, png_streams, W_, self.H, self.nc, rgb=want_rgb, sem_seg=want_sem,
+                                                 silhouette=want_sil, visible=want_vis)
+                        if on_frame is not None:
+                            on_frame(f, {"png": png_streams})
+                        return
                     prods = make_products()
                     if writer is not None:
                         writer._write(f, prods["rgb"], prods["depth"], prods["visible"], prods["silhouette"], prods["sem_seg"])

@@ -34,7 +34,8 @@ def test_ctypes_structs_match_the_header(tmp_path):
     structs = {"pg_raster_settings": _lib.RasterSettings, "pg_gaussians": _lib.Gaussians,
                "pg_raster_outputs": _lib.RasterOutputs, "pg_object_table": _lib.ObjectTable,
                "pg_frame_outputs": _lib.FrameOutputs, "pg_pose": _lib.Pose, "pg_canonical": _lib.Canonical,
-               "pg_scene": _lib.Scene, "pg_status": _lib.Status, "pg_launch_opts": _lib.LaunchOpts}
+               "pg_scene": _lib.Scene, "pg_status": _lib.Status, "pg_launch_opts": _lib.LaunchOpts,
+               "pg_png_image": _lib.PngImage}
     prog = "#include <stdio.h>\n#include \"pegasus_b200.h\"\nint main(void){\n"
     for n in structs:
         prog += f'printf("{n} %zu\\n", sizeof({n}));\n'
@@ -49,6 +50,10 @@ def test_ctypes_structs_match_the_header(tmp_path):
     assert int(out["PG_NUM_STAGES"]) == _lib.NUM_STAGES == len(_lib.STAGE_NAMES)
     assert int(out["PG_MAX_OBJECTS"]) == _lib.PG_MAX_OBJECTS and int(out["PG_MAX_COLORS"]) == _lib.PG_MAX_COLORS
     assert C.sizeof(_lib.Pose) == 4 * _lib.POSE_WORDS == 412
+    from pegasus_b200 import png_codec
+    hdr = open(HEADER).read()
+    assert f"#define PG_PNG_TABLE_WORDS {_lib.PNG_TABLE_WORDS}" in hdr and png_codec.TABLE_WORDS == _lib.PNG_TABLE_WORDS
+    assert f"#define PG_PNG_HIST_WORDS {_lib.PNG_HIST_WORDS}" in hdr and png_codec.N_LITLEN == _lib.PNG_HIST_WORDS
 
 
 def test_argument_errors_do_not_need_a_gpu():

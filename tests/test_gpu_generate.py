@@ -182,3 +182,65 @@ def test_two_rank_sharding_writes_the_same_dataset(tmp_path):
     cj = json.load(open(tmp_path / "ds" / "train" / "000000" / "scene_camera.json"))
     assert list(cj.keys()) == [str(f) for f in range(5)]
     assert not list((tmp_path / "ds" / "train" / "000000").glob("*.rank*.json"))
+
+
+@pytest.mark.parametrize("mode", ["dynamic", "static"])
+def test_gpu_png_dataset_decodes_to_the_host_encoded_dataset(mode, tmp_path):
+    """png_on_gpu=True: the files come from zlib streams produced on the device (pg_png_encode) and framed on the
+    host; every file decodes to the pixels of the dataset the host encoder writes, the JSON files are identical."""
+    import cv2
+    from pegasus_b200 import BOPDatasetWriter, DatasetGenerator, ObjectMeta
+    scene, cams, poses, objs = _scene_and_path()
+    if mode == "static":
+        poses = poses[-1]
+    W, H = cams[0].image_width, cams[0].image_height
+    metas = [ObjectMeta.from_points(10 + k, objs[oid]["xyz"]) for k, oid in enumerate(scene.object_ids)]
+    roots = {}
+    for tag, on_gpu in (("host", False), ("gpu", True)):
+        writer = BOPDatasetWriter(tag, tmp_path, 438.2178, 492.5640, 640, 480, W, H, scene_id=1, async_writes=False)
+        gen = DatasetGenerator(scene, W, H, frames_in_flight=3, writer_threads=2, png_on_gpu=on_gpu)
+        stats = gen.generate(cams, poses=poses, writer=writer, metas=metas)
+        writer.close()
+        assert stats["frames"] == len(cams)
+        roots[tag] = tmp_path / tag / "train" / "000001"
+        if on_gpu:
+            assert gen.png_fallbacks == 0
+            assert gen.d2h_bytes_per_frame < W * H * 8  # compressed streams, not raw products
+    files = sorted(p.relative_to(roots["host"]) for p in roots["host"].rglob("*.png"))
+    assert files == sorted(p.relative_to(roots["gpu"]) for p in roots["gpu"].rglob("*.png"))
+    assert len(files) == len(cams) * (3 + 2 * 2)
+    for rel in files:
+        a = cv2.imread(str(roots["host"] / rel), cv2.IMREAD_UNCHANGED)
+        b = cv2.imread(str(roots["gpu"] / rel), cv2.IMREAD_UNCHANGED)
+        assert a.dtype == b.dtype and a.shape == b.shape and np.array_equal(a, b), str(rel)
+    for name in ("scene_gt.json", "scene_camera.json"):
+        assert json.load(open(roots["host"] / name)) == json.load(open(roots["gpu"] / name))
+
+
+def test_gpu_png_capacity_overflow_falls_back_per_frame(tmp_path):
+    """Streams that outgrow the calibrated capacity are detected per frame and encoded again without a bound."""
+    import cv2
+    from pegasus_b200 import BOPDatasetWriter, DatasetGenerator
+    scene, cams, poses, _ = _scene_and_path(n_frames=4)
+    W, H = cams[0].image_width, cams[0].image_height
+    ref = _sequential(scene, cams, poses)
+    gen = DatasetGenerator(scene, W, H, frames_in_flight=2, writer_threads=2, png_on_gpu=True)
+    gen.calibrate(cams, None)
+    for e in gen.png_enc:  # far too small for the RGB stream
+        caps = list(e.capacity)
+        caps[0] = 256
+        e.set_capacities(caps)
+    sets = []
+    while not gen._free.empty():
+        sets.append(gen._free.get())
+    for h in sets:
+        h["png"] = torch.empty(gen.png_enc[0].arena_bytes, dtype=torch.uint8).pin_memory()
+        gen._free.put(h)
+    writer = BOPDatasetWriter("ds", tmp_path, 438.2178, 492.5640, 640, 480, W, H, scene_id=0, async_writes=False)
+    gen.generate(cams, poses=poses, writer=writer)
+    writer.close()
+    assert gen.png_fallbacks == len(cams)
+    root = tmp_path / "ds" / "train" / "000000"
+    for f, r in enumerate(ref):
+        assert np.array_equal(cv2.imread(str(root / "rgb" / f"{f:06d}.png"), cv2.IMREAD_UNCHANGED)[:, :, ::-1], r["rgb"])
+        assert np.array_equal(cv2.imread(str(root / "depth" / f"{f:06d}.png"), cv2.IMREAD_UNCHANGED), r["depth"])
