@@ -95,6 +95,25 @@ __device__ __forceinline__ int block_excl_max(int v, int* tmp) {  // max over th
     if (lane == 0) prev = -1;
     return max(base, prev);
 }
+__device__ __forceinline__ int block_excl_min_after(int v, int none, int* tmp) {  // min over the threads after this one
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_down_sync(0xffffffffu, x, o);
+        if (lane + o < 32) x = min(x, y);
+    }
+    __syncthreads();
+    if (lane == 0) tmp[warp] = x;
+    __syncthreads();
+    int base = none;
+#pragma unroll
+    for (int w = 0; w < PNG_WARPS; ++w)
+        if (w > warp) base = min(base, tmp[w]);
+    int next = __shfl_down_sync(0xffffffffu, x, 1);
+    if (lane == 31) next = none;
+    return min(base, next);
+}
 __device__ __forceinline__ unsigned long long block_sum64(unsigned long long v, unsigned long long* tmp) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -109,19 +128,23 @@ __device__ __forceinline__ unsigned long long block_sum64(unsigned long long v, 
 }
 
 // Row `row` of the image as PNG stream bytes in shared memory: f[0] = 1 (filter type Sub), f[1 + p] = raw[p] -
-// raw[p - bpp].  raw = big-endian samples; `raw_s` is staging of the unfiltered bytes.
-__device__ __forceinline__ void png_stage_row(const PngImage& im, int row, int width, uint8_t* raw_s, uint8_t* f) {
+// raw[p - bpp].  raw = big-endian samples; `raw_s` is staging of the unfiltered bytes.  Returns false (and leaves f
+// unwritten) for a row whose samples are all zero: most rows of a mask or a semantic map; their tokens have a closed
+// form (ZeroRow).
+__device__ __forceinline__ bool png_stage_row(const PngImage& im, int row, int width, uint8_t* raw_s, uint8_t* f) {
     const int kind = im.kind, bpp = png_bpp(kind), nraw = bpp * width;
     const uint8_t* src = reinterpret_cast<const uint8_t*>(im.src) + (size_t)row * im.src_pitch;
     const bool aligned = ((reinterpret_cast<uintptr_t>(src) | (uintptr_t)im.src_pitch) & 3) == 0;
     const int nw = aligned ? nraw / 4 : 0;
     uint32_t* raw_w = reinterpret_cast<uint32_t*>(raw_s);
     const uint32_t* src_w = reinterpret_cast<const uint32_t*>(src);
+    uint32_t nz = 0;
     for (int w = threadIdx.x; w < nw; w += PNG_THREADS) {
         uint32_t v = __ldg(src_w + w);
         if (kind == PG_PNG_GRAY16) v = __byte_perm(v, 0, 0x2301);   // two u16 -> big-endian bytes
         else if (kind == PG_PNG_MASK8) v = __vcmpne4(v, 0u);         // non-zero -> 255
         raw_w[w] = v;
+        nz |= v;
     }
     for (int p = 4 * nw + threadIdx.x; p < nraw; p += PNG_THREADS) {
         uint8_t v;
@@ -133,17 +156,49 @@ __device__ __forceinline__ void png_stage_row(const PngImage& im, int row, int w
             if (kind == PG_PNG_MASK8) v = v ? 255 : 0;
         }
         raw_s[p] = v;
+        nz |= v;
     }
-    __syncthreads();
+    if (!__syncthreads_or(nz != 0)) return false;
     for (int p = threadIdx.x; p < nraw; p += PNG_THREADS)
         f[1 + p] = (uint8_t)(raw_s[p] - (p >= bpp ? raw_s[p - bpp] : 0));
     if (threadIdx.x == 0) f[0] = 1;
     __syncthreads();
+    return true;
 }
 
-// The tokens of stream positions [i0, i1) of a row of L bytes; s = last run start before i0 (-1: none).
+// The tokens of an all-zero row, stream bytes [1, 0, 0, ... 0] (L bytes): literal 1, literal 0, then the L - 2 repeats
+// of the zero as q matches of 258 and a tail of r < 258 (one match when r >= 3, else r literals).
+struct ZeroRow {
+    int q, r, n;            // n = number of tokens
+    uint32_t lit1, lit0, m258, tail;  // token words (bits | nbits << 24)
+    __device__ __forceinline__ ZeroRow(const uint32_t* tok, int L) {
+        const int reps = L - 2;
+        q = reps / 258;
+        r = reps - 258 * q;
+        lit1 = tok[T_LIT + 1];
+        lit0 = tok[T_LIT + 0];
+        m258 = tok[T_LEN + 255];
+        tail = r >= 3 ? tok[T_LEN + r - 3] : lit0;
+        n = 2 + q + (r >= 3 ? 1 : r);
+    }
+    __device__ __forceinline__ uint32_t bits() const {
+        return (lit1 >> 24) + (lit0 >> 24) + (uint32_t)q * (m258 >> 24) + (r >= 3 ? 1u : (uint32_t)r) * (tail >> 24);
+    }
+    // token t in [0, n): its word and its bit offset inside the row
+    __device__ __forceinline__ uint32_t token(int t, uint32_t* off) const {
+        if (t == 0) { *off = 0; return lit1; }
+        if (t == 1) { *off = lit1 >> 24; return lit0; }
+        const uint32_t head = (lit1 >> 24) + (lit0 >> 24);
+        if (t < 2 + q) { *off = head + (uint32_t)(t - 2) * (m258 >> 24); return m258; }
+        *off = head + (uint32_t)q * (m258 >> 24) + (uint32_t)(t - 2 - q) * (tail >> 24);
+        return tail;
+    }
+};
+
+// The tokens of stream positions [i0, i1) of a row of L bytes; s = last run start before i0 (-1: none), nxt = first
+// run start at or after i1 (L: none) — with it the length of a chunk is found inside the thread's own positions.
 template <class Lit, class Len>
-__device__ __forceinline__ void png_walk(const uint8_t* f, int L, int i0, int i1, int s, Lit&& lit, Len&& len) {
+__device__ __forceinline__ void png_walk(const uint8_t* f, int L, int i0, int i1, int s, int nxt, Lit&& lit, Len&& len) {
     for (int i = i0; i < i1; ++i) {
         const uint8_t b = f[i];
         if (i == 0 || b != f[i - 1]) s = i;
@@ -155,9 +210,10 @@ __device__ __forceinline__ void png_walk(const uint8_t* f, int L, int i0, int i1
         const bool ge3 = cs + 2 < L && f[cs + 1] == b && f[cs + 2] == b;
         if (!ge3) { lit(i, b); continue; }    // chunk of 1 or 2 bytes: literals
         if (off == 0) {
-            int cl = 3;
-            while (cl < 258 && cs + cl < L && f[cs + cl] == b) ++cl;
-            len(i, cl);
+            int e = i + 1;                    // first position after the run: inside this thread's positions, else nxt
+            while (e < i1 && f[e] == b) ++e;
+            if (e == i1) e = nxt;
+            len(i, min(258, e - cs));
         }
     }
 }
@@ -171,11 +227,16 @@ struct PngRowSmem {
 // dynamic shared memory: PngRowSmem | raw[Lpad] | f[Lpad] | (write kernel) stream words
 __device__ __forceinline__ int png_lpad(int L) { return (L + 15) / 16 * 16; }
 
-__device__ __forceinline__ int png_last_start(const uint8_t* f, int i0, int i1) {
-    int ls = -1;
+// last (-1: none) and first (L: none) run start among positions [i0, i1)
+__device__ __forceinline__ void png_starts(const uint8_t* f, int L, int i0, int i1, int* last, int* first) {
+    int ls = -1, fs = L;
     for (int i = i0; i < i1; ++i)
-        if (i == 0 || f[i] != f[i - 1]) ls = i;
-    return ls;
+        if (i == 0 || f[i] != f[i - 1]) {
+            ls = i;
+            fs = min(fs, i);
+        }
+    *last = ls;
+    *first = fs;
 }
 
 __global__ void __launch_bounds__(PNG_THREADS) png_size_kernel(const PngBatch B) {
@@ -193,15 +254,35 @@ __global__ void __launch_bounds__(PNG_THREADS) png_size_kernel(const PngBatch B)
         const uint32_t a = row * per, b = min(n16, a + per);
         for (uint32_t i = a + threadIdx.x; i < b; i += PNG_THREADS) o[i] = make_uint4(0, 0, 0, 0);
     }
+    uint32_t* hist = im.hist;
+    if (!png_stage_row(im, row, B.width, raw_s, f)) {
+        if (threadIdx.x == 0) {
+            const ZeroRow z(im.table, L);
+            if (row == 0) im.result[0] = im.result[1] = 0u;
+            im.row_bits[row] = z.bits();
+            im.row_adler[2 * row] = 1ull;                       // the filter-type byte
+            im.row_adler[2 * row + 1] = (unsigned long long)L;  // (L - 0) * 1
+            if (hist) {
+                atomicAdd(&hist[1], 1u);
+                atomicAdd(&hist[0], 1u + (z.r < 3 ? (uint32_t)z.r : 0u));
+                if (z.q) atomicAdd(&hist[285], (uint32_t)z.q);
+                if (z.r >= 3) atomicAdd(&hist[png_len_symbol(z.r)], 1u);
+                if (row == 0) atomicAdd(&hist[256], 1u);
+            }
+        }
+        return;
+    }
     for (int i = threadIdx.x; i < PNG_TOKENS; i += PNG_THREADS) sm.tok[i] = __ldg(im.table + i);
-    png_stage_row(im, row, B.width, raw_s, f);
+    __syncthreads();
     const int S = (L + PNG_THREADS - 1) / PNG_THREADS;
     const int i0 = min(L, (int)threadIdx.x * S), i1 = min(L, i0 + S);
-    const int s0 = block_excl_max(png_last_start(f, i0, i1), reinterpret_cast<int*>(sm.tmp));
+    int my_last, my_first;
+    png_starts(f, L, i0, i1, &my_last, &my_first);
+    const int s0 = block_excl_max(my_last, reinterpret_cast<int*>(sm.tmp));
+    const int nx = block_excl_min_after(my_first, L, reinterpret_cast<int*>(sm.tmp));
     uint32_t bits = 0, sumA = 0;
     unsigned long long sumB = 0;
-    uint32_t* hist = im.hist;
-    png_walk(f, L, i0, i1, s0,
+    png_walk(f, L, i0, i1, s0, nx,
              [&](int, uint8_t b) {
                  bits += sm.tok[T_LIT + b] >> 24;
                  if (hist) atomicAdd(&hist[b], 1u);
@@ -248,7 +329,6 @@ __global__ void __launch_bounds__(PNG_THREADS) png_write_kernel(const PngBatch B
     uint8_t* f = raw_s + Lp;
     uint32_t* out_s = reinterpret_cast<uint32_t*>(f + Lp);
     const uint32_t cap = im.out_capacity;
-    for (int i = threadIdx.x; i < PNG_TOKENS; i += PNG_THREADS) sm.tok[i] = __ldg(im.table + i);
     // where this row starts: 16 bits of zlib header + the block header + the rows before it
     unsigned long long before = 0;
     for (int r = threadIdx.x; r < row; r += PNG_THREADS) before += im.row_bits[r];
@@ -258,42 +338,54 @@ __global__ void __launch_bounds__(PNG_THREADS) png_write_kernel(const PngBatch B
     const int shift = (int)(base & 31);
     const int nw = (int)((shift + (unsigned long long)my_bits + 31) / 32);
     for (int w = threadIdx.x; w < nw + 1; w += PNG_THREADS) out_s[w] = 0;
-    png_stage_row(im, row, B.width, raw_s, f);  // ends with a barrier: out_s is clear as well
-    const int S = (L + PNG_THREADS - 1) / PNG_THREADS;
-    const int i0 = min(L, (int)threadIdx.x * S), i1 = min(L, i0 + S);
-    const int s0 = block_excl_max(png_last_start(f, i0, i1), reinterpret_cast<int*>(sm.tmp));
-    uint32_t bits = 0;
-    png_walk(f, L, i0, i1, s0, [&](int, uint8_t b) { bits += sm.tok[T_LIT + b] >> 24; },
-             [&](int, int cl) { bits += sm.tok[T_LEN + cl - 3] >> 24; });
-    uint32_t total;
-    const uint32_t excl = block_excl_sum(bits, sm.tmp, &total);
-    // second walk: place the tokens.  64-bit accumulator; a word is stored plainly once this thread has produced it
-    // up to its last bit and did not start inside it, else OR-ed (neighbouring threads share those words).
-    {
-        const uint32_t pos = (uint32_t)shift + excl;
-        unsigned long long acc = 0;
-        int fill = (int)(pos & 31), w = (int)(pos >> 5);
-        bool first = true;
-        auto put = [&](uint32_t tok) {
-            acc |= (unsigned long long)(tok & 0xFFFFFFu) << fill;
-            fill += (int)(tok >> 24);
-            if (fill >= 32) {
-                if (first) atomicOr(&out_s[w], (uint32_t)acc);
-                else out_s[w] = (uint32_t)acc;
-                first = false;
-                acc >>= 32;
-                fill -= 32;
-                ++w;
-            }
-        };
-        png_walk(f, L, i0, i1, s0, [&](int, uint8_t b) { put(sm.tok[T_LIT + b]); },
-                 [&](int, int cl) { put(sm.tok[T_LEN + cl - 3]); });
-        if (fill > 0 && acc) atomicOr(&out_s[w], (uint32_t)acc);
-    }
-    __syncthreads();
-    // shared-memory stream -> global: whole words, the row's first and last word shared with its neighbours
     bool ok = true;
-    {
+    if (!png_stage_row(im, row, B.width, raw_s, f)) {
+        // all-zero row: a handful of tokens with closed-form offsets, OR-ed straight into the output
+        const ZeroRow z(im.table, L);
+        for (int t = threadIdx.x; t < z.n; t += PNG_THREADS) {
+            uint32_t off;
+            const uint32_t tok = z.token(t, &off);
+            ok &= png_or_bits(im.out, cap, base + off, tok & 0xFFFFFFu, (int)(tok >> 24));
+        }
+    } else {
+        for (int i = threadIdx.x; i < PNG_TOKENS; i += PNG_THREADS) sm.tok[i] = __ldg(im.table + i);
+        __syncthreads();  // tokens staged; out_s is clear as well
+        const int S = (L + PNG_THREADS - 1) / PNG_THREADS;
+        const int i0 = min(L, (int)threadIdx.x * S), i1 = min(L, i0 + S);
+        int my_last, my_first;
+        png_starts(f, L, i0, i1, &my_last, &my_first);
+        const int s0 = block_excl_max(my_last, reinterpret_cast<int*>(sm.tmp));
+        const int nx = block_excl_min_after(my_first, L, reinterpret_cast<int*>(sm.tmp));
+        uint32_t bits = 0;
+        png_walk(f, L, i0, i1, s0, nx, [&](int, uint8_t b) { bits += sm.tok[T_LIT + b] >> 24; },
+                 [&](int, int cl) { bits += sm.tok[T_LEN + cl - 3] >> 24; });
+        uint32_t total;
+        const uint32_t excl = block_excl_sum(bits, sm.tmp, &total);
+        // second walk: place the tokens.  64-bit accumulator; a word is stored plainly once this thread has produced
+        // it up to its last bit and did not start inside it, else OR-ed (neighbouring threads share those words).
+        {
+            const uint32_t pos = (uint32_t)shift + excl;
+            unsigned long long acc = 0;
+            int fill = (int)(pos & 31), w = (int)(pos >> 5);
+            bool first = true;
+            auto put = [&](uint32_t tok) {
+                acc |= (unsigned long long)(tok & 0xFFFFFFu) << fill;
+                fill += (int)(tok >> 24);
+                if (fill >= 32) {
+                    if (first) atomicOr(&out_s[w], (uint32_t)acc);
+                    else out_s[w] = (uint32_t)acc;
+                    first = false;
+                    acc >>= 32;
+                    fill -= 32;
+                    ++w;
+                }
+            };
+            png_walk(f, L, i0, i1, s0, nx, [&](int, uint8_t b) { put(sm.tok[T_LIT + b]); },
+                     [&](int, int cl) { put(sm.tok[T_LEN + cl - 3]); });
+            if (fill > 0 && acc) atomicOr(&out_s[w], (uint32_t)acc);
+        }
+        __syncthreads();
+        // shared-memory stream -> global: whole words, the row's first and last word shared with its neighbours
         uint32_t* g = reinterpret_cast<uint32_t*>(im.out) + (base >> 5);
         const unsigned long long w0 = base >> 5;
         for (int w = threadIdx.x; w < nw; w += PNG_THREADS) {
@@ -320,7 +412,7 @@ __global__ void __launch_bounds__(PNG_THREADS) png_write_kernel(const PngBatch B
         b = block_sum64(b, sm.tmp64);
         if (threadIdx.x == 0) {
             const unsigned long long end = base + my_bits;
-            const uint32_t eob = sm.tok[T_EOB];
+            const uint32_t eob = __ldg(im.table + T_EOB);
             ok &= png_or_bits(im.out, cap, end, eob & 0xFFFFFFu, (int)(eob >> 24));
             const unsigned long long nbytes = (end + (eob >> 24) + 7) / 8;
             const unsigned long long N = (unsigned long long)H * L;

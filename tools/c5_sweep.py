@@ -4,8 +4,9 @@ every frame's PNGs + BOP JSON): a bounded slice of the dataset sweep — `pegasu
 per scene a `ComposedScene` + `DatasetGenerator` -> `BOPDatasetWriter` into a tmpfs directory — reporting, separately,
 
   e2e_no_writer     frames/s of the generator loop alone (products land in pinned host memory: bench.py's `e2e`),
-  e2e_with_writer   frames/s with PNG encoding (OpenCV, one frame per writer thread) and the JSON files, per number of
-                    writer threads -> the core count at which the host stops being the limiter (or the box runs out),
+  e2e_with_writer   frames/s with PNG files and the JSON files, per number of writer threads, for both encoders: the host
+                    one (OpenCV / libpng, one frame per writer thread) and pg_png_encode (streams made on the GPU, the
+                    host only frames them) -> the core count at which the host stops being the limiter,
   sweep             the whole slice with the best thread count, scene switches (cloud synthesis excluded, scene build,
                     calibration) inside the clock.
 
@@ -47,7 +48,7 @@ def main():
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--threads", default="2,4,8,16,32")
-    ap.add_argument("--probe-views", type=int, default=60, help="views of scene 0 used for the writer-thread probe")
+    ap.add_argument("--probe-views", type=int, default=100, help="views of scene 0 used for the writer-thread probe")
     ap.add_argument("--out", default="/dev/shm/pg_c5")
     ap.add_argument("--seed", type=int, default=0)
     args = ap.parse_args()
@@ -117,9 +118,12 @@ def main():
     torch.cuda.synchronize()
     no_writer = n_probe / (time.perf_counter() - t)
     probe = []
-    for nt in [int(x) for x in args.threads.split(",")]:
-        g2 = DatasetGenerator(scene, W, H, frames_in_flight=3, writer_threads=nt)
+    for on_gpu, nt in [(g, int(x)) for g in (False, True) for x in args.threads.split(",")]:
+        g2 = DatasetGenerator(scene, W, H, frames_in_flight=3, writer_threads=nt, png_on_gpu=on_gpu)
         g2.pair_capacity = gen.pair_capacity
+        if on_gpu:
+            g2._calibrate_png(cams[::max(1, len(cams) // 16)], None)  # untimed set-up, like the pair capacity
+            torch.cuda.synchronize()
         tag = f"probe_t{nt}"
         wr = writer_for(spec0, tag)
         t = time.perf_counter()
@@ -127,7 +131,9 @@ def main():
         wr.close()  # joins the writer threads, flushes scene_camera.json / scene_gt.json
         dt = time.perf_counter() - t
         nbytes = dir_bytes(os.path.join(out_root, tag))
-        probe.append({"writer_threads": nt, "frames_per_s": n_probe / dt, "mb_per_frame": nbytes / n_probe / 1e6})
+        probe.append({"png": "gpu" if on_gpu else "host", "writer_threads": nt, "frames_per_s": n_probe / dt,
+                      "file_mb_per_frame": nbytes / n_probe / 1e6, "d2h_mb_per_frame": g2.d2h_bytes_per_frame / 1e6,
+                      "png_fallbacks": g2.png_fallbacks})
         shutil.rmtree(os.path.join(out_root, tag), ignore_errors=True)
         del g2
     best = max(probe, key=lambda p: p["frames_per_s"])
@@ -146,7 +152,8 @@ def main():
         synth_s += time.perf_counter() - ts  # stands for reading PLY files: not part of the clock
         tb = time.perf_counter()
         scene, cams, poses, metas = build(it.scene)
-        g = DatasetGenerator(scene, W, H, frames_in_flight=3, writer_threads=best["writer_threads"])
+        g = DatasetGenerator(scene, W, H, frames_in_flight=3, writer_threads=best["writer_threads"],
+                             png_on_gpu=best["png"] == "gpu")
         fr = list(range(it.first_view, it.first_view + it.n_views))
         scene.set_poses(poses)
         g.calibrate([cams[f] for f in fr[::max(1, len(fr) // 16)]], margin=1.25)
@@ -166,7 +173,7 @@ def main():
         res.update({
             "e2e_no_writer": {"value": no_writer * world, "unit": "frames/s", "views": n_probe,
                               "what": "DatasetGenerator alone on this rank's first scene x world"},
-            "e2e_with_writer": probe, "best_writer_threads": best["writer_threads"],
+            "e2e_with_writer": probe, "best": {"png": best["png"], "writer_threads": best["writer_threads"]},
             "sweep": {"value": total / wall_max, "unit": "frames/s", "frames": int(total), "wall_s": wall_max,
                       "scene_builds_rank0": len(items), "scene_build_s_rank0": build_s,
                       "what": "whole slice incl. scene builds + calibration, cloud synthesis excluded"},
