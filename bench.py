@@ -510,6 +510,50 @@ def measure(wl, K_steps, W_steps, numerics, want_stats=True, want_e2e=True):
     return res
 
 
+def with_writer(wl, cap, numerics, frames, host_frames):
+    """frames/s of the generator loop WITH its consumer — BOPDatasetWriter into a tmpfs directory (PNG files + BOP JSON;
+    /root/reference/pegasus.py:333-365) — once with the PNG streams made on the GPU (pg_png_encode; the writer threads
+    only frame them) and, on fewer frames, with the host encoder (OpenCV / libpng inside the writer threads)."""
+    import shutil
+    import tempfile
+    import torch
+    from pegasus_b200 import BOPDatasetWriter, DatasetGenerator, ObjectMeta
+    spec = wl.spec
+    Wd, Hd = spec["width"], spec["height"]
+    root = tempfile.mkdtemp(prefix="pg_bench_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    threads = max(2, min(16, (os.cpu_count() or 4)))
+    metas = [ObjectMeta.from_points(k, wl.objs[k]["xyz"]) for k in sorted(wl.objs)]
+    fx = 0.5 * Wd / math.tan(0.5 * wl.cams[0].FoVx)
+    res = {"writer_threads": threads, "host_cores": os.cpu_count(), "out": "tmpfs" if root.startswith("/dev/shm") else "tmp"}
+    try:
+        for tag, on_gpu, n in (("gpu_png", True, frames), ("host_png", False, host_frames)):
+            gen = DatasetGenerator(wl.scene, Wd, Hd, bg=wl.bg, frames_in_flight=3, writer_threads=threads, numerics=numerics,
+                                   png_on_gpu=on_gpu)
+            gen.pair_capacity = cap
+            cams = [wl.cams[i % len(wl.cams)] for i in range(n)]
+            pk = torch.stack([wl.packets_host[i % wl.n_pose_frames] for i in range(n)]) if wl.K else None
+            if on_gpu:  # untimed set-up, like the pair capacity: per-scene Huffman tables + stream capacities
+                gen._calibrate_png(wl.cams[::max(1, len(wl.cams) // 16)], None)
+            gen.generate(cams[:6], pose_packets=None if pk is None else pk[:6])  # warm-up
+            wr = BOPDatasetWriter(tag, root, fx, fx, Wd, Hd, Wd, Hd, scene_id=0)
+            torch.cuda.synchronize()
+            t = time.perf_counter()
+            st = gen.generate(cams, pose_packets=pk, writer=wr, metas=metas if wl.K else None)
+            wr.close()  # joins the writer threads, flushes scene_camera.json / scene_gt.json
+            dt = time.perf_counter() - t
+            nbytes = sum(os.path.getsize(os.path.join(r, f)) for r, _, fs in os.walk(os.path.join(root, tag)) for f in fs)
+            res[tag] = {"value": st["frames"] / dt, "unit": UNIT, "frames": st["frames"],
+                        "d2h_bytes_per_step": gen.d2h_bytes_per_frame, "file_bytes_per_step": nbytes / max(st["frames"], 1),
+                        "png_fallbacks": gen.png_fallbacks}
+            shutil.rmtree(os.path.join(root, tag), ignore_errors=True)
+            del gen
+    finally:
+        shutil.rmtree(root, ignore_errors=True)
+    res["what"] = ("DatasetGenerator -> BOPDatasetWriter: %d PNG files per frame + scene_gt / scene_camera JSON, wall clock "
+                   "from the first frame issued to the last file closed" % (3 + 2 * max(wl.K, 1)))
+    return res
+
+
 def time_launches(fn, n, stream):
     """Mean milliseconds of n back-to-back calls of fn() on `stream` (CUDA events, after 3 warm-up calls)."""
     import torch
@@ -640,6 +684,12 @@ def run_ours(args):
         gbs = (1.0 + 1.0 / 8) * nc * Wd * Hd / (t * 1e-3) / 1e9
         stages.append({"stage": "pack_masks", "ms": t, "share": None, "bound": "hbm", "achieved": gbs, "peak": hbm_peak,
                        "unit": "GB/s", "frac": gbs / hbm_peak, "what": "per plane 1 B read + 1 bit written per pixel; x2 per frame"})
+
+        # ---- the consumer (SURVEY §8 e asks for kernels-only and end-to-end separately): files on tmpfs
+        try:
+            extras["e2e_with_writer"] = with_writer(wl, cap, args.numerics, max(K_steps, 30), 24)
+        except Exception as e:  # noqa: BLE001 - a sub-record must not take the headline down
+            extras["e2e_with_writer"] = {"error": repr(e)}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
