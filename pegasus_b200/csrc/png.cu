@@ -34,6 +34,7 @@ struct PngImage {
     const uint32_t* table;
     uint32_t* row_bits;             // [H]
     unsigned long long* row_adler;  // [H][2]: sum of the row's stream bytes, sum of (L - i) * byte i
+    uint16_t* thread_bits;          // [H][PNG_THREADS] bits of each thread's tokens (size kernel -> write kernel)
     uint32_t* hist;
     uint32_t* result;
     uint32_t out_capacity;
@@ -199,21 +200,31 @@ struct ZeroRow {
 // run start at or after i1 (L: none) — with it the length of a chunk is found inside the thread's own positions.
 template <class Lit, class Len>
 __device__ __forceinline__ void png_walk(const uint8_t* f, int L, int i0, int i1, int s, int nxt, Lit&& lit, Len&& len) {
-    for (int i = i0; i < i1; ++i) {
-        const uint8_t b = f[i];
-        if (i == 0 || b != f[i - 1]) s = i;
-        const int k = i - s;
-        if (k == 0) { lit(i, b); continue; }
-        const int off = (k - 1) % 258;        // position inside its chunk of the run's repeats
-        if (off >= 3) continue;               // inside a match of >= 4 bytes
-        const int cs = i - off;               // chunk start
-        const bool ge3 = cs + 2 < L && f[cs + 1] == b && f[cs + 2] == b;
-        if (!ge3) { lit(i, b); continue; }    // chunk of 1 or 2 bytes: literals
-        if (off == 0) {
-            int e = i + 1;                    // first position after the run: inside this thread's positions, else nxt
-            while (e < i1 && f[e] == b) ++e;
-            if (e == i1) e = nxt;
-            len(i, min(258, e - cs));
+    if (i0 >= i1) return;
+    const uint32_t* fw = reinterpret_cast<const uint32_t*>(f);  // i0 is a multiple of 4: four positions per load
+    uint32_t prev = i0 > 0 ? f[i0 - 1] : 0x100u;                // 0x100: no byte equals it, position 0 starts a run
+    for (int wb = i0; wb < i1; wb += 4) {
+        const uint32_t word = fw[wb >> 2];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int i = wb + j;
+            if (i >= i1) break;
+            const uint32_t b = (word >> (8 * j)) & 255u;
+            if (b != prev) s = i;
+            prev = b;
+            const int k = i - s;
+            if (k == 0) { lit(i, b); continue; }
+            const int off = (k - 1) % 258;        // position inside its chunk of the run's repeats
+            if (off >= 3) continue;               // inside a match of >= 4 bytes
+            const int cs = i - off;               // chunk start
+            const bool ge3 = cs + 2 < L && f[cs + 1] == b && f[cs + 2] == b;
+            if (!ge3) { lit(i, b); continue; }    // chunk of 1 or 2 bytes: literals
+            if (off == 0) {
+                int e = i + 1;                    // first position after the run: inside this thread's positions, else nxt
+                while (e < i1 && f[e] == b) ++e;
+                if (e == i1) e = nxt;
+                len(i, min(258, e - cs));
+            }
         }
     }
 }
@@ -230,14 +241,29 @@ __device__ __forceinline__ int png_lpad(int L) { return (L + 15) / 16 * 16; }
 // last (-1: none) and first (L: none) run start among positions [i0, i1)
 __device__ __forceinline__ void png_starts(const uint8_t* f, int L, int i0, int i1, int* last, int* first) {
     int ls = -1, fs = L;
-    for (int i = i0; i < i1; ++i)
-        if (i == 0 || f[i] != f[i - 1]) {
-            ls = i;
-            fs = min(fs, i);
+    if (i0 < i1) {
+        const uint32_t* fw = reinterpret_cast<const uint32_t*>(f);
+        uint32_t prev = i0 > 0 ? f[i0 - 1] : 0x100u;
+        for (int wb = i0; wb < i1; wb += 4) {
+            const uint32_t word = fw[wb >> 2];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int i = wb + j;
+                const uint32_t b = (word >> (8 * j)) & 255u;
+                if (i < i1 && b != prev) {
+                    ls = i;
+                    fs = min(fs, i);
+                }
+                prev = b;
+            }
         }
+    }
     *last = ls;
     *first = fs;
 }
+
+// positions per thread: the row split evenly over the CTA, rounded up to whole words
+__device__ __forceinline__ int png_seg(int L) { return ((L + PNG_THREADS - 1) / PNG_THREADS + 3) & ~3; }
 
 __global__ void __launch_bounds__(PNG_THREADS) png_size_kernel(const PngBatch B) {
     extern __shared__ __align__(16) unsigned char png_smem[];
@@ -274,7 +300,7 @@ __global__ void __launch_bounds__(PNG_THREADS) png_size_kernel(const PngBatch B)
     }
     for (int i = threadIdx.x; i < PNG_TOKENS; i += PNG_THREADS) sm.tok[i] = __ldg(im.table + i);
     __syncthreads();
-    const int S = (L + PNG_THREADS - 1) / PNG_THREADS;
+    const int S = png_seg(L);
     const int i0 = min(L, (int)threadIdx.x * S), i1 = min(L, i0 + S);
     int my_last, my_first;
     png_starts(f, L, i0, i1, &my_last, &my_first);
@@ -297,6 +323,7 @@ __global__ void __launch_bounds__(PNG_THREADS) png_size_kernel(const PngBatch B)
     }
     uint32_t total;
     block_excl_sum(bits, sm.tmp, &total);
+    im.thread_bits[(size_t)row * PNG_THREADS + threadIdx.x] = (uint16_t)bits;
     const unsigned long long A = block_sum64(sumA, sm.tmp64);
     const unsigned long long Bs = block_sum64(sumB, sm.tmp64);
     if (threadIdx.x == 0) {
@@ -350,15 +377,13 @@ __global__ void __launch_bounds__(PNG_THREADS) png_write_kernel(const PngBatch B
     } else {
         for (int i = threadIdx.x; i < PNG_TOKENS; i += PNG_THREADS) sm.tok[i] = __ldg(im.table + i);
         __syncthreads();  // tokens staged; out_s is clear as well
-        const int S = (L + PNG_THREADS - 1) / PNG_THREADS;
+        const int S = png_seg(L);
         const int i0 = min(L, (int)threadIdx.x * S), i1 = min(L, i0 + S);
         int my_last, my_first;
         png_starts(f, L, i0, i1, &my_last, &my_first);
         const int s0 = block_excl_max(my_last, reinterpret_cast<int*>(sm.tmp));
         const int nx = block_excl_min_after(my_first, L, reinterpret_cast<int*>(sm.tmp));
-        uint32_t bits = 0;
-        png_walk(f, L, i0, i1, s0, nx, [&](int, uint8_t b) { bits += sm.tok[T_LIT + b] >> 24; },
-                 [&](int, int cl) { bits += sm.tok[T_LEN + cl - 3] >> 24; });
+        const uint32_t bits = im.thread_bits[(size_t)row * PNG_THREADS + threadIdx.x];  // counted by the size kernel
         uint32_t total;
         const uint32_t excl = block_excl_sum(bits, sm.tmp, &total);
         // second walk: place the tokens.  64-bit accumulator; a word is stored plainly once this thread has produced
@@ -456,8 +481,9 @@ int launch_png_encode(int n_images, const pg_png_image* images, int width, int h
             d.out = s.out;
             d.table = s.table;
             d.row_bits = reinterpret_cast<uint32_t*>(s.scratch);
-            d.row_adler = reinterpret_cast<unsigned long long*>(reinterpret_cast<unsigned char*>(s.scratch) +
-                                                                (((size_t)height * 4 + 15) / 16 * 16));
+            unsigned char* sc = reinterpret_cast<unsigned char*>(s.scratch);
+            d.row_adler = reinterpret_cast<unsigned long long*>(sc + (((size_t)height * 4 + 15) / 16 * 16));
+            d.thread_bits = reinterpret_cast<uint16_t*>(sc + (((size_t)height * 4 + 15) / 16 * 16) + (size_t)height * 16);
             d.hist = s.hist;
             d.result = s.result;
             d.out_capacity = s.out_capacity;
