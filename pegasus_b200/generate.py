@@ -35,6 +35,7 @@ import torch
 from . import _lib
 from . import png_codec
 from .png_gpu import FramePngEncoder, PngTables
+from .rasterizer import grown_capacity
 from .scene import ComposedScene
 from .sh_rotation import POSE_WORDS, generate_pose_packets
 
@@ -97,10 +98,12 @@ class DatasetGenerator:
         self.outs = [scene.alloc_outputs(W, H, masks=True) for _ in range(self.nslot)]
         self.Wb = (W + 7) // 8  # bytes per row of a bit-packed mask plane (pg_pack_masks)
         self.packs = [dict(rgb=torch.empty((H, W, 3), dtype=torch.uint8, device=dev),
-                           depth=torch.empty((H, W), dtype=torch.int16, device=dev),
-                           visible=torch.empty((nc, H, self.Wb), dtype=torch.uint8, device=dev),
-                           silhouette=torch.empty((nc, H, self.Wb), dtype=torch.uint8, device=dev))
+                           depth=torch.empty((H, W), dtype=torch.int16, device=dev))
                       for _ in range(self.nslot)]
+        if not png_on_gpu:  # the bit-packed mask planes are the raw path's wire format
+            for pk in self.packs:
+                pk.update(visible=torch.empty((nc, H, self.Wb), dtype=torch.uint8, device=dev),
+                          silhouette=torch.empty((nc, H, self.Wb), dtype=torch.uint8, device=dev))
         self.cam_dev = [_CameraSlot(dev) for _ in range(self.nslot)]
         self.pose_dev = [torch.zeros((max(self.K, 1), POSE_WORDS), dtype=torch.float32, device=dev)
                          for _ in range(self.nslot)]
@@ -109,13 +112,15 @@ class DatasetGenerator:
         n_sets = host_sets if host_sets is not None else self.nslot + self.writer_threads
         self._free: "queue.Queue[Dict[str, torch.Tensor]]" = queue.Queue()
         for _ in range(max(n_sets, self.nslot)):
-            self._free.put(dict(rgb=torch.empty((H, W, 3), dtype=torch.uint8).pin_memory(),
-                                depth=torch.empty((H, W), dtype=torch.int16).pin_memory(),
-                                sem_seg=torch.empty((H, W, 3), dtype=torch.uint8).pin_memory(),
-                                visible=torch.empty((nc, H, self.Wb), dtype=torch.uint8).pin_memory(),
-                                silhouette=torch.empty((nc, H, self.Wb), dtype=torch.uint8).pin_memory(),
-                                # the frame's pg_status, copied by the library at the end of the frame
-                                status=torch.zeros(_lib.STATUS_WORDS, dtype=torch.int32).pin_memory()))
+            # the frame's pg_status, copied by the library at the end of the frame
+            hs = dict(status=torch.zeros(_lib.STATUS_WORDS, dtype=torch.int32).pin_memory())
+            if not png_on_gpu:  # raw products; with PNG streams from the GPU the sets hold the streams (_calibrate_png)
+                hs.update(rgb=torch.empty((H, W, 3), dtype=torch.uint8).pin_memory(),
+                          depth=torch.empty((H, W), dtype=torch.int16).pin_memory(),
+                          sem_seg=torch.empty((H, W, 3), dtype=torch.uint8).pin_memory(),
+                          visible=torch.empty((nc, H, self.Wb), dtype=torch.uint8).pin_memory(),
+                          silhouette=torch.empty((nc, H, self.Wb), dtype=torch.uint8).pin_memory())
+            self._free.put(hs)
         self.h2d_bytes_per_frame = 35 * 4
         # u8 RGB + u16 depth + u8 sem-seg per pixel, the 2 x nc masks as ONE BIT per pixel: they are most of the
         # planes of a frame, and with 8 GPUs per host the D2H stream is what the host side saturates first
@@ -149,14 +154,18 @@ class DatasetGenerator:
             o = sc.render(cam, self.bg, masks=True, out=self.outs[0], sync_check=True, numerics=self.numerics)
             max_R = max(max_R, o["num_stored"])
         self.pair_capacity = int(max_R * margin) + 4096
-        for sl in range(self.nslot):
-            with torch.cuda.stream(self.streams[sl]):
-                sc.render(cams[0], self.bg, masks=True, out=self.outs[sl], sync_check=True,
-                          pair_capacity=self.pair_capacity, slot=sl, numerics=self.numerics)
-        torch.cuda.synchronize(self.dev)
+        self._size_slots(cams[0])
         if self.png_on_gpu:
             self._calibrate_png(cams, pose_packets)
         return self.pair_capacity
+
+    def _size_slots(self, cam) -> None:
+        """(Re)allocates every slot's workspace for the current pair capacity (one throw-away frame per slot)."""
+        for sl in range(self.nslot):
+            with torch.cuda.stream(self.streams[sl]):
+                self.scene.render(cam, self.bg, masks=True, out=self.outs[sl], sync_check=True,
+                                  pair_capacity=self.pair_capacity, slot=sl, numerics=self.numerics)
+        torch.cuda.synchronize(self.dev)
 
     def _pack_slot(self, sl: int, st: torch.cuda.Stream) -> None:
         L, o = _lib.load(), self.outs[sl]
@@ -298,24 +307,23 @@ class DatasetGenerator:
             R0, t0 = first_pose if first_pose is not None else (None, None)
         inflight: List[Optional[tuple]] = [None] * self.nslot
         futures = []
-        stats = dict(frames=0, overflow=0)
+        stats = dict(frames=0, overflow=0, regrown=0)
         # sticky overflow counters of the slots' workspaces before this call (calibration may have overflowed on purpose)
         self._overflow_seen = {sl: sc.read_status(slot=sl)["overflow_frames"] for sl in range(self.nslot)}
 
         def retire(sl):
+            """Hands the slot's finished frame to the writer.  Returns None, or (sequence index, pairs needed) of a
+            frame that exceeded the pair capacity: its products are invalid and never reach the writer."""
             job = inflight[sl]
             if job is None:
-                return
-            f, cam, host, pose_row = job
+                return None
+            f, cam, host, pose_row, seq = job
             self.done_ev[sl].synchronize()
             inflight[sl] = None
             if int(host["status"][1]):
-                # the frame's deepest pairs were dropped: its products are invalid and must not reach the writer
                 need = int(host["status"][5]) & 0xFFFFFFFF
                 self._free.put(host)
-                raise RuntimeError(f"frame {f}: the stored (tile, Gaussian) pairs exceeded the pair capacity "
-                                   f"{self.pair_capacity} (needed {need}); calibrate() over the views rendered or raise "
-                                   "`margin`")
+                return seq, need
             stats["frames"] += 1
             W_ = self.W
             png_streams = None
@@ -369,15 +377,43 @@ class DatasetGenerator:
             else:
                 self._free.put(host)
 
-        for i, f in enumerate(mine):
+        def regrow(seq, need):
+            """A frame outgrew the pair capacity (the calibration views were not the worst): every frame in flight was
+            issued after it and is discarded, the capacity grows to the measured demand (at least doubles), the
+            slots' workspaces are re-sized, and rendering resumes AT that frame.  Nothing invalid was written."""
+            for s2 in range(self.nslot):
+                job = inflight[s2]
+                if job is not None:
+                    self.done_ev[s2].synchronize()
+                    self._free.put(job[2])
+                    inflight[s2] = None
+            if self.pair_capacity >= (1 << 30):
+                raise RuntimeError(f"frame {mine[seq]}: the (tile, Gaussian) pairs exceed the supported maximum of 2^30")
+            self.pair_capacity = grown_capacity(self.pair_capacity, {"max_pairs_needed": need})
+            stats["regrown"] += 1
+            self._size_slots(cams[mine[seq]])
+            self._overflow_seen = {s2: sc.read_status(slot=s2)["overflow_frames"] for s2 in range(self.nslot)}
+            return seq
+
+        i, n_mine, issued_first = 0, len(mine), False
+        while True:
             sl = i % self.nslot
-            retire(sl)
+            bad = retire(sl)
+            if bad is not None:
+                i = regrow(*bad)
+                continue
+            if i >= n_mine:
+                if all(j is None for j in inflight):
+                    break
+                i += 1  # drain: visit the remaining slots in issue order
+                continue
+            f = mine[i]
             host = self._free.get()  # blocks while every set is with the writer (back-pressure)
             pose_row = None if (per_frame is None or static) else per_frame[f]
-            self._issue(i, sl, cams[f], cam_host[i], pose_row, host, first=(i == 0))
-            inflight[sl] = (f, cams[f], host, pose_row if pose_row is not None else (per_frame[0] if per_frame is not None else None))
-        for k in range(self.nslot):
-            retire((len(mine) + k) % self.nslot)
+            self._issue(i, sl, cams[f], cam_host[i], pose_row, host, first=not issued_first)
+            issued_first = True
+            inflight[sl] = (f, cams[f], host, pose_row if pose_row is not None else (per_frame[0] if per_frame is not None else None), i)
+            i += 1
         for fu in futures:
             fu.result()
         if pool is not None:
@@ -389,8 +425,7 @@ class DatasetGenerator:
                 self._overflow_seen[sl] = ov
                 stats["overflow"] += 1
         if stats["overflow"]:
-            raise RuntimeError("pair capacity overflowed while generating; call calibrate() over the views rendered "
-                               "or raise `margin`")
+            raise RuntimeError("a frame exceeded the pair capacity without its status block saying so")
         return stats
 
     def _pose_Rt(self, packet: torch.Tensor):

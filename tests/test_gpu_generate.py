@@ -244,3 +244,32 @@ def test_gpu_png_capacity_overflow_falls_back_per_frame(tmp_path):
     for f, r in enumerate(ref):
         assert np.array_equal(cv2.imread(str(root / "rgb" / f"{f:06d}.png"), cv2.IMREAD_UNCHANGED)[:, :, ::-1], r["rgb"])
         assert np.array_equal(cv2.imread(str(root / "depth" / f"{f:06d}.png"), cv2.IMREAD_UNCHANGED), r["depth"])
+
+
+@pytest.mark.parametrize("png_on_gpu", [False, True])
+def test_pair_capacity_overflow_regrows_and_resumes(png_on_gpu, tmp_path):
+    """A pair capacity that is too small for some frames (calibration missed the worst view): the generator discards
+    the frames in flight, grows the capacity to the measured demand, resumes at the failed frame — and the dataset is
+    the one a sufficient capacity produces.  Nothing of an overflowed frame reaches the writer."""
+    import cv2
+    from pegasus_b200 import BOPDatasetWriter, DatasetGenerator
+    scene, cams, poses, _ = _scene_and_path(n_frames=7)
+    W, H = cams[0].image_width, cams[0].image_height
+    ref = _sequential(scene, cams, poses)
+    gen = DatasetGenerator(scene, W, H, frames_in_flight=3, writer_threads=2, png_on_gpu=png_on_gpu)
+    full = gen.calibrate(cams, None)
+    gen.pair_capacity = max(1 << 10, full // 3)  # too small for every frame; regrowth is clamped to >= 2^20 pairs
+    gen._size_slots(cams[0])
+    seen = []
+    writer = BOPDatasetWriter("ds", tmp_path, 438.2178, 492.5640, 640, 480, W, H, scene_id=0, async_writes=False)
+    stats = gen.generate(cams, poses=poses, writer=writer, on_frame=lambda f, p: seen.append(f))
+    writer.close()
+    assert stats["frames"] == len(cams) and stats["regrown"] >= 1 and gen.pair_capacity >= full // 3
+    assert sorted(seen) == list(range(len(cams)))  # every frame delivered exactly once
+    root = tmp_path / "ds" / "train" / "000000"
+    for f, r in enumerate(ref):
+        assert np.array_equal(cv2.imread(str(root / "rgb" / f"{f:06d}.png"), cv2.IMREAD_UNCHANGED)[:, :, ::-1], r["rgb"])
+        assert np.array_equal(cv2.imread(str(root / "depth" / f"{f:06d}.png"), cv2.IMREAD_UNCHANGED), r["depth"])
+        for idx in range(2):
+            assert np.array_equal(cv2.imread(str(root / "mask_visib" / f"{f:06d}_{idx:06d}.png"), cv2.IMREAD_UNCHANGED),
+                                  r["visible"][idx] * 255)
