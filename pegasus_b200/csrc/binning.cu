@@ -1,8 +1,11 @@
-// binning.cu — tile binning after the depth sort (re-designed):
-//   emit_kernel      : key duplication in DEPTH order as a pure writer (output offsets come from the scan of the
-//                      per-Gaussian pair counts preprocess made: sort.cu scan_counts_kernel), one lane per
-//                      rectangle ROW: writes (tile id, Gaussian index) pairs.  48 B read per visible Gaussian,
-//                      8 B written per pair.  Also accumulates the digit histograms of both tile-sort passes
+// binning.cu — tile binning after the depth sort (re-designed as count -> scan -> write):
+//   count_kernel     : the only gather of the stage (one 48-byte record per visible Gaussian, in depth order); one lane
+//                      per rectangle ROW computes the run of tiles that can contribute and leaves it, with the
+//                      round / group / CTA pair counts, in depth-ordered tables.  No dependency between CTAs.
+//   pair_scan_kernel : one CTA scans the per-CTA totals; finalises the pair count, the overflow flag, sticky status.
+//   emit_kernel      : key duplication in DEPTH order as a pure writer: every warp knows its output offset on entry,
+//                      reads the runs back coalesced and writes (tile id, Gaussian index) pairs pair-parallel: 8 B
+//                      written per pair.  Also accumulates the digit histograms of both tile-sort passes
 //                      (shared-memory reductions: per pair for the low digit, per run for the high digit).
 //   tile_scan_kernel : exclusive digit bases of both tile-sort passes.
 //   tile_order_kernel: normalises the tile ranges the last sort pass reduced (identifyTileRanges happens

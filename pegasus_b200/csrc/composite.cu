@@ -1,13 +1,12 @@
-// composite.cu — per-tile front-to-back alpha compositing, one CTA per 16x16 tile,
-// warp-specialised: one PRODUCER warp stages the tile's sorted list, the CONSUMER warps own pixel blocks.
+// composite.cu — per-tile front-to-back alpha compositing: the ABI-side argument set-up and
+// launch selection, plus composite2_kernel, the round-1 kernel (one CTA per 16x16 tile, warp-specialised producer /
+// consumers, two pixels per lane in packed FP32, exact arithmetic only).  The default kernel is composite3_kernel
+// (composite3.cu); composite2_kernel stays for two jobs:
+//   * the counting runs (settings.debug bit 1 -> pg_read_stats): its STATS instantiation counts pair evaluations,
+//     exps, blends and warp-level hits of the same walk in exact arithmetic;
+//   * PG_COMP_VARIANT=20: a second implementation of the same arithmetic for A/B measurements and cross-checks.
 //
-//   composite2_kernel (default): 4 consumer warps, 8x8 pixels each, TWO pixels per lane in packed FP32
-//                                (FFMA2 / FMUL2 / FADD2), branch-free blending — see the block comment above it.
-//   composite_kernel           : the 1-pixel-per-lane kernel it replaced (8 consumer warps, 8x4 pixels each);
-//                                kept as PG_COMP_VARIANT=0..9 for A/B measurements and as a second
-//                                implementation of the same arithmetic.
-//
-// Walk of a tile's sorted list, per batch of up to COMP_BATCH entries:
+// Walk of a tile's sorted list, per batch of up to COMP_BATCH entries (shared with composite3, composite_common.cuh):
 //   1. ids are prefetched by TMA bulk copies (1 KB chunks, double-buffered); entries the binning stage proved
 //      invisible for the whole tile (PG_CULL_FLAG) and, once every main chain has terminated, environment
 //      entries are dropped by a ballot compaction — they are never fetched;
@@ -38,256 +37,13 @@ namespace pg {
 // COMP_STAGES: depth of the record ring (how far fast warps may run ahead of the slowest one);
 // ILP: hits evaluated together (2: geometry + exp of two hits interleave, blending stays in list order);
 // MINB: CTAs per SM the register allocation is bounded for.
-template <bool MASKS, bool STATS, int COMP_STAGES, int ILP, int MINB, int WAITNS, bool FASTEXP>
-__global__ void __launch_bounds__(COMP_THREADS, MINB) composite_kernel(const CompArgs a) {
-    using CompSmem = CompSmemT<COMP_STAGES>;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    CompSmem& sm = *reinterpret_cast<CompSmem*>(smem_raw);
-    float4* sm_eff = reinterpret_cast<float4*>(smem_raw + sizeof(CompSmem));
-    float* sm_tk = reinterpret_cast<float*>(smem_raw + sizeof(CompSmem) + PG_MAX_OBJECTS * sizeof(float4));
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int tile = (int)a.tile_order[blockIdx.x];
-    const int tile_x = tile % a.gx, tile_y = tile / a.gx;
-    const uint2 range = a.ranges[tile];
-    const int n = (int)(range.y - range.x);
-    const uint32_t lt = (1u << lane) - 1u;
-
-    if (tid == 0) {
-        for (int s = 0; s < COMP_STAGES; ++s) {
-            mbar_init(reinterpret_cast<uint64_t*>(&sm.full[s]), 33);
-            mbar_init(reinterpret_cast<uint64_t*>(&sm.empty[s]), 8);
-        }
-        mbar_init(reinterpret_cast<uint64_t*>(&sm.idbar[0]), 1);
-        mbar_init(reinterpret_cast<uint64_t*>(&sm.idbar[1]), 1);
-        sm.warps_done = 0;
-        sm.warps_main_done = 0;
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (MASKS && tid < a.num_objects)
-        sm_eff[tid] = make_float4(a.eff_color[tid][0], a.eff_color[tid][1], a.eff_color[tid][2], 0.0f);
-    __syncthreads();
-
-    if (warp == 8) {
-        composite_producer<MASKS, COMP_STAGES, 8, WAITNS>(a, sm, tile, range, n, lane, lt);
-        return;
-    }
-
-    // =========================== CONSUMERS ===========================
-    const int wx0 = tile_x * PG_TILE + (warp & 1) * 8, wy0 = tile_y * PG_TILE + (warp >> 1) * 4;
-    const int px = wx0 + (lane & 7), py = wy0 + (lane >> 3);
-    const bool inside = px < a.W && py < a.H;
-    float pfx = (float)px, pfy = (float)py;
-    asm volatile("" : "+f"(pfx), "+f"(pfy));  // keep them in registers: never rematerialise in the hit loop
-    // pixel-centre extent of this warp's block, clipped to the image
-    const float bx0 = (float)wx0, bx1 = (float)min(wx0 + 7, a.W - 1);
-    const float by0 = (float)wy0, by1 = (float)min(wy0 + 3, a.H - 1);
-    const int K = MASKS ? a.num_objects : 0;
-    const uint32_t all_k = K >= 32 ? 0xFFFFFFFFu : ((1u << K) - 1u);
-    float* my_tk = sm_tk + (warp * 32 + lane);  // object k's chain at my_tk[k * 256]
-    if (MASKS)
-        for (int k = 0; k < K; ++k) my_tk[k * 256] = 1.0f;
-
-    // A finished chain keeps its transmittance with the sign flipped (T > 0 always while alive, since a
-    // chain stops before T would drop below 1e-4): one compare serves "already done" and "done now".
-    float T = inside ? 1.0f : -1.0f, C0 = 0.0f, C1 = 0.0f, C2 = 0.0f, D = 0.0f;
-    float To = (inside && MASKS) ? 1.0f : -1.0f, S0 = 0.0f, S1 = 0.0f, S2 = 0.0f;
-    uint32_t done_k = (inside && MASKS) ? 0u : 0xFFFFFFFFu;
-    uint32_t last = 0;
-    uint32_t n_eval = 0, n_exp = 0, n_blend = 0;
-    bool w_main_done = false, w_done = false;  // warp-uniform, already reported to the producer
-
-    for (int it = 0;; ++it) {
-        const int s = it % COMP_STAGES;
-        // WAITNS < 0: only parties with nothing to do back off (the producer, finished consumers)
-        if (WAITNS < 0 && w_done) mbar_wait_t<-WAITNS>(reinterpret_cast<uint64_t*>(&sm.full[s]), (uint32_t)((it / COMP_STAGES) & 1));
-        else mbar_wait_t<(WAITNS < 0 ? 0 : WAITNS)>(reinterpret_cast<uint64_t*>(&sm.full[s]), (uint32_t)((it / COMP_STAGES) & 1));
-        const int cnt = *(volatile int*)&sm.cnt[s];
-        if (cnt == 0) break;
-        if (!w_done) {
-            const GeomRec* sr = sm.rec[s];
-            bool wm = !w_main_done;
-            // ---- per 32-entry chunk: lane-parallel cull against this warp's pixel block, then walk
-            //      the hits in list order
-#pragma unroll 1
-            for (int c0 = 0; c0 < cnt; c0 += 32) {
-                const int e = c0 + lane;
-                // objects some pixel of this warp still needs (bit k-1): every object while an objects-only
-                // chain is alive, else those whose silhouette chain is alive somewhere.  Entries of other
-                // objects can no longer change any output of this block and are not walked.
-                uint32_t need = 0;
-                if (MASKS && !wm) {  // while a main chain is alive every entry is wanted anyway
-                    need = __any_sync(0xffffffffu, To > 0.0f) ? all_k : (__reduce_or_sync(0xffffffffu, ~done_k) & all_k);
-                    if (need == 0) break;
-                }
-                bool hit = false;
-                if (e < cnt) {
-                    const float4 A = sr[e].a;
-                    const float4 B = sr[e].b;
-                    const int eo = MASKS ? (__float_as_int(B.w) & 63) : 0;
-                    const bool wanted = wm || (MASKS && eo > 0 && ((need >> ((uint32_t)(eo - 1) & 31u)) & 1u));
-                    hit = wanted && !block_culled(A.x, A.y, A.z, A.w, B.x, B.w, bx0, bx1, by0, by1);
-                }
-                uint32_t mm = __ballot_sync(0xffffffffu, hit);
-                // blend one hit into every chain of this pixel that still wants it (A.7 order of operations)
-                auto blend = [&](const GeomRec* r, const float4& B, float alpha, int obj) {
-                    const float om = sub(1.0f, alpha);
-                    {
-                        const float test_T = mul(T, om);  // negative when the chain is already done
-                        if (test_T < 0.0001f) T = -fabsf(T);
-                        else {
-                            const float4 Cc = r->c;
-                            C0 = fma(mul(Cc.x, alpha), T, C0);
-                            C1 = fma(mul(Cc.y, alpha), T, C1);
-                            C2 = fma(mul(Cc.z, alpha), T, C2);
-                            D = fma(mul(B.z, alpha), T, D);
-                            T = test_T;
-                            if (!MASKS) last = sm.pos[s][r - sr];
-                        }
-                    }
-                    if (MASKS && obj > 0) {
-                        {
-                            const float test_T = mul(To, om);
-                            if (test_T < 0.0001f) To = -fabsf(To);
-                            else {
-                                const float4 ec = sm_eff[obj - 1];
-                                S0 = fma(mul(ec.x, alpha), To, S0);
-                                S1 = fma(mul(ec.y, alpha), To, S1);
-                                S2 = fma(mul(ec.z, alpha), To, S2);
-                                To = test_T;
-                            }
-                        }
-                        const uint32_t kb = (uint32_t)(obj - 1) & 31u;
-                        if (!((done_k >> kb) & 1u)) {
-                            const float test_T = mul(my_tk[(obj - 1) * 256], om);
-                            if (test_T < 0.0001f) done_k |= 1u << kb;
-                            else my_tk[(obj - 1) * 256] = test_T;
-                        }
-                    }
-                };
-                auto power_of = [&](const float4& A, const float4& B) {
-                    const float dx = sub(A.x, pfx), dy = sub(A.y, pfy);
-                    const float w = mul(dy, mul(B.x, dy));
-                    const float sq = fma(dx, mul(A.z, dx), w);
-                    const float bxy = mul(mul(A.w, dx), dy);
-                    return fma(sq, -0.5f, -bxy);
-                };
-                if (ILP == 2 && !STATS) {
-#pragma unroll 1
-                    while (mm) {
-                        const GeomRec* r1 = sr + (c0 + __ffs(mm) - 1);
-                        mm &= mm - 1;
-                        const bool two = mm != 0;  // warp-uniform
-                        const GeomRec* r2 = two ? sr + (c0 + __ffs(mm) - 1) : r1;
-                        mm &= mm - 1;
-                        const float4 A1 = r1->a, B1 = r1->b, A2 = r2->a, B2 = r2->b;
-                        const float p1 = power_of(A1, B1), p2 = power_of(A2, B2);
-                        // both exponentials are evaluated unconditionally (independent chains interleave); a hit
-                        // outside [cut, 0] is discarded by its predicate, exactly like the branch of the ILP == 1 path
-                        const float a1 = fminf(0.99f, mul(B1.y, exp_sel<FASTEXP>(p1)));
-                        const float a2 = fminf(0.99f, mul(B2.y, exp_sel<FASTEXP>(p2)));
-                        const bool v1 = !(p1 > 0.0f) && !(p1 < B1.w) && !(a1 < 1.0f / 255.0f);
-                        const bool v2 = two && !(p2 > 0.0f) && !(p2 < B2.w) && !(a2 < 1.0f / 255.0f);
-                        if (v1) blend(r1, B1, a1, MASKS ? (__float_as_int(B1.w) & 63) : 0);
-                        if (v2) blend(r2, B2, a2, MASKS ? (__float_as_int(B2.w) & 63) : 0);
-                    }
-                } else {
-#pragma unroll 1
-                    while (mm) {
-                        const GeomRec* r = sr + (c0 + __ffs(mm) - 1);
-                        mm &= mm - 1;
-                        const float4 A = r->a;
-                        const float4 B = r->b;
-                        const float power = power_of(A, B);
-                        const int obj = MASKS ? (__float_as_int(B.w) & 63) : 0;  // warp-uniform
-                        bool live = true;  // STATS only: does any chain of this pixel still want this Gaussian?
-                        if (STATS) {
-                            live = T > 0.0f || (MASKS && obj > 0 && (To > 0.0f || !((done_k >> (obj - 1)) & 1u)));
-                            if (live) { ++n_eval; if (!(power > 0.0f) && !(power < B.w)) ++n_exp; }
-                        }
-                        // A.7: power > 0 skips; below the per-Gaussian cut alpha < 1/255 is certain (also a skip)
-                        if (!(power > 0.0f) && !(power < B.w)) {
-                            const float alpha = fminf(0.99f, mul(B.y, exp_sel<FASTEXP>(power)));
-                            if (!(alpha < 1.0f / 255.0f)) {
-                                if (STATS && live) ++n_blend;
-                                blend(r, B, alpha, obj);
-                            }
-                        }
-                    }
-                }
-                // warp-level progress: environment entries are no longer hits once every main chain is done
-                if (wm && __all_sync(0xffffffffu, T < 0.0f)) {
-                    wm = false;
-                    if (!MASKS) break;
-                }
-            }
-            // ---- report progress to the producer
-            if (!w_main_done && !wm) {
-                w_main_done = true;
-                if (lane == 0) atomicAdd(&sm.warps_main_done, 1);
-            }
-            const bool pix_done = T < 0.0f && (!MASKS || (To < 0.0f && (done_k & all_k) == all_k));
-            if (__all_sync(0xffffffffu, pix_done)) {
-                w_done = true;
-                if (lane == 0) atomicAdd(&sm.warps_done, 1);
-            }
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&sm.empty[s]);
-    }
-
-    if (inside) {
-        T = fabsf(T);
-        To = fabsf(To);
-        const size_t HW = (size_t)a.W * a.H, pix = (size_t)py * a.W + px;
-        const float bg0 = a.bg[0], bg1 = a.bg[1], bg2 = a.bg[2];
-        a.out_color[pix] = fma(T, bg0, C0);
-        a.out_color[HW + pix] = fma(T, bg1, C1);
-        a.out_color[2 * HW + pix] = fma(T, bg2, C2);
-        a.out_depth[pix] = D;
-        if (a.out_final_T) a.out_final_T[pix] = T;
-        if (!MASKS && a.out_n_contrib) a.out_n_contrib[pix] = last;
-        if (MASKS) {
-            const float s0 = fma(To, bg0, S0), s1 = fma(To, bg1, S1), s2 = fma(To, bg2, S2);
-            if (a.seg_color) {
-                a.seg_color[pix] = s0; a.seg_color[HW + pix] = s1; a.seg_color[2 * HW + pix] = s2;
-            }
-            if (a.sem_seg) {
-                a.sem_seg[3 * pix] = (uint8_t)(int)mul(s0, 255.0f);
-                a.sem_seg[3 * pix + 1] = (uint8_t)(int)mul(s1, 255.0f);
-                a.sem_seg[3 * pix + 2] = (uint8_t)(int)mul(s2, 255.0f);
-            }
-            if (a.visible) {
-                for (int c = 0; c < a.num_colors; ++c) {
-                    float d0 = sub(s0, a.set_color[c][0]), d1 = sub(s1, a.set_color[c][1]), d2 = sub(s2, a.set_color[c][2]);
-                    float dist = sqrt(add(add(mul(d0, d0), mul(d1, d1)), mul(d2, d2)));
-                    a.visible[(size_t)c * HW + pix] = dist <= 0.1f ? 1 : 0;
-                }
-            }
-            if (a.silhouette) {
-                for (int kk = 0; kk < K; ++kk) {
-                    const int ci = a.color_index[kk];
-                    const float tk = my_tk[kk * 256];
-                    const float4 ec = sm_eff[kk];
-                    const float w = sub(1.0f, tk);
-                    float i0 = fma(tk, bg0, mul(ec.x, w));
-                    float i1 = fma(tk, bg1, mul(ec.y, w));
-                    float i2 = fma(tk, bg2, mul(ec.z, w));
-                    float d0 = sub(i0, a.set_color[ci][0]), d1 = sub(i1, a.set_color[ci][1]), d2 = sub(i2, a.set_color[ci][2]);
-                    float dist = sqrt(add(add(mul(d0, d0), mul(d1, d1)), mul(d2, d2)));
-                    a.silhouette[(size_t)ci * HW + pix] = dist <= 0.1f ? 1 : 0;
-                }
-            }
-        }
-    }
-    if (STATS) flush_stats(a.stats, n_eval, n_exp, n_blend);
-}
 
 // =================================================================================================
 // 2 pixels per thread: packed FP32 (sm_100 FFMA2 / FMUL2 / FADD2 — PTX fma/mul/add.rn.f32x2).
 //
-// The 1-pixel kernel above is issue-bound (83 % issue-active, FMA pipe 41 %, ALU pipe 39 %): every
-// instruction of the hit loop serves 32 pixels.  Here a warp owns an 8x8 pixel block, a lane owns the two
+// A 1-pixel-per-lane kernel is issue-bound (83 % issue-active, FMA pipe 41 %, ALU pipe 39 %, profiles/r1ab_*): every
+// instruction of its hit loop serves 32 pixels.  Here a warp owns an 8x8 pixel block, a lane owns the two
 // vertically adjacent pixels (x, y0) and (x, y0 + 1), and the per-pixel arithmetic of both runs in ONE packed
 // instruction per operation: each half is an individually rounded IEEE binary32 op in the same order as the
 // scalar kernel (the per-Gaussian operands ride along as broadcast scalars, SASS `R.F32`), so results stay
@@ -626,20 +382,8 @@ static int launch_two(const CompArgs& a, dim3 grid, cudaStream_t stream) {
     return PG_OK;
 }
 
-template <bool MASKS, bool STATS, int STAGES, int ILP, int MINB, int WAITNS = 0, bool FASTEXP = false>
-static int launch_one(const CompArgs& a, dim3 grid, cudaStream_t stream) {
-    const int smem = (int)sizeof(CompSmemT<STAGES>) +
-                     (MASKS ? (int)(PG_MAX_OBJECTS * sizeof(float4)) + a.num_objects * 256 * (int)sizeof(float) : 0);
-    PG_CUDA_CHECK(ensure_dynamic_smem(composite_kernel<MASKS, STATS, STAGES, ILP, MINB, WAITNS, FASTEXP>, smem));
-    composite_kernel<MASKS, STATS, STAGES, ILP, MINB, WAITNS, FASTEXP><<<grid, COMP_THREADS, smem, stream>>>(a);
-    return PG_OK;
-}
-
-// PG_COMP_VARIANT (tuning only, read once).  Measured on B200, C2 workload (profiles/README.md):
-//  1-pixel kernel (r1t): 0: 4 stages, ILP 1 -> 1.235 ms; 1: 6 stages 1.222; 3: ILP 2 1.139; 4: ILP 2, registers
-//    bounded for 3 CTAs/SM 1.119; 9: variant 4 with MUFU ex2 (NOT bit-reproducible, measurement only) 1.019.
-//  2-pixel packed kernel (r1ac): 20 (default): ILP 2, 79 registers, 5 CTAs/SM 1.051 ms; 22: 72 registers 1.098;
-//    21: ILP 1 1.176; 28 / 26 / 27: 3-stage ring for 5-6 CTAs/SM 1.175 / 1.211 / 1.261.
+// PG_COMP_VARIANT (tuning only, read once): 30 (default) composite3_kernel; 20 the round-1 composite2_kernel
+// (1.05 ms on the C2 workload where composite3 takes 1.08 exact / 0.95 fast; profiles/README.md).
 static int comp_variant() {
     static int v = -1;
     if (v < 0) {
@@ -660,34 +404,10 @@ int launch_composite(const CompArgs& a, int gy, bool masks, cudaStream_t stream)
         // default: composite3_kernel (composite3.cu).  Statistics runs (debug bit 1) use composite2_kernel below,
         // whose exact arithmetic walks the same hits.
         rc = launch_composite3(a, grid, masks, a.fast != 0, var, stream);
-    } else if (var >= 20) {
-        // 2 pixels per thread, packed FP32 (composite2_kernel).  20: ILP 2, 4 CTAs/SM; 21: ILP 1, 5 CTAs/SM;
-        // 22: ILP 2, 5 CTAs/SM; 23: ILP 2, 6 stages; 24: ILP 1, 6 CTAs/SM; 25: ILP 2, 3 CTAs/SM
-        if (!masks) rc = st ? launch_two<false, true, 4, 1, 4>(a, grid, stream) : launch_two<false, false, 4, 2, 4>(a, grid, stream);
-        else if (st) rc = launch_two<true, true, 4, 1, 4>(a, grid, stream);
-        else {
-            switch (var) {
-                case 21: rc = launch_two<true, false, 4, 1, 5>(a, grid, stream); break;
-                case 22: rc = launch_two<true, false, 4, 2, 5>(a, grid, stream); break;
-                case 23: rc = launch_two<true, false, 6, 2, 4>(a, grid, stream); break;
-                case 24: rc = launch_two<true, false, 4, 1, 6>(a, grid, stream); break;
-                case 25: rc = launch_two<true, false, 4, 2, 3>(a, grid, stream); break;
-                case 26: rc = launch_two<true, false, 3, 2, 6>(a, grid, stream); break;
-                case 27: rc = launch_two<true, false, 3, 1, 6>(a, grid, stream); break;
-                case 28: rc = launch_two<true, false, 3, 2, 5>(a, grid, stream); break;
-                default: rc = launch_two<true, false, 4, 2, 4>(a, grid, stream); break;
-            }
-        }
-    } else if (!masks) rc = st ? launch_one<false, true, 4, 1, 4>(a, grid, stream) : launch_one<false, false, 4, 1, 4>(a, grid, stream);
-    else if (st) rc = launch_one<true, true, 4, 1, 4>(a, grid, stream);
-    else {
-        switch (var) {
-            case 1: rc = launch_one<true, false, 6, 1, 4>(a, grid, stream); break;
-            case 3: rc = launch_one<true, false, 4, 2, 4>(a, grid, stream); break;
-            case 0: rc = launch_one<true, false, 4, 1, 4>(a, grid, stream); break;
-            case 9: rc = launch_one<true, false, 4, 2, 3, 0, true>(a, grid, stream); break;
-            default: rc = launch_one<true, false, 4, 2, 3>(a, grid, stream); break;
-        }
+    } else if (!masks) {
+        rc = st ? launch_two<false, true, 4, 1, 4>(a, grid, stream) : launch_two<false, false, 4, 2, 4>(a, grid, stream);
+    } else {
+        rc = st ? launch_two<true, true, 4, 1, 4>(a, grid, stream) : launch_two<true, false, 4, 2, 4>(a, grid, stream);
     }
     if (rc) return rc;
     PG_CUDA_CHECK(cudaGetLastError());

@@ -107,15 +107,13 @@ __device__ __forceinline__ void flush_stats(unsigned long long* stats, uint32_t 
     }
 }
 
-// Warp-specialised: warp 8 is the PRODUCER (TMA-prefetches the tile's ids in 2 KB chunks, drops
+// Warp-specialised: the CTA's last warp is the PRODUCER (TMA-prefetches the tile's ids in 1 KB chunks, drops
 // culled / no-longer-needed entries by ballot compaction, gathers each surviving 48-byte record into
 // a 4-stage shared-memory ring with cp.async whose completion arrives on the stage's `full`
-// mbarrier); warps 0..7 are
-// CONSUMERS, each owning an 8x4 pixel block: wait `full`, cull the batch lane-parallel against the
-// block, walk the hits, arrive on `empty`.  No CTA-wide barrier in the steady state; a consumer whose
-// 32 pixels are finished keeps releasing stages, the producer stops when all 8 have finished.
+// mbarrier); warps 0..3 are CONSUMERS, each owning an 8x8 pixel block (two pixels per lane): wait `full`, cull
+// the batch lane-parallel against the block, walk the hits, arrive on `empty`.  No CTA-wide barrier in the steady
+// state; a consumer whose pixels are finished keeps releasing stages, the producer stops when all have finished.
 constexpr int COMP_BATCH = 128;
-constexpr int COMP_THREADS = 288;
 
 constexpr int COMP_IDCHUNK = 256;
 constexpr int COMP_PEND = 512;

@@ -2,7 +2,7 @@
 // per-frame launch sequence:
 //
 //   memset(workspace head)                      clear counters, histograms, look-back status
-//   preprocess_kernel                           A.1-A.5, writes GeomRec / depth key / tile rect / radii
+//   preprocess_kernel                           A.1-A.5, writes GeomRec / depth key / radii
 //   compact_hist_kernel + scan_rows_kernel      (depth key, index) of the visible Gaussians in index order + the digit
 //                                               histograms of those keys (4 x 8 bit)
 //   onesweep_pass_kernel x4                     visible Gaussians by depth (stable)
@@ -14,7 +14,10 @@
 //   onesweep_pass_kernel x2                     stored pairs by tile id (stable)  => reference order; the last
 //                                               pass also reduces the tile ranges (identifyTileRanges)
 //   tile_order_kernel                           normalises the ranges, tiles by descending list length
-//   composite_kernel | composite_masks_kernel   A.7 (+ fused K+3 passes)
+//   composite3_kernel<MASKS>                    A.7 (+ fused K+3 passes); composite2_kernel for counting runs
+//
+// Around the frame: pose_kernel (pg_pose_apply), pack_kernel / pack_masks_kernel, png_size_kernel + png_write_kernel
+// (pg_png_encode).
 //
 // Nothing here synchronises with the host: R stays on the device (grids are sized by the pair
 // capacity and surplus CTAs exit), overflow is reported through pg_read_status.
