@@ -11,7 +11,7 @@ for tool in memcheck synccheck racecheck; do
   timeout 900 $SAN --tool $tool --print-limit 20 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/sanitize_$tool.log 2>&1
   echo "$tool smoke(): exit $? | $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY' $OUT/sanitize_$tool.log | tail -1)" >> $OUT/sanitize_summary.txt
 done
-timeout 1500 $SAN --tool memcheck --print-limit 20 python -m pytest tests/test_gpu_render_call.py tests/test_gpu_generate.py -m gpu -x -q \
+timeout 1500 $SAN --tool memcheck --print-limit 20 python -m pytest tests/test_gpu_render_call.py tests/test_gpu_generate.py tests/test_gpu_png.py -m gpu -x -q \
   > $OUT/sanitize_memcheck_tests.log 2>&1
-echo "memcheck tests/test_gpu_render_call.py tests/test_gpu_generate.py: exit $? | $(grep -E 'ERROR SUMMARY' $OUT/sanitize_memcheck_tests.log | tail -1) | $(grep -E 'passed|failed' $OUT/sanitize_memcheck_tests.log | tail -1)" >> $OUT/sanitize_summary.txt
+echo "memcheck tests/test_gpu_render_call.py tests/test_gpu_generate.py tests/test_gpu_png.py: exit $? | $(grep -E 'ERROR SUMMARY' $OUT/sanitize_memcheck_tests.log | tail -1) | $(grep -E 'passed|failed' $OUT/sanitize_memcheck_tests.log | tail -1)" >> $OUT/sanitize_summary.txt
 cat $OUT/sanitize_summary.txt
