@@ -26,6 +26,7 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <utility>
 #include <vector>
@@ -94,10 +95,20 @@ static std::atomic<unsigned long long> g_launches{0};
 void count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
 
 constexpr int kStageEvents = PG_NUM_STAGES + 1;
-static std::vector<cudaEvent_t> g_events;  // [max_frames][kStageEvents]
-static int g_prof_max = 0;
-static std::atomic<int> g_prof_frames{0};
-static thread_local int t_prof_frame = -1;  // slot of the forward in flight on this thread
+// One profiling session = an event table [max_frames][kStageEvents], shared by reference: a forward in flight on
+// another thread keeps the table it started with alive while pg_profile_enable installs the next one.
+struct ProfSession {
+    std::vector<cudaEvent_t> events;
+    int max_frames = 0;
+    std::atomic<int> frames{0};
+    ~ProfSession() {
+        for (cudaEvent_t e : events) cudaEventDestroy(e);
+    }
+};
+static std::mutex g_prof_mu;
+static std::shared_ptr<ProfSession> g_prof;                 // guarded by g_prof_mu
+static thread_local std::shared_ptr<ProfSession> t_prof;    // session of the forward in flight on this thread
+static thread_local int t_prof_frame = -1;                  // its slot in that session
 
 static int check_opts(const pg_launch_opts* o) {
     if (!o) return PG_OK;
@@ -129,12 +140,16 @@ static int comp_join(const pg_launch_opts* o, cudaStream_t stream) {
 
 static void prof_begin_frame() {
     t_prof_frame = -1;
-    if (g_prof_max == 0) return;
-    int f = g_prof_frames.fetch_add(1);
-    if (f < g_prof_max) t_prof_frame = f;
+    {
+        std::lock_guard<std::mutex> lk(g_prof_mu);
+        t_prof = g_prof;
+    }
+    if (!t_prof) return;
+    const int f = t_prof->frames.fetch_add(1);
+    if (f < t_prof->max_frames) t_prof_frame = f;
 }
 static void prof_mark(int stage_boundary, cudaStream_t stream) {
-    if (t_prof_frame >= 0) cudaEventRecord(g_events[(size_t)t_prof_frame * kStageEvents + stage_boundary], stream);
+    if (t_prof_frame >= 0) cudaEventRecord(t_prof->events[(size_t)t_prof_frame * kStageEvents + stage_boundary], stream);
 }
 
 template <typename T>
@@ -389,22 +404,37 @@ int pg_read_stats(const void* ws, uint64_t* host_stats8, pg_stream_t stream) {
 uint64_t pg_launch_count(void) { return (uint64_t)g_launches.load(); }
 
 int pg_profile_enable(int32_t max_frames) {
-    for (cudaEvent_t e : g_events) cudaEventDestroy(e);
-    g_events.clear();
-    g_prof_max = 0;
-    g_prof_frames.store(0);
-    if (max_frames <= 0) return PG_OK;
-    g_events.resize((size_t)max_frames * kStageEvents);
-    for (auto& e : g_events) PG_CUDA_CHECK(cudaEventCreate(&e));
-    g_prof_max = max_frames;
+    std::shared_ptr<ProfSession> next;
+    if (max_frames > 0) {
+        next = std::make_shared<ProfSession>();
+        next->events.resize((size_t)max_frames * kStageEvents);
+        for (auto& e : next->events) {
+            e = nullptr;
+            PG_CUDA_CHECK(cudaEventCreate(&e));
+        }
+        next->max_frames = max_frames;
+    }
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof = next;  // the previous session's events are destroyed when its last forward lets go of it
     return PG_OK;
 }
 
-int32_t pg_profile_frames(void) { int f = g_prof_frames.load(); return f < g_prof_max ? f : g_prof_max; }
+static std::shared_ptr<ProfSession> prof_current() {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    return g_prof;
+}
+
+int32_t pg_profile_frames(void) {
+    const auto p = prof_current();
+    if (!p) return 0;
+    const int f = p->frames.load();
+    return f < p->max_frames ? f : p->max_frames;
+}
 
 int pg_profile_read(int32_t frame, float* stage_ms) {
-    if (frame < 0 || frame >= pg_profile_frames() || !stage_ms) { set_error("bad profile frame"); return PG_ERR_INVALID; }
-    cudaEvent_t* ev = &g_events[(size_t)frame * kStageEvents];
+    const auto p = prof_current();
+    if (!p || frame < 0 || frame >= pg_profile_frames() || !stage_ms) { set_error("bad profile frame"); return PG_ERR_INVALID; }
+    cudaEvent_t* ev = &p->events[(size_t)frame * kStageEvents];
     PG_CUDA_CHECK(cudaEventSynchronize(ev[PG_NUM_STAGES]));
     for (int i = 0; i < PG_NUM_STAGES; ++i) PG_CUDA_CHECK(cudaEventElapsedTime(&stage_ms[i], ev[i], ev[i + 1]));
     return PG_OK;
