@@ -131,3 +131,44 @@ def test_full_hd_frame_round_trip_and_ratio():
     assert len(streams["sem"]) < 0.01 * raw["sem"]
     got = pm.decode_png(pc.KIND_GRAY16, pc.png_file(pc.KIND_GRAY16, W, H, streams["depth"]))
     assert np.array_equal(got, depth)
+
+
+def test_more_images_than_one_launch_batch():
+    """A frame of 32 objects has 3 + 64 images; the library encodes them in batches of 24 per launch pair."""
+    dev = torch.device("cuda", 0)
+    H, W = 33, 200
+    rng = np.random.default_rng(3)
+    imgs = []
+    for k in range(53):
+        m = np.zeros((H, W), np.uint8)
+        m[k % H:, (3 * k) % W:] = 1
+        m[rng.integers(0, H, 5), rng.integers(0, W, 5)] ^= 1
+        imgs.append((f"m{k}", pc.KIND_MASK8, "mask", m))
+    tables = PngTables(dev, ["mask"])
+    enc = FramePngEncoder(tables, W, H, [(n, k, g, to_dev(k, a, dev)) for n, k, g, a in imgs])
+    st = torch.cuda.current_stream(dev)
+    enc.accumulate_hist(st)
+    tables.rebuild_from_hist()
+    out = enc.encode_unbounded(st)
+    for n, k, g, a in imgs:
+        assert zlib.decompress(out[n]) == pm.scanlines(k, a).tobytes(), n
+
+
+def test_strided_source_rows_and_4k_width():
+    """Rows may be strided (a view into a larger buffer); a 3840-wide RGB row still fits the shared-memory staging."""
+    dev = torch.device("cuda", 0)
+    H, W = 6, 3840
+    rng = np.random.default_rng(4)
+    big = rng.integers(0, 256, (H, W + 64, 3), dtype=np.uint8)
+    big[:, 1000:3000] = (9, 9, 200)
+    t = torch.from_numpy(big).to(dev)[:, 32:32 + W]          # pitch (W + 64) * 3, offset 96 bytes
+    d16 = rng.integers(0, 65536, (H, W + 2)).astype(np.uint16)
+    td = torch.from_numpy(d16.view(np.int16).copy()).to(dev)[:, 1:1 + W]   # 2-byte aligned only: the byte path
+    tables = PngTables(dev, ["rgb", "depth"])
+    enc = FramePngEncoder(tables, W, H, [("rgb", pc.KIND_RGB8, "rgb", t), ("depth", pc.KIND_GRAY16, "depth", td)])
+    st = torch.cuda.current_stream(dev)
+    enc.accumulate_hist(st)
+    tables.rebuild_from_hist()
+    out = enc.encode_unbounded(st)
+    assert zlib.decompress(out["rgb"]) == pm.scanlines(pc.KIND_RGB8, big[:, 32:32 + W]).tobytes()
+    assert zlib.decompress(out["depth"]) == pm.scanlines(pc.KIND_GRAY16, d16[:, 1:1 + W]).tobytes()
