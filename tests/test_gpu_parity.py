@@ -372,9 +372,10 @@ def test_composed_frame_matches_reference_k_plus_3_passes():
     for c in synth.orbit_cameras(2, 640, 480, seed=3100):
         cam = Camera(c["R"], c["T"], c["FoVx"], c["FoVy"], c["W"], c["H"])
         ocam = util.oracle_cam(c)
-        # use the device camera tensors' values on the oracle side (host-vs-device matmul may differ by an ulp)
-        ocam["world_view_transform"] = cam.world_view_transform.cpu().numpy()
-        ocam["full_proj_transform"] = cam.full_proj_transform.cpu().numpy()
+        # the product's Camera and the oracle's agree bit for bit on both matrices; the camera centre comes from a
+        # 4x4 inverse (torch's LU vs numpy's: last ulp), so the oracle is given the product's
+        assert np.array_equal(ocam["world_view_transform"], cam.world_view_transform.cpu().numpy())
+        assert np.array_equal(ocam["full_proj_transform"], cam.full_proj_transform.cpu().numpy())
         ocam["camera_center"] = cam.camera_center.cpu().numpy()
         ref = oracle.render_frame_reference(ocam, env_act, posed, colors, bg, activated=True)
         out = sc.render(cam, torch.zeros(3, device="cuda"))
@@ -550,8 +551,10 @@ def test_full_size_properties_1080p_3M():
     inp = dict(means3D=sc.means3D.cpu().numpy(), opacities=sc.opacity.cpu().numpy()[:, None],
                scales=sc.scales.cpu().numpy(), rotations=sc.rotations.cpu().numpy(), shs=sc.shs.cpu().numpy())
     ocam = util.oracle_cam(c)
-    ocam["world_view_transform"] = cam.world_view_transform.cpu().numpy()
-    ocam["full_proj_transform"] = cam.full_proj_transform.cpu().numpy()
+    # the product's Camera and the oracle's agree bit for bit on both matrices; the camera centre comes from a 4x4
+    # inverse (torch's LU vs numpy's: last ulp), so the oracle is given the product's
+    assert np.array_equal(ocam["world_view_transform"], cam.world_view_transform.cpu().numpy())
+    assert np.array_equal(ocam["full_proj_transform"], cam.full_proj_transform.cpu().numpy())
     ocam["camera_center"] = cam.camera_center.cpu().numpy()
     ref = util.oracle_forward(inp, ocam, np.zeros(3, np.float32))
     np.testing.assert_array_equal(out["radii"].cpu().numpy(), ref["radii"])
