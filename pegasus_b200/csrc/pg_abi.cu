@@ -454,8 +454,8 @@ int pg_pack_masks(int32_t width, int32_t height, int32_t n_planes, const uint8_t
 
 size_t pg_png_scratch_bytes(int32_t height) {
     if (height <= 0) return 0;
-    // row bit counts (u32), Adler partial sums (2 x u64), per-thread bit counts (256 x u16) of every row
-    return ((size_t)height * 4 + 15) / 16 * 16 + (size_t)height * 16 + (size_t)height * 512;
+    // per row: bit count (u32), Adler partial sums (2 x u64), per-thread bit counts (256 x u16); H + 1 row offsets (u32)
+    return ((size_t)height * 4 + 15) / 16 * 16 + (size_t)height * 16 + (size_t)height * 512 + (((size_t)height + 1) * 4 + 15) / 16 * 16;
 }
 
 size_t pg_png_worst_case_bytes(int32_t kind, int32_t width, int32_t height) {

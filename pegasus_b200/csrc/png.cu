@@ -1,21 +1,26 @@
 // png.cu — the zlib streams of a frame's PNG files, produced on the device (the reference converts and
-// PNG-encodes every product on the host, /root/reference/pegasus.py:340-358 + imageio; ~170 ms of CPU per 1080p frame
-// against a 1.6 ms frame).  One launch pair encodes all images of a frame:
+// PNG-encodes every product on the host, /root/reference/pegasus.py:340-358 + imageio; ~150 ms of CPU per 1080p frame
+// against a 1.6 ms frame).  Three launches encode all images of a frame:
 //
-//   png_size_kernel   per (image, row): stage the row, PNG Sub filter, tokenize, count the row's bits, its Adler-32
-//                     partial sums (and, when calibrating, the token histogram); zero-fills the output buffers.
-//   png_write_kernel  per (image, row): the same tokens again, now placed: the row's bit offset is the sum of the
-//                     earlier rows' counts, tokens are packed into a shared-memory bit stream through a 64-bit
-//                     register accumulator and written out as whole words (first / last word of a row: atomic OR).
-//                     Row 0 adds the zlib + deflate block header, the last row the end-of-block code and Adler-32.
+//   png_size_kernel   per (image, row): stage the row, PNG Sub filter (one SIMD subtraction per 4 bytes), find the run
+//                     starts (one bit per byte in a 64-bit mask per thread), tokenize, count the row's bits and each
+//                     thread's share of them, the row's Adler-32 partial sums (and, when calibrating, the token
+//                     histogram); zero-fills the output buffers.
+//   png_scan_kernel   per image: exclusive scan of the rows' bit counts = every row's place in the stream; writes what
+//                     is not a row: zlib + deflate block header, end-of-block code, Adler-32, the stream's length.
+//   png_write_kernel  per (image, row): the same tokens again, now placed: tokens are packed into a shared-memory
+//                     bit stream through a 64-bit register accumulator and written out as whole words (first / last
+//                     word of a row: atomic OR, the neighbouring rows share them).
 //
 // Tokens (one dynamic-Huffman deflate block per image, code table STATIC per scene, built on the host from a
 // calibration histogram: pegasus_b200/png_codec.py): a run of equal bytes of the filtered row stream is its first
 // byte as a literal, then the repeats in chunks of 258 — a chunk of >= 3 bytes is ONE match (length, distance 1),
 // a shorter one literals.  Piecewise-constant images (masks, semantic colours) become zeros under the Sub filter
-// and collapse into matches; noisy ones (RGB, depth) are Huffman-coded residuals.  Every byte decides its token
-// from its position in its run alone, so the rows are tokenized by 256 threads in parallel, no sequential pass.
-// Byte / integer work, bound by shared-memory traffic; bit-exact against tests/png_model.py and stock zlib.
+// and collapse into matches; noisy ones (RGB, depth) are Huffman-coded residuals.  Every byte's token follows from
+// its position in its run alone, so a row is tokenized by 256 threads in parallel: a block-wide max-scan gives each
+// thread the last run start before its bytes, a min-scan the first one after them, and inside its own bytes it
+// visits run starts and chunk boundaries only (dense words — four run starts — take four literals at once).
+// Byte / integer work, instruction-bound; bit-exact against tests/png_model.py and stock zlib.
 #include "pg_common.cuh"
 
 namespace pg {
@@ -35,6 +40,7 @@ struct PngImage {
     uint32_t* row_bits;             // [H]
     unsigned long long* row_adler;  // [H][2]: sum of the row's stream bytes, sum of (L - i) * byte i
     uint16_t* thread_bits;          // [H][PNG_THREADS] bits of each thread's tokens (size kernel -> write kernel)
+    uint32_t* row_off;              // [H + 1] exclusive scan of row_bits (scan kernel -> write kernel)
     uint32_t* hist;
     uint32_t* result;
     uint32_t out_capacity;
@@ -128,16 +134,18 @@ __device__ __forceinline__ unsigned long long block_sum64(unsigned long long v, 
     return t;
 }
 
-// Row `row` of the image as PNG stream bytes in shared memory: f[0] = 1 (filter type Sub), f[1 + p] = raw[p] -
-// raw[p - bpp].  raw = big-endian samples; `raw_s` is staging of the unfiltered bytes.  Returns false (and leaves f
-// unwritten) for a row whose samples are all zero: most rows of a mask or a semantic map; their tokens have a closed
-// form (ZeroRow).
-__device__ __forceinline__ bool png_stage_row(const PngImage& im, int row, int width, uint8_t* raw_s, uint8_t* f) {
+// Shared-memory layout of a row.  The PNG stream of a row is L = 1 + bpp * W bytes: position 0 = the filter type
+// (1 = Sub), position 1 + p = raw[p] - raw[p - bpp] (raw = big-endian samples).  It is kept at byte OFFSET o =
+// position + 3 of the word array `fw`, so that the filtered samples start on a word boundary and the filter is one
+// SIMD subtraction per 4 bytes: fw[w + 1] = raw_w[w] - (raw bytes bpp earlier).  Offsets 0..2 are padding.
+// Returns false (fw unwritten) for a row whose samples are all zero: most rows of a mask or a semantic map; their
+// tokens have a closed form (ZeroRow).
+__device__ __forceinline__ bool png_stage_row(const PngImage& im, int row, int width, uint32_t* raw_w, uint32_t* fw) {
     const int kind = im.kind, bpp = png_bpp(kind), nraw = bpp * width;
     const uint8_t* src = reinterpret_cast<const uint8_t*>(im.src) + (size_t)row * im.src_pitch;
     const bool aligned = ((reinterpret_cast<uintptr_t>(src) | (uintptr_t)im.src_pitch) & 3) == 0;
-    const int nw = aligned ? nraw / 4 : 0;
-    uint32_t* raw_w = reinterpret_cast<uint32_t*>(raw_s);
+    const int nw = aligned ? nraw / 4 : 0, nwr = (nraw + 3) / 4;
+    uint8_t* raw_s = reinterpret_cast<uint8_t*>(raw_w);
     const uint32_t* src_w = reinterpret_cast<const uint32_t*>(src);
     uint32_t nz = 0;
     for (int w = threadIdx.x; w < nw; w += PNG_THREADS) {
@@ -147,22 +155,27 @@ __device__ __forceinline__ bool png_stage_row(const PngImage& im, int row, int w
         raw_w[w] = v;
         nz |= v;
     }
-    for (int p = 4 * nw + threadIdx.x; p < nraw; p += PNG_THREADS) {
-        uint8_t v;
-        if (kind == PG_PNG_GRAY16) {
-            const uint16_t s = reinterpret_cast<const uint16_t*>(src)[p >> 1];
-            v = (p & 1) ? (uint8_t)(s & 255u) : (uint8_t)(s >> 8);
-        } else {
-            v = src[p];
-            if (kind == PG_PNG_MASK8) v = v ? 255 : 0;
+    for (int p = 4 * nw + threadIdx.x; p < 4 * nwr; p += PNG_THREADS) {  // unaligned source / the last partial word
+        uint8_t v = 0;
+        if (p < nraw) {
+            if (kind == PG_PNG_GRAY16) {
+                const uint16_t s = reinterpret_cast<const uint16_t*>(src)[p >> 1];
+                v = (p & 1) ? (uint8_t)(s & 255u) : (uint8_t)(s >> 8);
+            } else {
+                v = src[p];
+                if (kind == PG_PNG_MASK8) v = v ? 255 : 0;
+            }
         }
         raw_s[p] = v;
         nz |= v;
     }
     if (!__syncthreads_or(nz != 0)) return false;
-    for (int p = threadIdx.x; p < nraw; p += PNG_THREADS)
-        f[1 + p] = (uint8_t)(raw_s[p] - (p >= bpp ? raw_s[p - bpp] : 0));
-    if (threadIdx.x == 0) f[0] = 1;
+    const int sh = 32 - 8 * bpp;
+    for (int w = threadIdx.x; w < nwr; w += PNG_THREADS) {
+        const uint32_t cur = raw_w[w], before = w ? raw_w[w - 1] : 0u;
+        fw[w + 1] = __vsub4(cur, __funnelshift_r(before, cur, sh));  // bytes 4w-bpp .. 4w-bpp+3
+    }
+    if (threadIdx.x == 0) fw[0] = 0x01000000u;  // offset 3 = position 0 = filter type Sub
     __syncthreads();
     return true;
 }
@@ -196,36 +209,77 @@ struct ZeroRow {
     }
 };
 
-// The tokens of stream positions [i0, i1) of a row of L bytes; s = last run start before i0 (-1: none), nxt = first
-// run start at or after i1 (L: none) — with it the length of a chunk is found inside the thread's own positions.
+// ---- tokens of one thread's part of a row --------------------------------------------------------------------
+// A thread owns the words [w0, w1) of `fw`, i.e. offsets [4 w0, 4 w1).  `mask` has bit j set when offset 4 w0 + j
+// starts a run (its byte differs from the one before it; position 0 always does).  With the last start before the
+// part (`s`, from a block-wide max-scan) and the first one after it (`nxt`, min-scan) every token follows from the
+// mask alone — no byte is compared twice and no position inside a long run is visited.
+struct PngPart {
+    int o0, o1;               // offsets [o0, o1) that are stream positions of this thread
+    unsigned long long mask;  // run starts, bit j <-> offset 4 w0 + j
+    int base;                 // 4 w0
+};
+
+__device__ __forceinline__ PngPart png_part(const uint32_t* fw, int Lo) {
+    const int nwo = (Lo + 3) / 4;
+    const int sw = (nwo + PNG_THREADS - 1) / PNG_THREADS;   // words per thread (<= 16, checked by the launcher)
+    const int w0 = min(nwo, (int)threadIdx.x * sw), w1 = min(nwo, w0 + sw);
+    PngPart p;
+    p.base = 4 * w0;
+    p.o0 = max(p.base, 3);
+    p.o1 = min(4 * w1, Lo);
+    unsigned long long m = 0;
+    uint32_t prevw = w0 > 0 ? fw[w0 - 1] : 0u;
+    for (int w = w0; w < w1; ++w) {
+        const uint32_t cur = fw[w];
+        const uint32_t ne = __vcmpne4(cur, (cur << 8) | (prevw >> 24));      // 0xFF where byte != the byte before it
+        const uint32_t nib = (((ne & 0x01010101u) * 0x01020408u) >> 24) & 15u;  // one bit per byte
+        m |= (unsigned long long)nib << (4 * (w - w0));
+        prevw = cur;
+    }
+    if (w0 == 0 && w1 > 0) m = (m & ~7ull) | 8ull;            // offsets 0..2 are padding, offset 3 always starts a run
+    const int n = p.o1 - p.base;                              // drop the offsets beyond the row
+    if (n < 64) m &= n > 0 ? ((1ull << n) - 1ull) : 0ull;
+    p.mask = m;
+    return p;
+}
+
+// repeats of a run: offsets [a, b) all continue the run that started at offset s and ends before offset e
 template <class Lit, class Len>
-__device__ __forceinline__ void png_walk(const uint8_t* f, int L, int i0, int i1, int s, int nxt, Lit&& lit, Len&& len) {
-    if (i0 >= i1) return;
-    const uint32_t* fw = reinterpret_cast<const uint32_t*>(f);  // i0 is a multiple of 4: four positions per load
-    uint32_t prev = i0 > 0 ? f[i0 - 1] : 0x100u;                // 0x100: no byte equals it, position 0 starts a run
-    for (int wb = i0; wb < i1; wb += 4) {
-        const uint32_t word = fw[wb >> 2];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int i = wb + j;
-            if (i >= i1) break;
-            const uint32_t b = (word >> (8 * j)) & 255u;
-            if (b != prev) s = i;
-            prev = b;
-            const int k = i - s;
-            if (k == 0) { lit(i, b); continue; }
-            const int off = (k - 1) % 258;        // position inside its chunk of the run's repeats
-            if (off >= 3) continue;               // inside a match of >= 4 bytes
-            const int cs = i - off;               // chunk start
-            const bool ge3 = cs + 2 < L && f[cs + 1] == b && f[cs + 2] == b;
-            if (!ge3) { lit(i, b); continue; }    // chunk of 1 or 2 bytes: literals
-            if (off == 0) {
-                int e = i + 1;                    // first position after the run: inside this thread's positions, else nxt
-                while (e < i1 && f[e] == b) ++e;
-                if (e == i1) e = nxt;
-                len(i, min(258, e - cs));
-            }
+__device__ __forceinline__ void png_repeats(uint32_t v, int s, int a, int b, int e, Lit&& lit, Len&& len) {
+    int cs = s + 1 + ((a - s - 1) / 258) * 258;     // start of the 258-chunk that holds offset a
+    for (; cs < b; cs += 258) {
+        const int cl = min(258, e - cs);
+        if (cl >= 3) {
+            if (cs >= a) len(cl);                   // one match, emitted by the chunk's first offset
+        } else {
+            for (int o = max(cs, a); o < min(cs + cl, b); ++o) lit(v);
         }
+    }
+}
+
+template <class Lit, class Len>
+__device__ __forceinline__ void png_walk(const uint32_t* fw, const PngPart& p, int s, int nxt, Lit&& lit, Len&& len) {
+    const uint8_t* f8 = reinterpret_cast<const uint8_t*>(fw);
+    int pos = p.o0;
+    while (pos < p.o1) {
+        const unsigned long long m = p.mask >> (pos - p.base);
+        // dense data (photographic rows: every byte differs from its neighbour): four literals straight from the word
+        if ((pos & 3) == 0 && pos + 4 <= p.o1 && ((uint32_t)m & 15u) == 15u) {
+            uint32_t word = fw[pos >> 2];
+#pragma unroll 1
+            for (int j = 0; j < 4; ++j, word >>= 8) lit(word & 255u);
+            s = pos + 3;
+            pos += 4;
+            continue;
+        }
+        const int next = m ? pos + __ffsll((long long)m) - 1 : p.o1;   // next run start at or after pos
+        if (next > pos) png_repeats(f8[s], s, pos, next, next < p.o1 ? next : nxt, lit, len);
+        if (next < p.o1) {
+            s = next;
+            lit(f8[next]);
+        }
+        pos = next + 1;
     }
 }
 
@@ -235,44 +289,36 @@ struct PngRowSmem {
     unsigned long long tmp64[PNG_WARPS];
 };
 
-// dynamic shared memory: PngRowSmem | raw[Lpad] | f[Lpad] | (write kernel) stream words
-__device__ __forceinline__ int png_lpad(int L) { return (L + 15) / 16 * 16; }
+// dynamic shared memory: PngRowSmem | raw words | fw words | (write kernel) stream words
+__device__ __forceinline__ int png_row_words(int L) { return ((L + 3 + 3) / 4 + 4 + 3) & ~3; }
 
-// last (-1: none) and first (L: none) run start among positions [i0, i1)
-__device__ __forceinline__ void png_starts(const uint8_t* f, int L, int i0, int i1, int* last, int* first) {
-    int ls = -1, fs = L;
-    if (i0 < i1) {
-        const uint32_t* fw = reinterpret_cast<const uint32_t*>(f);
-        uint32_t prev = i0 > 0 ? f[i0 - 1] : 0x100u;
-        for (int wb = i0; wb < i1; wb += 4) {
-            const uint32_t word = fw[wb >> 2];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int i = wb + j;
-                const uint32_t b = (word >> (8 * j)) & 255u;
-                if (i < i1 && b != prev) {
-                    ls = i;
-                    fs = min(fs, i);
-                }
-                prev = b;
-            }
-        }
+// sum of the stream bytes of the thread's part and of (L - position) * byte (Adler-32 partial sums)
+__device__ __forceinline__ void png_adler_part(const uint32_t* fw, const PngPart& p, int L, uint32_t* sumA,
+                                               unsigned long long* sumB) {
+    uint32_t a = 0;
+    unsigned long long b = 0;
+    for (int o = p.base; o < p.o1; o += 4) {
+        uint32_t word = fw[o >> 2];
+        if (o < 3) word &= 0xFF000000u;                                  // padding offsets
+        if (o + 4 > p.o1) word &= 0xFFFFFFFFu >> (8 * (o + 4 - p.o1));   // offsets beyond the part
+        const uint32_t sa = __dp4a(word, 0x01010101u, 0u);
+        a += sa;
+        // weight of offset o + j: L - (o + j - 3)
+        b += (unsigned long long)(L + 3 - o) * sa - __dp4a(word, 0x03020100u, 0u);
     }
-    *last = ls;
-    *first = fs;
+    *sumA = a;
+    *sumB = b;
 }
 
-// positions per thread: the row split evenly over the CTA, rounded up to whole words
-__device__ __forceinline__ int png_seg(int L) { return ((L + PNG_THREADS - 1) / PNG_THREADS + 3) & ~3; }
-
+template <bool HIST>
 __global__ void __launch_bounds__(PNG_THREADS) png_size_kernel(const PngBatch B) {
     extern __shared__ __align__(16) unsigned char png_smem[];
     const PngImage& im = B.img[blockIdx.y];
     const int row = blockIdx.x, H = B.height;
-    const int L = png_bpp(im.kind) * B.width + 1, Lp = png_lpad(L);
+    const int L = png_bpp(im.kind) * B.width + 1, Lo = L + 3, RW = png_row_words(L);
     PngRowSmem& sm = *reinterpret_cast<PngRowSmem*>(png_smem);
-    uint8_t* raw_s = png_smem + sizeof(PngRowSmem);
-    uint8_t* f = raw_s + Lp;
+    uint32_t* raw_w = reinterpret_cast<uint32_t*>(png_smem + sizeof(PngRowSmem));
+    uint32_t* fw = raw_w + RW;
     // zero-fill this row's share of the output buffer (the write kernel ORs into it)
     {
         const uint32_t n16 = im.out_capacity / 16, per = (n16 + H - 1) / H;
@@ -280,8 +326,8 @@ __global__ void __launch_bounds__(PNG_THREADS) png_size_kernel(const PngBatch B)
         const uint32_t a = row * per, b = min(n16, a + per);
         for (uint32_t i = a + threadIdx.x; i < b; i += PNG_THREADS) o[i] = make_uint4(0, 0, 0, 0);
     }
-    uint32_t* hist = im.hist;
-    if (!png_stage_row(im, row, B.width, raw_s, f)) {
+    uint32_t* hist = HIST ? im.hist : nullptr;  // calibration launches only
+    if (!png_stage_row(im, row, B.width, raw_w, fw)) {
         if (threadIdx.x == 0) {
             const ZeroRow z(im.table, L);
             if (row == 0) im.result[0] = im.result[1] = 0u;
@@ -299,28 +345,24 @@ __global__ void __launch_bounds__(PNG_THREADS) png_size_kernel(const PngBatch B)
         return;
     }
     for (int i = threadIdx.x; i < PNG_TOKENS; i += PNG_THREADS) sm.tok[i] = __ldg(im.table + i);
-    __syncthreads();
-    const int S = png_seg(L);
-    const int i0 = min(L, (int)threadIdx.x * S), i1 = min(L, i0 + S);
-    int my_last, my_first;
-    png_starts(f, L, i0, i1, &my_last, &my_first);
-    const int s0 = block_excl_max(my_last, reinterpret_cast<int*>(sm.tmp));
-    const int nx = block_excl_min_after(my_first, L, reinterpret_cast<int*>(sm.tmp));
-    uint32_t bits = 0, sumA = 0;
-    unsigned long long sumB = 0;
-    png_walk(f, L, i0, i1, s0, nx,
-             [&](int, uint8_t b) {
+    const PngPart part = png_part(fw, Lo);
+    const int my_last = part.mask ? part.base + 63 - __clzll((long long)part.mask) : -1;
+    const int my_first = part.mask ? part.base + __ffsll((long long)part.mask) - 1 : Lo;
+    const int s0 = block_excl_max(my_last, reinterpret_cast<int*>(sm.tmp));   // also orders sm.tok
+    const int nx = block_excl_min_after(my_first, Lo, reinterpret_cast<int*>(sm.tmp));
+    uint32_t bits = 0;
+    png_walk(fw, part, s0, nx,
+             [&](uint32_t b) {
                  bits += sm.tok[T_LIT + b] >> 24;
-                 if (hist) atomicAdd(&hist[b], 1u);
+                 if (HIST && hist) atomicAdd(&hist[b], 1u);
              },
-             [&](int, int cl) {
+             [&](int cl) {
                  bits += sm.tok[T_LEN + cl - 3] >> 24;
-                 if (hist) atomicAdd(&hist[png_len_symbol(cl)], 1u);
+                 if (HIST && hist) atomicAdd(&hist[png_len_symbol(cl)], 1u);
              });
-    for (int i = i0; i < i1; ++i) {
-        sumA += f[i];
-        sumB += (unsigned long long)(L - i) * f[i];
-    }
+    uint32_t sumA;
+    unsigned long long sumB;
+    png_adler_part(fw, part, L, &sumA, &sumB);
     uint32_t total;
     block_excl_sum(bits, sm.tmp, &total);
     im.thread_bits[(size_t)row * PNG_THREADS + threadIdx.x] = (uint16_t)bits;
@@ -346,27 +388,72 @@ __device__ __forceinline__ bool png_or_bits(uint8_t* out, uint32_t cap, unsigned
     return true;
 }
 
+// One CTA per image between the two row kernels: exclusive scan of the rows' bit counts (every row's place in the
+// stream), and everything of the stream that is not a row: zlib header, deflate block header, end-of-block code,
+// padding, Adler-32 combined from the rows' partial sums, the stream's length.
+__global__ void __launch_bounds__(PNG_THREADS) png_scan_kernel(const PngBatch B) {
+    __shared__ uint32_t tmp[PNG_WARPS + 1];
+    __shared__ unsigned long long tmp64[PNG_WARPS];
+    const PngImage& im = B.img[blockIdx.x];
+    const int H = B.height, L = png_bpp(im.kind) * B.width + 1;
+    const uint32_t cap = im.out_capacity;
+    // rows [r0, r1) of this thread, in order
+    const int per = (H + PNG_THREADS - 1) / PNG_THREADS;
+    const int r0 = min(H, (int)threadIdx.x * per), r1 = min(H, r0 + per);
+    uint32_t mine = 0;
+    unsigned long long a = 0, b = 0;
+    for (int r = r0; r < r1; ++r) {
+        mine += im.row_bits[r];
+        const unsigned long long ar = im.row_adler[2 * r];
+        a += ar;
+        b += (im.row_adler[2 * r + 1] + (unsigned long long)(H - 1 - r) * (unsigned long long)L % 65521ull * (ar % 65521ull)) % 65521ull;
+    }
+    uint32_t total;
+    uint32_t run = block_excl_sum(mine, tmp, &total);
+    for (int r = r0; r < r1; ++r) {
+        im.row_off[r] = run;
+        run += im.row_bits[r];
+    }
+    a = block_sum64(a, tmp64);
+    b = block_sum64(b, tmp64);
+    const uint32_t hdr_bits = __ldg(im.table + T_HDR_BITS);
+    bool ok = true;
+    for (int k = threadIdx.x; 32 * k < (int)hdr_bits; k += PNG_THREADS)
+        ok &= png_or_bits(im.out, cap, 16ull + 32ull * k, __ldg(im.table + T_HDR + k), min(32, (int)hdr_bits - 32 * k));
+    if (threadIdx.x == 0) {
+        im.row_off[H] = total;
+        ok &= png_or_bits(im.out, cap, 0, 0x0178u, 16);  // zlib header: CM 8, 32 K window, level 0
+        const unsigned long long end = 16ull + hdr_bits + total;
+        const uint32_t eob = __ldg(im.table + T_EOB);
+        ok &= png_or_bits(im.out, cap, end, eob & 0xFFFFFFu, (int)(eob >> 24));
+        const unsigned long long nbytes = (end + (eob >> 24) + 7) / 8;
+        const unsigned long long N = (unsigned long long)H * L;
+        const uint32_t A = (uint32_t)((1ull + a) % 65521ull), Bv = (uint32_t)((N + b) % 65521ull);
+        const uint32_t adler = (Bv << 16) | A;
+        for (int q = 0; q < 4; ++q) ok &= png_or_bits(im.out, cap, 8ull * (nbytes + q), (adler >> (24 - 8 * q)) & 255u, 8);
+        im.result[0] = (uint32_t)min(nbytes + 4ull, 0xFFFFFFFFull);
+    }
+    if (!ok) im.result[1] = 1u;
+}
+
 __global__ void __launch_bounds__(PNG_THREADS) png_write_kernel(const PngBatch B) {
     extern __shared__ __align__(16) unsigned char png_smem[];
     const PngImage& im = B.img[blockIdx.y];
-    const int row = blockIdx.x, H = B.height;
-    const int L = png_bpp(im.kind) * B.width + 1, Lp = png_lpad(L);
+    const int row = blockIdx.x;
+    const int L = png_bpp(im.kind) * B.width + 1, Lo = L + 3, RW = png_row_words(L);
     PngRowSmem& sm = *reinterpret_cast<PngRowSmem*>(png_smem);
-    uint8_t* raw_s = png_smem + sizeof(PngRowSmem);
-    uint8_t* f = raw_s + Lp;
-    uint32_t* out_s = reinterpret_cast<uint32_t*>(f + Lp);
+    uint32_t* raw_w = reinterpret_cast<uint32_t*>(png_smem + sizeof(PngRowSmem));
+    uint32_t* fw = raw_w + RW;
+    uint32_t* out_s = fw + RW;
     const uint32_t cap = im.out_capacity;
-    // where this row starts: 16 bits of zlib header + the block header + the rows before it
-    unsigned long long before = 0;
-    for (int r = threadIdx.x; r < row; r += PNG_THREADS) before += im.row_bits[r];
-    const uint32_t hdr_bits = __ldg(im.table + T_HDR_BITS);
-    const unsigned long long base = 16ull + hdr_bits + block_sum64(before, sm.tmp64);
+    // where this row starts: 16 bits of zlib header + the block header + the rows before it (png_scan_kernel)
+    const unsigned long long base = 16ull + __ldg(im.table + T_HDR_BITS) + im.row_off[row];
     const uint32_t my_bits = im.row_bits[row];
     const int shift = (int)(base & 31);
     const int nw = (int)((shift + (unsigned long long)my_bits + 31) / 32);
     for (int w = threadIdx.x; w < nw + 1; w += PNG_THREADS) out_s[w] = 0;
     bool ok = true;
-    if (!png_stage_row(im, row, B.width, raw_s, f)) {
+    if (!png_stage_row(im, row, B.width, raw_w, fw)) {
         // all-zero row: a handful of tokens with closed-form offsets, OR-ed straight into the output
         const ZeroRow z(im.table, L);
         for (int t = threadIdx.x; t < z.n; t += PNG_THREADS) {
@@ -376,13 +463,11 @@ __global__ void __launch_bounds__(PNG_THREADS) png_write_kernel(const PngBatch B
         }
     } else {
         for (int i = threadIdx.x; i < PNG_TOKENS; i += PNG_THREADS) sm.tok[i] = __ldg(im.table + i);
-        __syncthreads();  // tokens staged; out_s is clear as well
-        const int S = png_seg(L);
-        const int i0 = min(L, (int)threadIdx.x * S), i1 = min(L, i0 + S);
-        int my_last, my_first;
-        png_starts(f, L, i0, i1, &my_last, &my_first);
-        const int s0 = block_excl_max(my_last, reinterpret_cast<int*>(sm.tmp));
-        const int nx = block_excl_min_after(my_first, L, reinterpret_cast<int*>(sm.tmp));
+        const PngPart part = png_part(fw, Lo);
+        const int my_last = part.mask ? part.base + 63 - __clzll((long long)part.mask) : -1;
+        const int my_first = part.mask ? part.base + __ffsll((long long)part.mask) - 1 : Lo;
+        const int s0 = block_excl_max(my_last, reinterpret_cast<int*>(sm.tmp));  // its barriers also order sm.tok / out_s
+        const int nx = block_excl_min_after(my_first, Lo, reinterpret_cast<int*>(sm.tmp));
         const uint32_t bits = im.thread_bits[(size_t)row * PNG_THREADS + threadIdx.x];  // counted by the size kernel
         uint32_t total;
         const uint32_t excl = block_excl_sum(bits, sm.tmp, &total);
@@ -405,8 +490,8 @@ __global__ void __launch_bounds__(PNG_THREADS) png_write_kernel(const PngBatch B
                     ++w;
                 }
             };
-            png_walk(f, L, i0, i1, s0, nx, [&](int, uint8_t b) { put(sm.tok[T_LIT + b]); },
-                     [&](int, int cl) { put(sm.tok[T_LEN + cl - 3]); });
+            png_walk(fw, part, s0, nx, [&](uint32_t b) { put(sm.tok[T_LIT + b]); },
+                     [&](int cl) { put(sm.tok[T_LEN + cl - 3]); });
             if (fill > 0 && acc) atomicOr(&out_s[w], (uint32_t)acc);
         }
         __syncthreads();
@@ -420,40 +505,12 @@ __global__ void __launch_bounds__(PNG_THREADS) png_write_kernel(const PngBatch B
             else g[w] = v;
         }
     }
-    if (row == 0) {
-        if (threadIdx.x == 0) ok &= png_or_bits(im.out, cap, 0, 0x0178u, 16);  // zlib header: CM 8, 32 K window, level 0
-        for (int k = threadIdx.x; 32 * k < (int)hdr_bits; k += PNG_THREADS)
-            ok &= png_or_bits(im.out, cap, 16ull + 32ull * k, __ldg(im.table + T_HDR + k), min(32, (int)hdr_bits - 32 * k));
-    }
-    if (row == H - 1) {
-        // end of block, padding to a byte, Adler-32 of the uncompressed stream (all rows' partial sums)
-        unsigned long long a = 0, b = 0;
-        for (int r = threadIdx.x; r < H; r += PNG_THREADS) {
-            const unsigned long long ar = im.row_adler[2 * r];
-            a += ar;
-            b += (im.row_adler[2 * r + 1] + (unsigned long long)(H - 1 - r) * (unsigned long long)L % 65521ull * (ar % 65521ull)) % 65521ull;
-        }
-        a = block_sum64(a, sm.tmp64);
-        b = block_sum64(b, sm.tmp64);
-        if (threadIdx.x == 0) {
-            const unsigned long long end = base + my_bits;
-            const uint32_t eob = __ldg(im.table + T_EOB);
-            ok &= png_or_bits(im.out, cap, end, eob & 0xFFFFFFu, (int)(eob >> 24));
-            const unsigned long long nbytes = (end + (eob >> 24) + 7) / 8;
-            const unsigned long long N = (unsigned long long)H * L;
-            const uint32_t A = (uint32_t)((1ull + a) % 65521ull), Bv = (uint32_t)((N + b) % 65521ull);
-            const uint32_t adler = (Bv << 16) | A;
-            for (int q = 0; q < 4; ++q)
-                ok &= png_or_bits(im.out, cap, 8ull * (nbytes + q), (adler >> (24 - 8 * q)) & 255u, 8);
-            im.result[0] = (uint32_t)min(nbytes + 4ull, 0xFFFFFFFFull);
-        }
-    }
     if (!ok) im.result[1] = 1u;
 }
 
 size_t png_dynamic_smem(int width, bool write) {
-    const size_t L = 3 * (size_t)width + 1, Lp = (L + 15) / 16 * 16;
-    size_t b = sizeof(PngRowSmem) + 2 * Lp;
+    const size_t L = 3 * (size_t)width + 1, rw = ((L + 3 + 3) / 4 + 4 + 3) & ~(size_t)3;   // = png_row_words(L)
+    size_t b = sizeof(PngRowSmem) + 2 * rw * 4;
     if (write) b += ((15 * L + 31) / 32 + 4) * 4;
     return (b + 15) / 16 * 16;
 }
@@ -461,11 +518,15 @@ size_t png_dynamic_smem(int width, bool write) {
 int launch_png_encode(int n_images, const pg_png_image* images, int width, int height, cudaStream_t stream) {
     if (n_images == 0 || width == 0 || height == 0) return PG_OK;
     const size_t smem_size = png_dynamic_smem(width, false), smem_write = png_dynamic_smem(width, true);
-    if (smem_write > 200 * 1024) {
-        set_error("pg_png_encode: image width %d needs %zu bytes of shared memory per row", width, smem_write);
+    // a thread's part of a row is at most 16 words (its run starts live in one 64-bit mask)
+    if (smem_write > 200 * 1024 || (3 * (size_t)width + 1 + 3 + 3) / 4 > 16 * (size_t)PNG_THREADS) {
+        set_error("pg_png_encode: image width %d is not supported (rows of at most %d stream bytes)", width,
+                  64 * PNG_THREADS - 8);
         return PG_ERR_INVALID;
     }
-    int rc = ensure_dynamic_smem(png_size_kernel, smem_size);
+    int rc = ensure_dynamic_smem(png_size_kernel<false>, smem_size);
+    if (rc != PG_OK) return rc;
+    rc = ensure_dynamic_smem(png_size_kernel<true>, smem_size);
     if (rc != PG_OK) return rc;
     rc = ensure_dynamic_smem(png_write_kernel, smem_write);
     if (rc != PG_OK) return rc;
@@ -484,6 +545,7 @@ int launch_png_encode(int n_images, const pg_png_image* images, int width, int h
             unsigned char* sc = reinterpret_cast<unsigned char*>(s.scratch);
             d.row_adler = reinterpret_cast<unsigned long long*>(sc + (((size_t)height * 4 + 15) / 16 * 16));
             d.thread_bits = reinterpret_cast<uint16_t*>(sc + (((size_t)height * 4 + 15) / 16 * 16) + (size_t)height * 16);
+            d.row_off = reinterpret_cast<uint32_t*>(sc + (((size_t)height * 4 + 15) / 16 * 16) + (size_t)height * (16 + 512));
             d.hist = s.hist;
             d.result = s.result;
             d.out_capacity = s.out_capacity;
@@ -491,11 +553,17 @@ int launch_png_encode(int n_images, const pg_png_image* images, int width, int h
             d.src_pitch = s.src_pitch;
         }
         const dim3 grid((unsigned)height, (unsigned)B.n);
-        png_size_kernel<<<grid, PNG_THREADS, smem_size, stream>>>(B);
+        bool any_hist = false;
+        for (int i = 0; i < B.n; ++i) any_hist |= B.img[i].hist != nullptr;
+        if (any_hist) png_size_kernel<true><<<grid, PNG_THREADS, smem_size, stream>>>(B);
+        else png_size_kernel<false><<<grid, PNG_THREADS, smem_size, stream>>>(B);
+        PG_CUDA_CHECK(cudaGetLastError());
+        PG_CUDA_CHECK(cudaGetLastError());
+        png_scan_kernel<<<(unsigned)B.n, PNG_THREADS, 0, stream>>>(B);
         PG_CUDA_CHECK(cudaGetLastError());
         png_write_kernel<<<grid, PNG_THREADS, smem_write, stream>>>(B);
         PG_CUDA_CHECK(cudaGetLastError());
-        count_launch(2);
+        count_launch(3);
     }
     return PG_OK;
 }

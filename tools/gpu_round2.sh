@@ -29,9 +29,10 @@ python tools/ncu_summary.py $OUT/prof.ncu-rep $OUT/ncu_full_summary.json > $OUT/
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:'pose_kernel|pack_kernel|pack_masks' -s 6 -c 3 -o $OUT/prof_pose \
   python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-gpu-baseline --no-extras > $OUT/prof_pose_run.log 2>&1
 python tools/ncu_summary.py $OUT/prof_pose.ncu-rep $OUT/ncu_pose_summary.json > $OUT/ncu_pose_summary.txt 2>&1
-# pg_png_encode on one frame of the same workload: timing, then ncu --set full of one steady-state launch pair
+# pg_png_encode on one frame of the same workload: timing, then ncu --set full of one steady-state launch triple
+# (3 kernels per call; the calibration of png_time.py makes 8 calls, 3 warm-up calls follow)
 timeout 600 python tools/png_time.py > $OUT/png_time.json 2> $OUT/png_time.err
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:png_ -s 10 -c 2 -o $OUT/prof_png \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:png_ -s 33 -c 3 -o $OUT/prof_png \
   python tools/png_time.py --n 4 > $OUT/prof_png_run.log 2>&1
 python tools/ncu_summary.py $OUT/prof_png.ncu-rep $OUT/ncu_png_summary.json > $OUT/ncu_png_summary.txt 2>&1
 ls -la $OUT
