@@ -14,4 +14,7 @@ done
 timeout 1500 $SAN --tool memcheck --print-limit 20 python -m pytest tests/test_gpu_render_call.py tests/test_gpu_generate.py tests/test_gpu_png.py -m gpu -x -q \
   > $OUT/sanitize_memcheck_tests.log 2>&1
 echo "memcheck tests/test_gpu_render_call.py tests/test_gpu_generate.py tests/test_gpu_png.py: exit $? | $(grep -E 'ERROR SUMMARY' $OUT/sanitize_memcheck_tests.log | tail -1) | $(grep -E 'passed|failed' $OUT/sanitize_memcheck_tests.log | tail -1)" >> $OUT/sanitize_summary.txt
+timeout 900 $SAN --tool racecheck --print-limit 10 python -m pytest tests/test_gpu_png.py -m gpu -x -q -k "bit_for_bit or batch or strided" \
+  > $OUT/sanitize_racecheck_png.log 2>&1
+echo "racecheck tests/test_gpu_png.py (small images): exit $? | $(grep -E 'RACECHECK SUMMARY' $OUT/sanitize_racecheck_png.log | tail -1) | $(grep -E 'passed|failed' $OUT/sanitize_racecheck_png.log | tail -1)" >> $OUT/sanitize_summary.txt
 cat $OUT/sanitize_summary.txt
