@@ -471,14 +471,26 @@ static int launch_three(const CompArgs& a, dim3 grid, cudaStream_t stream) {
 }
 
 // masks: fused K+3 passes; fast: PG_NUMERICS_FAST
+// CTAs per SM the register allocation is bounded for.  With masks the kernel wants 87 registers; bounded for 5 CTAs
+// per SM (72 registers, 4 of them spilled) it runs 0.899 instead of 0.948 ms (fast; exact 1.008 vs 1.057): 20 instead
+// of 16 consumer warps per SM hide more of the dependent chains.  6 CTAs (64 registers, 12 spilled; shared memory
+// allows 5) 0.987, 7 CTAs 1.173; __maxnreg__(80), spill-free, 0.923.  The plain kernel needs 51-64 registers: unaffected.
+#ifndef PG_COMP3_MINB
+#define PG_COMP3_MINB 5
+#endif
+#ifndef PG_COMP3_MINB_PLAIN
+#define PG_COMP3_MINB_PLAIN 4
+#endif
+
 int launch_composite3(const CompArgs& a, dim3 grid, bool masks, bool fast, int variant, cudaStream_t stream) {
     (void)variant;
+    constexpr int MB = PG_COMP3_MINB, MBP = PG_COMP3_MINB_PLAIN;
     if (!masks) {
         const bool nc = a.out_n_contrib != nullptr;
-        if (fast) return nc ? launch_three<false, true, true, 4, 4>(a, grid, stream) : launch_three<false, false, true, 4, 4>(a, grid, stream);
-        return nc ? launch_three<false, true, false, 4, 4>(a, grid, stream) : launch_three<false, false, false, 4, 4>(a, grid, stream);
+        if (fast) return nc ? launch_three<false, true, true, 4, MBP>(a, grid, stream) : launch_three<false, false, true, 4, MBP>(a, grid, stream);
+        return nc ? launch_three<false, true, false, 4, MBP>(a, grid, stream) : launch_three<false, false, false, 4, MBP>(a, grid, stream);
     }
-    return fast ? launch_three<true, false, true, 4, 4>(a, grid, stream) : launch_three<true, false, false, 4, 4>(a, grid, stream);
+    return fast ? launch_three<true, false, true, 4, MB>(a, grid, stream) : launch_three<true, false, false, 4, MB>(a, grid, stream);
 }
 
 }  // namespace pg
