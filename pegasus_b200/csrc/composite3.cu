@@ -490,6 +490,12 @@ int launch_composite3(const CompArgs& a, dim3 grid, bool masks, bool fast, int v
         if (fast) return nc ? launch_three<false, true, true, 4, MBP>(a, grid, stream) : launch_three<false, false, true, 4, MBP>(a, grid, stream);
         return nc ? launch_three<false, true, false, 4, MBP>(a, grid, stream) : launch_three<false, false, false, 4, MBP>(a, grid, stream);
     }
+    // the tighter register bound only pays when shared memory lets the extra CTA in (227 KB per SM, 1 KB per CTA
+    // reserved by the runtime: up to 9 objects); frames with more objects keep the spill-free 4-CTA build
+    const int smem = (int)((sizeof(CompSmemT<4>) + 15) / 16 * 16) + COMP2_CW * QSTRIDE +
+                     (int)((COMP2_CW + 1) * PG_MAX_OBJECTS * sizeof(float4)) + a.num_objects * 256 * (int)sizeof(float);
+    if (MB > 4 && MB * (smem + 1024) > 227 * 1024)
+        return fast ? launch_three<true, false, true, 4, 4>(a, grid, stream) : launch_three<true, false, false, 4, 4>(a, grid, stream);
     return fast ? launch_three<true, false, true, 4, MB>(a, grid, stream) : launch_three<true, false, false, 4, MB>(a, grid, stream);
 }
 

@@ -77,7 +77,7 @@ class DatasetGenerator:
 
     def __init__(self, scene: ComposedScene, width: int, height: int, bg: Optional[torch.Tensor] = None,
                  frames_in_flight: int = 3, host_sets: Optional[int] = None, writer_threads: int = 4,
-                 overlap_compositing: bool = True, numerics=None, png_on_gpu: bool = False):
+                 overlap_compositing: bool = False, numerics=None, png_on_gpu: bool = False):
         self.scene = scene
         self.dev = scene.device
         self.W, self.H = int(width), int(height)
@@ -88,9 +88,10 @@ class DatasetGenerator:
         self.writer_threads = max(1, int(writer_threads))
         self.numerics = numerics  # None: process default (pegasus_b200.set_numerics / PG_NUMERICS)
         dev, W, H, nc = self.dev, self.W, self.H, self.nc
-        # Each slot owns a HIGH-priority stream (pose, per-Gaussian stage, sorts, packing, copies) and a
-        # normal-priority one for the compositing kernel (pg_launch_opts.composite_stream): the latency-bound
-        # stages of frame i+1 take the SM slots frame i's compositing CTAs free and co-run with them.
+        # overlap_compositing=True: each slot owns a HIGH-priority stream (pose, per-Gaussian stage, sorts, packing,
+        # copies) and a normal-priority one for the compositing kernel (pg_launch_opts.composite_stream): the
+        # latency-bound stages of frame i+1 take the SM slots frame i's compositing CTAs free.  Off by default: with
+        # compositing at 5 CTAs per SM one stream per slot measures the same end to end and 3 % better device-resident.
         self.overlap = bool(overlap_compositing) and self.nslot > 1
         self.streams = [torch.cuda.Stream(device=dev, priority=-1 if self.overlap else 0) for _ in range(self.nslot)]
         self.comp_streams = [torch.cuda.Stream(device=dev, priority=0) if self.overlap else None

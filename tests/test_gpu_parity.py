@@ -347,11 +347,14 @@ def _compare_frame(out, ref, colors, K_ids):
     return stats
 
 
-def test_composed_frame_matches_reference_k_plus_3_passes():
+@pytest.mark.parametrize("sizes,views", [((6000, 5000, 4000), 2), ((900,) * 18, 1)], ids=["3 objects", "18 objects"])
+def test_composed_frame_matches_reference_k_plus_3_passes(sizes, views):
+    """18 objects: past the object count up to which the compositing kernel runs its 5-CTAs-per-SM build."""
     from pegasus_b200 import ComposedScene, Camera, synth
-    env, objs = util.small_scene(n_env=30000, n_obj=(6000, 5000, 4000), seed=51)
-    colors = oracle.generate_colors(3)
-    poses = _pose_list(3, 9)
+    K = len(sizes)
+    env, objs = util.small_scene(n_env=30000, n_obj=sizes, seed=51)
+    colors = oracle.generate_colors(K)
+    poses = _pose_list(K, 9)
     bg = np.zeros(3, np.float32)
     sc = ComposedScene(env, objs, colors, sh_mode="rotate")
     sc.set_poses(poses)
@@ -369,7 +372,7 @@ def test_composed_frame_matches_reference_k_plus_3_passes():
         n = objs[oid]["xyz"].shape[0]
         posed[oid] = rows(lo, lo + n)
         lo += n
-    for c in synth.orbit_cameras(2, 640, 480, seed=3100):
+    for c in synth.orbit_cameras(views, 640, 480, seed=3100):
         cam = Camera(c["R"], c["T"], c["FoVx"], c["FoVy"], c["W"], c["H"])
         ocam = util.oracle_cam(c)
         # the product's Camera and the oracle's agree bit for bit on both matrices; the camera centre comes from a
@@ -386,7 +389,7 @@ def test_composed_frame_matches_reference_k_plus_3_passes():
         np.testing.assert_array_equal(out["seg_color"].permute(1, 2, 0).cpu().numpy(), ref["seg_float"])
         assert ref["visible"].sum() > 500 and ref["silhouette"].sum() > 500
         # silhouettes come from 1 - T_k instead of a 3-channel accumulation: only threshold-band pixels may differ
-        assert sum(stats.values()) <= 20, stats
+        assert sum(stats.values()) <= 7 * K, stats
         # the product's default numerics on the same frame: images inside the tolerances, masks equal to the exact
         # mode's except for a handful of threshold pixels
         fast = sc.render(cam, torch.zeros(3, device="cuda"), numerics="fast")
@@ -395,7 +398,7 @@ def test_composed_frame_matches_reference_k_plus_3_passes():
         assert_fast_close(fast["depth"].permute(1, 2, 0).cpu().numpy(), ref["depth"], "fast depth", DEPTH_RTOL, rel=True)
         assert_fast_close(fast["seg_color"].permute(1, 2, 0).cpu().numpy(), ref["seg_float"], "fast seg", RGB_TOL)
         for name in ("visible", "silhouette"):
-            assert int((fast[name] != out[name]).sum()) <= 10, name
+            assert int((fast[name] != out[name]).sum()) <= 4 * K, name
         assert int((fast["sem_seg"].int() - out["sem_seg"].int()).abs().max()) <= 1
 
 
