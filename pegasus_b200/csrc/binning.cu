@@ -130,7 +130,8 @@ __device__ __forceinline__ uint32_t emit_row(const EmitWarpSmem& ws, uint32_t t,
 //   grp_loc[group]     = stored pairs of the CTA's groups before this one;
 //   cta_pairs[cta]     = stored pairs of the CTA  -> pair_scan_kernel -> cta_base[cta].
 template <bool KEEP_ALL>
-__global__ void __launch_bounds__(EMIT_THREADS)
+// bounded for 6 CTAs per SM: count + emit 0.208 vs 0.219 ms unbounded (46 / 29 registers), 0.214 at 8
+__global__ void __launch_bounds__(EMIT_THREADS, 6)
 count_kernel(const uint32_t* __restrict__ perm, ushort4* __restrict__ srect,
              const GeomRec* __restrict__ recs, uint32_t P, int W, int H, int gx, int gy,
              uint32_t* __restrict__ runs_fix, uint32_t* __restrict__ runs_ovf, uint32_t* __restrict__ ovf_base,
@@ -318,7 +319,8 @@ pair_scan_kernel(const uint32_t* __restrict__ cta_pairs, uint32_t* __restrict__ 
 //       j % 32): coalesced stores, no lane walks a long run alone.
 // Output order = depth order, rows top to bottom, tiles left to right = the reference's order.
 template <bool KEEP_ALL>
-__global__ void __launch_bounds__(EMIT_THREADS)
+// bounded for 6 CTAs per SM: count + emit 0.208 vs 0.219 ms unbounded (46 / 29 registers), 0.214 at 8
+__global__ void __launch_bounds__(EMIT_THREADS, 6)
 emit_kernel(const uint32_t* __restrict__ perm, const uint32_t* __restrict__ cta_base, const uint32_t* __restrict__ grp_loc,
             const uint32_t* __restrict__ rnd_off,
             const uint32_t* __restrict__ runs_fix, const uint32_t* __restrict__ runs_ovf,

@@ -115,8 +115,10 @@ __global__ void __launch_bounds__(256) scan_rows_kernel(uint32_t* __restrict__ h
     row[tid] = base + x - v;
 }
 
-template <bool IOTA, bool WRITE_KEYS>
-__global__ void __launch_bounds__(SORT_THREADS, 4)
+// MINB: CTAs per SM the registers are bounded for.  The tile sort (20 M items, issue-bound) wants 4 (64 registers;
+// 3: 0.309 vs 0.282 ms); the depth sort (1.8 M items, one wave, latency-bound) 3 (85 registers, no spills: 0.105 vs 0.116 ms).
+template <bool IOTA, bool WRITE_KEYS, int MINB>
+__global__ void __launch_bounds__(SORT_THREADS, MINB)
 onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, uint32_t* __restrict__ keys_out,
                      const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ vals_out,
                      const uint32_t* __restrict__ n_ptr, uint32_t n_imm, int begin_bit, int num_bits,
@@ -314,14 +316,16 @@ int launch_onesweep_pass(bool iota, bool write_keys, const uint32_t* keys_in, ui
                          uint32_t n_env, uint32_t* tile_obj_count, cudaStream_t stream) {
     if (max_tiles == 0) return PG_OK;
     dim3 grid(max_tiles), block(SORT_THREADS);
-    if (iota && write_keys)
-        onesweep_pass_kernel<true, true><<<grid, block, 0, stream>>>(keys_in, keys_out, vals_in, vals_out, n_ptr, n_imm, begin_bit, num_bits, bin_base, status, ticket, ranges_raw, n_env, tile_obj_count);
-    else if (!iota && write_keys)
-        onesweep_pass_kernel<false, true><<<grid, block, 0, stream>>>(keys_in, keys_out, vals_in, vals_out, n_ptr, n_imm, begin_bit, num_bits, bin_base, status, ticket, ranges_raw, n_env, tile_obj_count);
-    else if (!iota && !write_keys)
-        onesweep_pass_kernel<false, false><<<grid, block, 0, stream>>>(keys_in, keys_out, vals_in, vals_out, n_ptr, n_imm, begin_bit, num_bits, bin_base, status, ticket, ranges_raw, n_env, tile_obj_count);
-    else
-        onesweep_pass_kernel<true, false><<<grid, block, 0, stream>>>(keys_in, keys_out, vals_in, vals_out, n_ptr, n_imm, begin_bit, num_bits, bin_base, status, ticket, ranges_raw, n_env, tile_obj_count);
+    // small grids (at most two waves of 3 CTAs per SM on 148 SMs: the depth sort of a few million Gaussians) are
+    // latency-bound and run the spill-free 3-CTA build
+    const bool depth_pass = write_keys && !ranges_raw && max_tiles <= 148u * 3u * 2u;
+#define PG_ONESWEEP(I, W, M) onesweep_pass_kernel<I, W, M><<<grid, block, 0, stream>>>(keys_in, keys_out, vals_in, vals_out, n_ptr, n_imm, begin_bit, num_bits, bin_base, status, ticket, ranges_raw, n_env, tile_obj_count)
+    if (iota && write_keys) PG_ONESWEEP(true, true, 4);
+    else if (!iota && write_keys && depth_pass) PG_ONESWEEP(false, true, 3);
+    else if (!iota && write_keys) PG_ONESWEEP(false, true, 4);
+    else if (!iota && !write_keys) PG_ONESWEEP(false, false, 4);
+    else PG_ONESWEEP(true, false, 4);
+#undef PG_ONESWEEP
     PG_CUDA_CHECK(cudaGetLastError());
     count_launch(1);
     return PG_OK;
