@@ -64,7 +64,7 @@ namespace pg {
 // the standalone transmittance of object k at the two pixels of each lane (slot = warp * 32 + lane).
 template <bool MASKS, bool STATS, int COMP_STAGES, int ILP, int MINB>
 __global__ void __launch_bounds__(COMP2_THREADS, MINB) composite2_kernel(const CompArgs a) {
-    using CompSmem = CompSmemT<COMP_STAGES>;
+    using CompSmem = CompSmemT<COMP_STAGES, !MASKS>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     CompSmem& sm = *reinterpret_cast<CompSmem*>(smem_raw);
     float4* sm_eff = reinterpret_cast<float4*>(smem_raw + sizeof(CompSmem));
@@ -374,7 +374,7 @@ static int comp_smem_pad() {
 
 template <bool MASKS, bool STATS, int STAGES, int ILP, int MINB>
 static int launch_two(const CompArgs& a, dim3 grid, cudaStream_t stream) {
-    const int smem = (int)sizeof(CompSmemT<STAGES>) + comp_smem_pad() +
+    const int smem = (int)sizeof(CompSmemT<STAGES, !MASKS>) + comp_smem_pad() +
                      (MASKS ? (int)(PG_MAX_OBJECTS * sizeof(float4)) + a.num_objects * 256 * (int)sizeof(float) : 0);
     // residency is bounded by shared memory (~39 KB per CTA): ask for the largest carve-out
     PG_CUDA_CHECK(ensure_dynamic_smem(composite2_kernel<MASKS, STATS, STAGES, ILP, MINB>, smem, true));

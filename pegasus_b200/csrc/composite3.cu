@@ -82,7 +82,7 @@ constexpr int QSTRIDE = COMP_BATCH + 16;  // bytes of one warp's hit queue (entr
 // transmittance of object k at the two pixels of each lane (slot = warp * 32 + lane).
 template <bool MASKS, bool NCONTRIB, bool FAST, int COMP_STAGES, int MINB>
 __global__ void __launch_bounds__(COMP2_THREADS, MINB) composite3_kernel(const CompArgs a) {
-    using CompSmem = CompSmemT<COMP_STAGES>;
+    using CompSmem = CompSmemT<COMP_STAGES, !MASKS>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     CompSmem& sm = *reinterpret_cast<CompSmem*>(smem_raw);
     constexpr int kQueueOff = (int)((sizeof(CompSmem) + 15) / 16 * 16);
@@ -463,7 +463,7 @@ __global__ void __launch_bounds__(COMP2_THREADS, MINB) composite3_kernel(const C
 
 template <bool MASKS, bool NCONTRIB, bool FAST, int STAGES, int MINB>
 static int launch_three(const CompArgs& a, dim3 grid, cudaStream_t stream) {
-    const int smem = (int)((sizeof(CompSmemT<STAGES>) + 15) / 16 * 16) + COMP2_CW * QSTRIDE +
+    const int smem = (int)((sizeof(CompSmemT<STAGES, !MASKS>) + 15) / 16 * 16) + COMP2_CW * QSTRIDE +
                      (MASKS ? (int)((COMP2_CW + 1) * PG_MAX_OBJECTS * sizeof(float4)) + a.num_objects * 256 * (int)sizeof(float) : 0);
     PG_CUDA_CHECK(ensure_dynamic_smem(composite3_kernel<MASKS, NCONTRIB, FAST, STAGES, MINB>, smem, true));
     composite3_kernel<MASKS, NCONTRIB, FAST, STAGES, MINB><<<grid, COMP2_THREADS, smem, stream>>>(a);
@@ -491,8 +491,8 @@ int launch_composite3(const CompArgs& a, dim3 grid, bool masks, bool fast, int v
         return nc ? launch_three<false, true, false, 4, MBP>(a, grid, stream) : launch_three<false, false, false, 4, MBP>(a, grid, stream);
     }
     // the tighter register bound only pays when shared memory lets the extra CTA in (227 KB per SM, 1 KB per CTA
-    // reserved by the runtime: up to 9 objects); frames with more objects keep the spill-free 4-CTA build
-    const int smem = (int)((sizeof(CompSmemT<4>) + 15) / 16 * 16) + COMP2_CW * QSTRIDE +
+    // reserved by the runtime: up to 13 objects); frames with more objects keep the spill-free 4-CTA build
+    const int smem = (int)((sizeof(CompSmemT<4, false>) + 15) / 16 * 16) + COMP2_CW * QSTRIDE +
                      (int)((COMP2_CW + 1) * PG_MAX_OBJECTS * sizeof(float4)) + a.num_objects * 256 * (int)sizeof(float);
     if (MB > 4 && MB * (smem + 1024) > 227 * 1024)
         return fast ? launch_three<true, false, true, 4, 4>(a, grid, stream) : launch_three<true, false, false, 4, 4>(a, grid, stream);

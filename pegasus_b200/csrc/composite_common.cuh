@@ -119,13 +119,15 @@ constexpr int COMP_IDCHUNK = 256;
 constexpr int COMP_PEND = 512;
 static_assert(COMP_BATCH - 1 + COMP_IDCHUNK <= COMP_PEND, "pending ring too small");
 
-template <int COMP_STAGES>
+// POS: the 1-based list position of every staged entry travels with it (n_contrib of the plain pass); the fused
+// frame has no use for it and its CTAs are 4 KB smaller, which is what lets a fifth CTA per SM in up to 13 objects.
+template <int COMP_STAGES, bool POS>
 struct CompSmemT {
     GeomRec rec[COMP_STAGES][COMP_BATCH];
-    uint32_t pos[COMP_STAGES][COMP_BATCH];  // 1-based list position of each staged entry (n_contrib)
-    uint32_t ids[2][COMP_IDCHUNK];          // producer: raw id chunks, TMA double buffer
+    uint32_t pos[POS ? COMP_STAGES : 1][POS ? COMP_BATCH : 1];  // 1-based list position of each staged entry
+    alignas(16) uint32_t ids[2][COMP_IDCHUNK];  // producer: raw id chunks, TMA double buffer (16-byte destinations)
     uint32_t pend[COMP_PEND];               // producer: compacted ids not yet staged (circular)
-    uint32_t pendpos[COMP_PEND];
+    uint32_t pendpos[POS ? COMP_PEND : 1];
     unsigned long long full[COMP_STAGES];
     unsigned long long empty[COMP_STAGES];
     unsigned long long idbar[2];
@@ -175,7 +177,7 @@ __device__ __forceinline__ float exp_sel(float x) {
 // compaction, gathers each surviving 48-byte record into the COMP_STAGES-deep shared-memory ring with
 // cp.async whose completion arrives on the stage's `full` mbarrier.  NCW = number of consumer warps.
 template <bool MASKS, int COMP_STAGES, int NCW, int WAITNS>
-__device__ __forceinline__ void composite_producer(const CompArgs& a, CompSmemT<COMP_STAGES>& sm, const int tile,
+__device__ __forceinline__ void composite_producer(const CompArgs& a, CompSmemT<COMP_STAGES, !MASKS>& sm, const int tile,
                                                    const uint2 range, const int n, const int lane, const uint32_t lt) {
     // =========================== PRODUCER ===========================
     int obj_left = 0;  // un-culled object entries not yet compacted
@@ -222,7 +224,7 @@ __device__ __forceinline__ void composite_producer(const CompArgs& a, CompSmemT<
                 if (keep) {
                     const int slot = (head + fill + __popc(bal & lt)) & (COMP_PEND - 1);
                     sm.pend[slot] = v;
-                    sm.pendpos[slot] = gi - range.x + 1u;
+                    if (!MASKS) sm.pendpos[slot] = gi - range.x + 1u;
                 }
                 fill += __popc(bal);
                 if (MASKS) obj_left -= __popc(__ballot_sync(0xffffffffu, is_obj));
