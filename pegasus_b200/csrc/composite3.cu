@@ -473,8 +473,8 @@ static int launch_three(const CompArgs& a, dim3 grid, cudaStream_t stream) {
 // masks: fused K+3 passes; fast: PG_NUMERICS_FAST
 // CTAs per SM the register allocation is bounded for.  With masks the kernel wants 87 registers; bounded for 5 CTAs
 // per SM (72 registers, 4 of them spilled) it runs 0.899 instead of 0.948 ms (fast; exact 1.008 vs 1.057): 20 instead
-// of 16 consumer warps per SM hide more of the dependent chains.  6 CTAs (64 registers, 12 spilled; shared memory
-// allows 5) 0.987, 7 CTAs 1.173; 6 CTAs with a 3-stage ring so that they fit 0.971; __maxnreg__(80), spill-free, 0.923.  The plain kernel needs 51-64 registers: unaffected.
+// of 16 consumer warps per SM hide more of the dependent chains.  6 CTAs (64 registers, 12 spilled) 0.956,
+// 7 CTAs 1.173; __maxnreg__(80), spill-free, 0.923.  The plain kernel needs 51-64 registers: unaffected.
 #ifndef PG_COMP3_MINB
 #define PG_COMP3_MINB 5
 #endif
