@@ -24,7 +24,6 @@ update_object_pose never refreshes — in dynamic mode the GT pose is the FIRST 
 from __future__ import annotations
 
 import json
-import os
 import threading
 from dataclasses import dataclass, field
 from pathlib import Path

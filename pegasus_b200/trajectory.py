@@ -12,7 +12,7 @@ Pose schedule — static_object_pose / dynamic_object_pose / update_object_pose 
 from __future__ import annotations
 
 import math
-from typing import Dict, Iterable, List, Mapping, Optional, Sequence, Tuple
+from typing import Dict, Iterable, List, Mapping, Sequence, Tuple
 
 import numpy as np
 

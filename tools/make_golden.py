@@ -25,7 +25,6 @@ import json
 import math
 import os
 import sys
-import types
 
 import numpy as np
 import torch
