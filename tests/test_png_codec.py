@@ -65,3 +65,29 @@ def test_long_runs_are_cut_at_258():
     toks = pm.tokenize_row(f)
     assert toks == [("lit", 0), ("len", 258), ("len", 258), ("len", 258), ("lit", 0), ("lit", 0)]
     assert [pc.length_symbol(v)[0] for v in (3, 10, 11, 12, 257, 258)] == [257, 264, 265, 265, 284, 285]
+
+
+def test_random_run_structures_round_trip():
+    """Rows made of random runs (lengths around the 3 / 258 / 259 boundaries) over every kind and odd widths."""
+    rng = np.random.default_rng(123)
+    lens = np.array([1, 2, 3, 4, 5, 17, 257, 258, 259, 260, 516, 517, 600])
+    for kind, W in ((pc.KIND_MASK8, 1031), (pc.KIND_RGB8, 347), (pc.KIND_GRAY16, 521)):
+        rows = []
+        for _ in range(6):
+            vals, out = rng.integers(0, 4, 64), []
+            for v in vals:
+                out += [int(v)] * int(rng.choice(lens))
+            rows.append(out[:W] + [0] * max(0, W - len(out)))
+        a = np.asarray(rows)
+        if kind == pc.KIND_RGB8:
+            img = np.repeat(a[..., None], 3, axis=2).astype(np.uint8) * 60
+        elif kind == pc.KIND_GRAY16:
+            img = (a * 21845).astype(np.uint16)
+        else:
+            img = (a > 1).astype(np.uint8)
+        table = pc.build_table(pm.token_hist(kind, [img]))
+        z = pm.encode(kind, img, table)
+        assert zlib.decompress(z) == pm.scanlines(kind, img).tobytes()
+        got = pm.decode_png(kind, pc.png_file(kind, W, img.shape[0], z))
+        want = img if kind != pc.KIND_MASK8 else (img != 0).astype(np.uint8) * 255
+        assert np.array_equal(got, want)
