@@ -172,3 +172,41 @@ def test_strided_source_rows_and_4k_width():
     out = enc.encode_unbounded(st)
     assert zlib.decompress(out["rgb"]) == pm.scanlines(pc.KIND_RGB8, big[:, 32:32 + W]).tobytes()
     assert zlib.decompress(out["depth"]) == pm.scanlines(pc.KIND_GRAY16, d16[:, 1:1 + W]).tobytes()
+
+
+def test_run_lengths_around_chunk_and_thread_boundaries():
+    """Rows made of random runs with lengths around 3 / 258 / 259 / 516 (match chunking) that start and end anywhere
+    relative to the threads' parts of a row: the kernel's streams must equal the restated tokenizer's bit for bit."""
+    dev = torch.device("cuda", 0)
+    rng = np.random.default_rng(321)
+    lens = np.array([1, 2, 3, 4, 5, 17, 63, 64, 65, 257, 258, 259, 260, 516, 517, 600, 1500])
+    imgs = []
+    W, H = 2047, 12
+    for kind, name in ((pc.KIND_MASK8, "mask"), (pc.KIND_RGB8, "rgb"), (pc.KIND_GRAY16, "depth")):
+        rows = []
+        for _ in range(H):
+            out = []
+            while len(out) < W:
+                out += [int(rng.integers(0, 4))] * int(rng.choice(lens))
+            rows.append(out[:W])
+        a = np.asarray(rows)
+        if kind == pc.KIND_RGB8:
+            img = np.repeat(a[..., None], 3, axis=2).astype(np.uint8) * 60
+        elif kind == pc.KIND_GRAY16:
+            img = (a * 21845).astype(np.uint16)
+        else:
+            img = (a > 1).astype(np.uint8)
+        imgs.append((name, kind, name, img))
+    tables = PngTables(dev, ["mask", "rgb", "depth"])
+    enc = FramePngEncoder(tables, W, H, [(n, k, g, to_dev(k, a, dev)) for n, k, g, a in imgs])
+    st = torch.cuda.current_stream(dev)
+    enc.accumulate_hist(st)
+    h = tables.hist.cpu().numpy().astype(np.int64)
+    for n, k, g, a in imgs:
+        assert np.array_equal(h[tables.index[g]], pm.token_hist(k, [a])), n
+    tables.rebuild_from_hist()
+    host_tables = tables.dev.cpu().numpy().view(np.uint32)
+    out = enc.encode_unbounded(st)
+    for n, k, g, a in imgs:
+        assert out[n] == pm.encode(k, a, host_tables[tables.index[g]]), n
+        assert zlib.decompress(out[n]) == pm.scanlines(k, a).tobytes(), n
